@@ -1,0 +1,147 @@
+/*
+ * pykmer_b200.h -- C ABI of libpykmer_b200.so, the B200 (sm_100a) replacement for
+ * the two data-parallel hot paths of sauloal/pykmer.
+ *
+ * The reference is pure Python and exposes no FFI; the drop-in boundary is its
+ * two CLIs and four file formats.  This header is the seam
+ * a maintainer binds with ctypes at the reference's two natural function seams;
+ * INTEGRATION.md shows the stub.  Each entry point cites the reference code it
+ * replaces (file:line into sauloal/pykmer).
+ *
+ * Conventions: plain C symbols; every function returns PK_OK (0) or a negative
+ * PK_ERR_* and leaves a message for pk_last_error() (thread-local); nothing is
+ * thrown or allocated across the ABI except through the create/alloc calls
+ * below; `*_dev` pointers are device pointers on the handle's / current device,
+ * `*_host` pointers are host pointers; pk_stream is a cudaStream_t (NULL = the
+ * legacy default stream).  A pk_indexer belongs to one GPU and is not
+ * thread-safe; independent handles are independent.
+ */
+#ifndef PYKMER_B200_H
+#define PYKMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_OK          0
+#define PK_ERR_ARG    -1   /* bad argument (the reference raises AssertionError/ValueError) */
+#define PK_ERR_CUDA   -2   /* CUDA runtime failure, text in pk_last_error() */
+#define PK_ERR_STATE  -3   /* call out of order (e.g. feed after finalize) */
+#define PK_ERR_NOMEM  -4   /* device or pinned-host allocation failed */
+
+#define PK_ABI_VERSION 1
+
+typedef void *pk_stream;
+typedef struct pk_indexer pk_indexer;
+
+/* ------------------------------------------------------------------ general */
+int         pk_abi_version(void);
+const char *pk_last_error(void);
+int         pk_device_count(int *count);
+/* name_len bytes of name are filled (NUL-terminated); any out pointer may be NULL */
+int         pk_device_info(int device, char *name, size_t name_len, int *sm_count,
+                           size_t *total_mem_bytes, int *cc_major, int *cc_minor);
+/* pinned (page-locked) host memory for the streaming copies */
+int         pk_host_alloc(void **ptr, size_t bytes);
+int         pk_host_free(void *ptr);
+
+/* ------------------------------------------------------------------ indexer
+ * Replaces gen_kmers + the consumer loop of create_fasta_index + process_kmers
+ * (indexer.py:130-160, 340-384, 162-297) and Header.update_stats
+ * (tools.py:246-263).
+ *
+ * The sequence is fed as a cleaned byte STREAM: the host has applied the
+ * reference's text rules (indexer.py:55-95) and joined the records with one
+ * byte outside ACGTacgt.  Any such byte voids the K windows containing it
+ * (indexer.py:144), so the separator also keeps windows inside records
+ * (indexer.py:133-141).  Feeds concatenate: the last K-1 bases carry over.
+ *
+ * The handle owns table[range_hi - range_lo] (uint8, saturating at 255,
+ * indexer.py:239,262) covering canonical k-mer values [range_lo, range_hi);
+ * windows whose canonical value falls outside are ignored.  range 0..4^K is the
+ * whole .kin; a sub-range is one shard of the k-mer-axis partition.
+ */
+#define PK_MODE_AUTO      0
+#define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
+#define PK_MODE_PARTITION 2   /* bucket k-mers by table window, count window by window on chip */
+
+int pk_indexer_create(pk_indexer **out, int kmer_len, int device,
+                      uint64_t range_lo, uint64_t range_hi, int mode);
+int pk_indexer_destroy(pk_indexer *ix);
+/* zero the table, counters, carry and stream offset; keeps allocations */
+int pk_indexer_reset(pk_indexer *ix, pk_stream stream);
+
+/* Optional record table (stream offsets of each record's first byte, ascending).
+ * When set, pk_indexer_record_flags reports which records produced >= 1 counted
+ * window -- the rule by which the reference lists `chromosomes`
+ * (indexer.py:349-351).  May be called again between feeds with a LONGER table
+ * (records are discovered as the file is parsed); entries already registered
+ * must not change. */
+int pk_indexer_set_records(pk_indexer *ix, const uint64_t *rec_starts_host, size_t nrec);
+
+/* seq_dev must be 16-byte aligned.  Asynchronous on `stream`. */
+int pk_indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_stream stream);
+/* Streams seq_host through double-buffered cudaMemcpyAsync on a side stream,
+ * overlapping copy and counting.  Pinned memory (pk_host_alloc) gives full PCIe
+ * speed.  Returns after the last chunk is enqueued; the buffer must stay
+ * untouched until pk_indexer_sync / pk_indexer_finalize. */
+int pk_indexer_feed_host(pk_indexer *ix, const uint8_t *seq_host, size_t n);
+int pk_indexer_sync(pk_indexer *ix);
+
+/* Finish counting and compute the statistics of tools.py:246-263 over the
+ * handle's range.  hist_host[i] = #{table == i+1}, i in 0..254.
+ * stats_host = {num_kmers (indexer.py:342), vals_sum, vals_count, vals_min,
+ * vals_max}.  Synchronises.  Feeding after finalize is allowed (statistics are
+ * recomputed by the next finalize). */
+int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]);
+int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec);
+
+/* Device view of the table (valid after finalize), and a copy to host memory. */
+int pk_indexer_table_device(pk_indexer *ix, const uint8_t **table_dev, size_t *bytes);
+int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t offset, size_t bytes);
+/* launches of this library's kernels issued through the handle so far */
+int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches);
+
+/* Header.update_stats (tools.py:246-263) over any device table.
+ * stats_host = {vals_sum, vals_count, vals_min, vals_max}.  Synchronises `stream`. */
+int pk_table_stats_device(const uint8_t *table_dev, size_t n, int64_t hist_host[255],
+                          uint64_t stats_host[4], pk_stream stream);
+
+/* ------------------------------------------------------------------ merger
+ * Replaces Header.calculate_distance (tools.py:439-493) and the pair loop of
+ * merge (merger.py:136-176): valid = (min <= count <= max) (tools.py:473-474);
+ * matrix[k][l] = (Total_k, Total_l, Shared_kl) = (G[k][k], G[l][l], G[k][l]) with
+ * G = B * B^T over the 0/1 presence rows B.
+ */
+/* bit (i & 31) of bits_dev[i >> 5] = (min <= table_dev[i] <= max); n need not be
+ * a multiple of 32 (tail bits are 0); table_dev 16-byte aligned. */
+int pk_threshold_pack_device(const uint8_t *table_dev, size_t n, int min_count, int max_count,
+                             uint32_t *bits_dev, pk_stream stream);
+/* gram_dev[k * nsamples + l] (+)= popcount(bits[k] & bits[l]) over `words` 32-bit
+ * words; sample k starts at bits_dev + k * stride_words.  accumulate = 0
+ * overwrites gram_dev, 1 adds to it (k-mer-axis slabs / shards). */
+int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
+                   int64_t *gram_dev, int accumulate, pk_stream stream);
+/* One pair, straight from two device tables: out_host = {Total_s, Total_o, Shared}
+ * -- the return value of Header.calculate_distance (tools.py:493).  Synchronises. */
+int pk_pair_counts_device(const uint8_t *s_dev, const uint8_t *o_dev, size_t n, int min_count,
+                          int max_count, uint64_t out_host[3], pk_stream stream);
+/* Whole merge from host tables: streams every table once through pinned-copy +
+ * threshold_pack, then one Gram pass.  matrix_host is uint64[N][N][3]
+ * (merger.py:136; the diagonal, which the reference leaves uninitialised, is
+ * (T_k, T_k, T_k)). */
+int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t n, int min_count,
+                  int max_count, int device, uint64_t *matrix_host);
+
+/* Deterministic synthetic count table (benchmark input):
+ * entries [lo, hi) of sample `sample`, bit-identical to pykmer_b200/synth.py. */
+int pk_synth_table_device(uint8_t *dst_dev, int sample, uint64_t lo, uint64_t hi,
+                          pk_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYKMER_B200_H */

@@ -1,0 +1,49 @@
+// common.h -- error plumbing shared by the translation units of libpykmer_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pykmer_b200.h"
+
+#define PK_API extern "C" __attribute__((visibility("default")))
+
+int pk_set_error(int code, const char *fmt, ...);
+
+#define PK_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return pk_set_error(e__ == cudaErrorMemoryAllocation ? PK_ERR_NOMEM         \
+                                                                 : PK_ERR_CUDA,         \
+                                "%s:%d %s -> %s", __FILE__, __LINE__, #call,            \
+                                cudaGetErrorString(e__));                               \
+    } while (0)
+
+#define PK_REQUIRE(cond, ...)                                                           \
+    do {                                                                                \
+        if (!(cond)) return pk_set_error(PK_ERR_ARG, __VA_ARGS__);                      \
+    } while (0)
+
+static inline int pk_sm_count(int device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0)
+        n = 148;
+    return n;
+}
+
+// restores the caller's current device on scope exit
+struct pk_device_guard {
+    int prev = -1;
+    bool ok = true;
+    explicit pk_device_guard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+        want = device;
+    }
+    ~pk_device_guard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    int want = -1;
+};

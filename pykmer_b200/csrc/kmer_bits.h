@@ -1,0 +1,114 @@
+// kmer_bits.h -- the bit algebra of the indexer scan, shared by the CUDA kernels
+// and by a host-side unit test (tests/host/test_kmer_bits.cpp), so that the index
+// arithmetic can be checked on a machine without a GPU.
+//
+// Replaces, from the reference (sauloal/pykmer): the CONV lookup
+// (indexer.py:36-41) and the per-window arithmetic of gen_kmers
+// (indexer.py:141-150) followed by pos = min(fwd, rev) (indexer.py:341).
+//
+// Layout.  The base stream is cut into GROUPS of 16 bases.  A group is encoded as
+//   codes : 32 bits, base 0 of the group in bits 31:30 ... base 15 in bits 1:0
+//   vmask : 16 bits, bit (15 - j) set iff base j is one of ACGTacgt
+// so "earlier base = more significant digit", which is exactly the reference's
+// first-base-most-significant encoding of a window (indexer.py:131,149): a window
+// is a contiguous slice of the concatenation prev2:prev1:cur of three groups.
+// The reverse complement is a slice of the digit-reversed, complemented
+// concatenation rcw(cur):rcw(prev1):rcw(prev2).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PK_HD __host__ __device__ __forceinline__
+#else
+#define PK_HD inline
+#endif
+
+#define PK_GROUP 16
+
+// CONV (indexer.py:36-41): bits 1:0 = code (A0 C1 G2 T3), bit 2 = valid.
+PK_HD uint32_t pk_lut_entry(uint32_t c) {
+    switch (c) {
+        case 'A': case 'a': return 4u | 0u;
+        case 'C': case 'c': return 4u | 1u;
+        case 'G': case 'g': return 4u | 2u;
+        case 'T': case 't': return 4u | 3u;
+        default: return 0u;
+    }
+}
+
+// Encode 16 bytes (w[0] holds bytes 0..3, little endian) through a 256-entry LUT.
+template <typename LutT>
+PK_HD void pk_encode16(const uint32_t w[4], const LutT* lut, uint32_t& codes, uint32_t& vmask) {
+    uint32_t c = 0, v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            uint32_t e = lut[(w[i] >> (8 * b)) & 0xFFu];
+            c = (c << 2) | (e & 3u);
+            v = (v << 1) | (e >> 2);
+        }
+    }
+    codes = c;
+    vmask = v;
+}
+
+PK_HD uint32_t pk_brev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+
+// Reverse the 16 two-bit digits of a group and complement them (digit d -> 3 - d).
+PK_HD uint32_t pk_rcw(uint32_t x) {
+    x = pk_brev32(x);                                            // digits reversed, bits in a digit swapped
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);     // swap back inside each digit
+    return ~x;
+}
+
+// vcat: validity bits of prev2:prev1:cur (bit 15-j = base j of cur, +16 per group
+// further back).  Returns W with bit p = AND(vcat[p .. p+K-1]); the window that
+// ENDS at base j of cur is valid iff bit (15 - j) of W is set (indexer.py:144).
+PK_HD uint64_t pk_valid_windows(uint64_t vcat, int K) {
+    uint64_t W = vcat;
+    int run = 1;
+    while (run * 2 <= K) { W &= W >> run; run *= 2; }
+    if (run < K) W &= W >> (K - run);
+    return W;
+}
+
+PK_HD uint64_t pk_kmer_mask(int K) { return K >= 32 ? ~0ull : ((1ull << (2 * K)) - 1ull); }
+
+// Forward value of the window ending at base j of cur: digits j-K+1 .. j, first
+// base most significant (indexer.py:149).  pc2 is only needed when K > 17.
+PK_HD uint64_t pk_fwd_at(uint32_t pc2, uint32_t pc1, uint32_t cc, int j, int K) {
+    const int s = 2 * (15 - j);                                  // 0..30
+    uint64_t lo = (((uint64_t)pc1 << 32) | cc) >> s;
+    if (s) lo |= (uint64_t)pc2 << (64 - s);
+    return lo & pk_kmer_mask(K);
+}
+
+// Reverse-complement value of the same window (indexer.py:150): a slice of
+// r0:r1:r2 = rcw(cur):rcw(prev1):rcw(prev2) starting at bit t = 66 + 2j - 2K.
+PK_HD uint64_t pk_rc_at(uint32_t r2, uint32_t r1, uint32_t r0, int j, int K) {
+    const int t = 66 + 2 * j - 2 * K;                            // >= 4 for K <= 31
+    uint64_t v;
+    if (t >= 64)      v = (uint64_t)r0 >> (t - 64);
+    else if (t >= 32) v = (((uint64_t)r0 << 32) | r1) >> (t - 32);
+    else              v = ((((uint64_t)r1 << 32) | r2) >> t) | ((uint64_t)r0 << (64 - t));
+    return v & pk_kmer_mask(K);
+}
+
+// 32-bit fast forms for K <= 16 (one halo group).
+PK_HD uint32_t pk_fwd32_at(uint64_t cat /* pc1:cc */, int j, uint32_t mask) {
+    return (uint32_t)(cat >> (2 * (15 - j))) & mask;
+}
+PK_HD uint32_t pk_rc32_at(uint64_t rcat /* r0:r1 */, int j, int K, uint32_t mask) {
+    return (uint32_t)(rcat >> (34 + 2 * j - 2 * K)) & mask;      // 2 <= shift <= 62 for K <= 16
+}

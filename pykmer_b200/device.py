@@ -1,0 +1,219 @@
+"""Thin Python layer over the C ABI: PyTorch owns the buffers (pinned host and
+device tensors, streams), libpykmer_b200.so does the work.  Nothing here computes;
+if the CUDA library or a GPU is missing the calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+lib = nat.lib
+
+
+def _stream_ptr(stream: Optional["torch.cuda.Stream"] = None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+def pinned_empty(nbytes: int) -> torch.Tensor:
+    return torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
+
+
+def to_device_u8(arr, device: Optional[int] = None) -> torch.Tensor:
+    """uint8 numpy array / tensor -> contiguous CUDA tensor (torch does the copy)."""
+    if isinstance(arr, torch.Tensor):
+        t = arr
+    else:
+        a = np.ascontiguousarray(arr, dtype=np.uint8)
+        t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    return t.to(dev, non_blocking=False).contiguous()
+
+
+class Indexer:
+    """One pk_indexer handle (one GPU, one k-mer range)."""
+
+    def __init__(self, kmer_len: int, device: int = 0, range_lo: int = 0,
+                 range_hi: Optional[int] = None, mode: int = nat.PK_MODE_AUTO):
+        self.kmer_len = kmer_len
+        self.device = device
+        self.range_lo = range_lo
+        self.range_hi = 4 ** kmer_len if range_hi is None else range_hi
+        self._h = ctypes.c_void_p()
+        nat.check(lib.pk_indexer_create(ctypes.byref(self._h), kmer_len, device, range_lo,
+                                        self.range_hi, mode))
+        self._nrec = 0
+        self._keep: List[object] = []        # host buffers that async feeds still read
+
+    def close(self) -> None:
+        if self._h:
+            lib.pk_indexer_destroy(self._h)
+            self._h = ctypes.c_void_p()
+        self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self, stream=None) -> None:
+        nat.check(lib.pk_indexer_reset(self._h, _stream_ptr(stream)))
+
+    def set_records(self, starts) -> None:
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        nat.check(lib.pk_indexer_set_records(self._h, starts.ctypes.data, starts.size))
+        self._nrec = int(starts.size)
+
+    def feed_device(self, seq: torch.Tensor, stream=None) -> None:
+        assert seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()
+        nat.check(lib.pk_indexer_feed_device(self._h, seq.data_ptr(), seq.numel(),
+                                             _stream_ptr(stream)))
+
+    def feed_host(self, seq) -> None:
+        """seq: uint8 numpy array or (ideally pinned) CPU tensor.  Asynchronous."""
+        if isinstance(seq, torch.Tensor):
+            assert seq.dtype == torch.uint8 and seq.is_contiguous() and not seq.is_cuda
+            p, n = seq.data_ptr(), seq.numel()
+        else:
+            seq = np.ascontiguousarray(seq, dtype=np.uint8)
+            p, n = seq.ctypes.data, seq.size
+        self._keep.append(seq)
+        nat.check(lib.pk_indexer_feed_host(self._h, p, n))
+
+    def sync(self) -> None:
+        nat.check(lib.pk_indexer_sync(self._h))
+        self._keep.clear()
+
+    def finalize(self) -> Tuple[List[int], dict]:
+        hist = np.zeros(255, dtype=np.int64)
+        st = np.zeros(5, dtype=np.uint64)
+        nat.check(lib.pk_indexer_finalize(self._h, hist.ctypes.data, st.ctypes.data))
+        self._keep.clear()
+        return hist.tolist(), {"num_kmers": int(st[0]), "vals_sum": int(st[1]),
+                               "vals_count": int(st[2]), "vals_min": int(st[3]),
+                               "vals_max": int(st[4])}
+
+    def record_flags(self) -> np.ndarray:
+        flags = np.zeros(max(self._nrec, 1), dtype=np.uint8)
+        nat.check(lib.pk_indexer_record_flags(self._h, flags.ctypes.data, self._nrec))
+        return flags[:self._nrec]
+
+    def table_ptr(self) -> Tuple[int, int]:
+        p, n = ctypes.c_void_p(), ctypes.c_size_t(0)
+        nat.check(lib.pk_indexer_table_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return int(p.value), int(n.value)
+
+    def table_to_host(self, dst=None, offset: int = 0, nbytes: Optional[int] = None):
+        """Copy table[offset:offset+nbytes] into dst (numpy / CPU tensor; pinned is fastest)."""
+        total = self.range_hi - self.range_lo
+        nbytes = total - offset if nbytes is None else nbytes
+        if dst is None:
+            dst = pinned_empty(nbytes)
+        p = dst.data_ptr() if isinstance(dst, torch.Tensor) else dst.ctypes.data
+        nat.check(lib.pk_indexer_table_to_host(self._h, p, offset, nbytes))
+        return dst
+
+    def launch_count(self) -> int:
+        n = ctypes.c_uint64(0)
+        nat.check(lib.pk_indexer_launch_count(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+
+def table_stats(table, device: Optional[int] = None):
+    """Header.update_stats arithmetic (tools.py:246-263) on the GPU.
+    -> (hist list[255], (vals_sum, vals_count, vals_min, vals_max))"""
+    t = to_device_u8(table, device)
+    hist = np.zeros(255, dtype=np.int64)
+    st = np.zeros(4, dtype=np.uint64)
+    with torch.cuda.device(t.device):
+        nat.check(lib.pk_table_stats_device(t.data_ptr(), t.numel(), hist.ctypes.data,
+                                            st.ctypes.data, _stream_ptr()))
+    return hist.tolist(), tuple(int(v) for v in st)
+
+
+def pair_counts(s, o, min_count: int = 1, max_count: int = 255, device: Optional[int] = None):
+    """Header.calculate_distance arithmetic (tools.py:473-482) on the GPU."""
+    a, b = to_device_u8(s, device), to_device_u8(o, device)
+    assert a.numel() == b.numel()
+    out = np.zeros(3, dtype=np.uint64)
+    with torch.cuda.device(a.device):
+        nat.check(lib.pk_pair_counts_device(a.data_ptr(), b.data_ptr(), a.numel(), min_count,
+                                            max_count, out.ctypes.data, _stream_ptr()))
+    return tuple(int(v) for v in out)
+
+
+def threshold_pack(table: torch.Tensor, min_count: int, max_count: int,
+                   out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+    """uint8 CUDA table -> int32 CUDA bitmask words (bit i&31 of word i>>5)."""
+    assert table.is_cuda and table.dtype == torch.uint8 and table.is_contiguous()
+    n = table.numel()
+    words = (n + 31) // 32
+    if out is None:
+        out = torch.empty(words, dtype=torch.int32, device=table.device)
+    assert out.is_cuda and out.numel() >= words and out.element_size() == 4
+    with torch.cuda.device(table.device):
+        nat.check(lib.pk_threshold_pack_device(table.data_ptr(), n, min_count, max_count,
+                                               out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def gram(bits: torch.Tensor, words: Optional[int] = None, out: Optional[torch.Tensor] = None,
+         accumulate: bool = False, stream=None) -> torch.Tensor:
+    """bits: (N, stride_words) int32 CUDA -> (N, N) int64 CUDA Gram matrix."""
+    assert bits.is_cuda and bits.dim() == 2 and bits.element_size() == 4 and bits.is_contiguous()
+    N, stride = bits.shape
+    words = stride if words is None else words
+    if out is None:
+        out = torch.zeros((N, N), dtype=torch.int64, device=bits.device)
+        accumulate = False
+    with torch.cuda.device(bits.device):
+        nat.check(lib.pk_gram_device(bits.data_ptr(), N, words, stride, out.data_ptr(),
+                                     1 if accumulate else 0, _stream_ptr(stream)))
+    return out
+
+
+def matrix_from_gram(G: np.ndarray) -> np.ndarray:
+    """(N, N, 3) uint64: [k, l] = (G[k,k], G[l,l], G[k,l])  (merger.py:175-176)."""
+    G = np.asarray(G)
+    d = np.diag(G).astype(np.uint64)
+    N = G.shape[0]
+    m = np.empty((N, N, 3), dtype=np.uint64)
+    m[:, :, 0] = d[:, None]
+    m[:, :, 1] = d[None, :]
+    m[:, :, 2] = G.astype(np.uint64)
+    return m
+
+
+def merge_host(tables: Sequence[np.ndarray], min_count: int = 1, max_count: int = 255,
+               device: int = 0) -> np.ndarray:
+    """Whole merge from host tables through pk_merge_host -> (N, N, 3) uint64."""
+    N = len(tables)
+    arrs = [np.ascontiguousarray(t, dtype=np.uint8) for t in tables]
+    n = arrs[0].size
+    assert all(a.size == n for a in arrs)
+    ptrs = (ctypes.c_void_p * N)(*[a.ctypes.data for a in arrs])
+    m = np.zeros((N, N, 3), dtype=np.uint64)
+    nat.check(lib.pk_merge_host(ptrs, N, n, min_count, max_count, device, m.ctypes.data))
+    return m
+
+
+def synth_table(sample: int, lo: int, hi: int, out: Optional[torch.Tensor] = None,
+                device: Optional[int] = None, stream=None) -> torch.Tensor:
+    if out is None:
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        out = torch.empty(hi - lo, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(out.device):
+        nat.check(lib.pk_synth_table_device(out.data_ptr(), sample, lo, hi, _stream_ptr(stream)))
+    return out

@@ -1,0 +1,171 @@
+"""CPU-only checks: host logic, text rules, file formats, and that the C ABI loads
+and exports every symbol include/pykmer_b200.h declares (no compute calls)."""
+import glob
+import gzip
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pykmer_b200 import fasta, synth
+from pykmer_b200.tools import Header, Timer, frag_size_rule, gen_checksum
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_kmer_bits_algebra_on_host(tmp_path):
+    """The exact bit algebra the CUDA scan uses (kmer_bits.h), checked against a
+    literal restatement of indexer.py:141-150 for every odd K <= 31."""
+    exe = str(tmp_path / "test_kmer_bits")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-I", os.path.join(ROOT, "pykmer_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "host", "test_kmer_bits.cpp"), "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.startswith("ok:")
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from pykmer_b200 import _native as nat
+    text = open(os.path.join(ROOT, "include", "pykmer_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(nat.SYMBOLS)
+    for name in declared:
+        assert getattr(nat.lib, name) is not None
+    assert nat.lib.pk_abi_version() == 1
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "inputs", "*"))),
+                         ids=lambda p: os.path.basename(p))
+@pytest.mark.parametrize("chunk", [64 << 20, 4096, 61, 5])
+def test_fasta_reader_matches_reference_text_rules(path, chunk):
+    recs = list(oracle.parse_records(path))
+    want, starts, lengths, names = oracle.records_to_stream(recs)
+    fs = fasta.FastaStream(path, chunk_bytes=chunk)
+    got = fs.read_all()
+    assert fs.names == names and fs.lengths == lengths and fs.starts == starts.tolist()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("text", [
+    b"", b"\n\n", b"ACGT\n", b">only header", b">a\n>b\n>c\nAC\n", b">a\rACGT\rAC\r>b\r\rGG",
+    b">a\r\nAC GT\r\n\tACGT \r\n", b"  >lead\n  ACGT\n", b">x\x0c\nAC\x0bGT\x1c\n",
+    b">caf\xc3\xa9 name  \nACGT\n", b">a\nACGT>notheader\n>b\nTT\n",
+])
+def test_fasta_reader_edge_cases(tmp_path, text):
+    p = str(tmp_path / "e.fa")
+    open(p, "wb").write(text)
+    recs = list(oracle.parse_records(p))
+    want, starts, lengths, names = oracle.records_to_stream(recs)
+    for chunk in (1 << 20, 3):
+        fs = fasta.FastaStream(p, chunk_bytes=chunk)
+        got = fs.read_all()
+        assert fs.names == names and fs.lengths == lengths and fs.starts == starts.tolist()
+        assert np.array_equal(got, want)
+
+
+def test_fasta_reader_rejects_non_ascii_sequence(tmp_path):
+    p = str(tmp_path / "bad.fa")
+    open(p, "wb").write(b">a\nAC\xc3\xa9GT\n")
+    with pytest.raises(ValueError):
+        fasta.FastaStream(p).read_all()
+
+
+def test_bgzf_writer_is_readable_as_gzip(tmp_path):
+    raw = os.urandom(200_000) + b"ACGT" * 50_000
+    blob = synth.bgzf_compress(raw, level=1)
+    assert gzip.decompress(blob) == raw
+    assert blob.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def test_header_names_sizes_and_frag_rule(tmp_path):
+    f = str(tmp_path / "g.fa.gz")
+    h = Header("proj", input_file=f, kmer_len=15)
+    assert h.index_file_root == f + ".15.kin"
+    assert h.index_tmp_file == f + ".15.kin.tmp" and h.metadata_file == f + ".15.kin.json"
+    assert h.kmer_size == h.data_size == h.max_size == 4 ** 15
+    assert h.file_ver == "KMER001" and h.max_val == 255 and h.frag_size == 357_914_000
+    open(f + ".15.kin.bgz", "wb").close()
+    assert h.index_file == f + ".15.kin.bgz"        # tools.py:185-190 prefers the .bgz
+    for K in (3, 5, 7, 9, 11, 13, 15, 17, 19):
+        assert frag_size_rule(4 ** K, 500_000_000, 1_000_000_000) == oracle.frag_size_rule(K)
+    for bad in (0, 4, -1):
+        with pytest.raises(AssertionError):        # tools.py:165-167
+            Header("p", input_file=f, kmer_len=bad)
+
+
+def test_header_metadata_roundtrip_and_errors(tmp_path):
+    gold = json.load(open(os.path.join(GOLD, "indexer", "tiny_mixed.fa.05.json")))
+    base = str(tmp_path / "tiny_mixed.fa")
+    open(base, "w").close()
+    meta = {k: gold.get(k) for k in Header.HEADER_FIXED + Header.HEADER_DATA}
+    meta.update(input_file_path=base, kmer_len=5)
+    json.dump(meta, open(base + ".05.kin.json", "w"))
+    h = Header("whatever", index_file=base + ".05.kin")
+    assert h.kmer_len == 5 and h.input_file_path == base and h.num_kmers == gold["num_kmers"]
+    lean = h.to_dict(lean=True)
+    assert "chromosomes" not in lean and len(lean) == 32 and len(h.to_dict()) == 33
+    h2 = Header("whatever", index_file=base + ".05.kin.bgz")     # .bgz suffix is stripped
+    assert h2.kmer_len == 5
+    del meta["hist"]
+    json.dump(meta, open(base + ".05.kin.json", "w"))
+    with pytest.raises(KeyError):                                 # tools.py:394
+        Header("whatever", index_file=base + ".05.kin")
+    meta["hist"] = gold["hist"]
+    meta["kmer_size"] = 7
+    json.dump(meta, open(base + ".05.kin.json", "w"))
+    with pytest.raises(AssertionError):                           # tools.py:401
+        Header("whatever", index_file=base + ".05.kin")
+
+
+def test_init_tmp_file_is_sparse_and_overwrite_rule(tmp_path):
+    f = str(tmp_path / "x.fa")
+    h = Header("p", input_file=f, kmer_len=5)
+    h.init_index_tmp_file(overwrite=True)
+    assert os.path.getsize(h.index_tmp_file) == 4 ** 5
+    open(h.index_file_root, "wb").close()
+    with pytest.raises(ValueError):                               # tools.py:319,325
+        h.init_index_tmp_file(overwrite=False)
+    h.init_index_tmp_file(overwrite=True)
+    assert not os.path.exists(h.index_file_root)
+
+
+def test_timer_and_checksum(tmp_path):
+    t = Timer()
+    t.update(1000)
+    assert t.val_last == 1000 and t.speed_ela >= 0
+    p = tmp_path / "c.bin"
+    p.write_bytes(b"abc")
+    assert gen_checksum(str(p)) == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+
+
+def test_synth_tables_are_slice_consistent():
+    full = synth.synth_table(3, 7)
+    assert np.array_equal(full[1000:5000], synth.synth_table_slice(3, 1000, 5000))
+    nz = np.count_nonzero(synth.synth_table(0, 9)) / 4 ** 9
+    assert 0.12 < nz < 0.20
+    assert synth.synth_table(1, 9).max() == 255
+
+
+def test_merger_argument_validation(tmp_path):
+    from pykmer_b200 import merger
+    with pytest.raises(AssertionError):
+        merger.merge(str(tmp_path / "p"), [tmp_path / "a.kin"], min_count=0)
+    with pytest.raises(AssertionError):
+        merger.merge(str(tmp_path / "p"), [tmp_path / "a.kin"], max_count=256)
+    with pytest.raises(AssertionError):                           # inputs must exist
+        merger.merge(str(tmp_path / "p"), [tmp_path / "a.kin", tmp_path / "b.kin"])
+    (tmp_path / "a.txt").write_bytes(b"")
+    with pytest.raises(AssertionError):                           # extension rule merger.py:109
+        merger.merge(str(tmp_path / "p"), [tmp_path / "a.txt"])
+    with pytest.raises(SystemExit):                               # merger.py:224-226
+        merger.main([str(tmp_path / "p"), str(tmp_path / "a.kin")])
+    args = merger.build_parser().parse_args(["proj", "a.kin", "b.kin", "--max-count=50"])
+    assert args.max_count == 50 and args.min_count == 1 and args.threads == 4
