@@ -1,0 +1,463 @@
+#!/usr/bin/env python3
+"""bench.py -- the reference's headline metric on B200: indexer bp/s at K=15 on a
+synthetic tomato-sized (782.5 Mbp) multi-FASTA stream (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                             # CPU arm (oracle port)
+    python bench.py --workload merger [--samples 50] ...             # second hot path
+
+One "step" = one whole pass of the hot path over the workload: zero the table,
+scan + count the 782.5 Mbp stream, compute hist / vals_* (and, for e2e, move the
+stream in from pinned host memory and the 1 GiB table back out).  N > 1 (torchrun)
+shards the canonical k-mer axis: every rank scans the whole stream and counts only
+its own k-mer range; hist / vals_* / num_kmers are combined with one NCCL
+all-reduce.  Total work is fixed, so scaling is "strong".
+
+Prints ONE JSON line (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = {"indexer": ("indexer_bp_per_s_K{K}", "bp/s"), "merger": ("merger_bitmask_GB_per_s", "GB/s")}
+L2_NOTE = "inputs exceed L2: 0.78 GB stream + 1 GiB table per step vs 126 MB L2"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="indexer", choices=["indexer", "merger"])
+    ap.add_argument("--kmer", type=int, default=15)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 782.5 Mbp genome")
+    ap.add_argument("--samples", type=int, default=50, help="merger: number of samples")
+    ap.add_argument("--max-count", type=int, default=50, help="merger: --max-count")
+    ap.add_argument("--mode", type=int, default=0, help="indexer counting mode (0 auto)")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=128.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ inputs
+
+def load_stream(scale: float, rank: int, world: int):
+    """The cleaned 782.5 Mbp stream (+ record table).  Generated once per box (seeded,
+    pykmer_b200/synth.py) and cached under the temp dir so that N ranks share it."""
+    from pykmer_b200 import synth
+    tag = f"pykmer_b200_syn782M_{synth.SYN782M_SEED:x}_{scale:.6f}"
+    path = os.path.join(tempfile.gettempdir(), tag + ".npz")
+    if rank == 0 and not os.path.exists(path):
+        recs = synth.syn782m_records(scale=scale)
+        stream, starts, lengths, names = synth.records_to_stream(recs)
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, stream=stream, starts=starts, lengths=np.asarray(lengths, dtype=np.int64))
+        os.replace(tmp, path)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    z = np.load(path)
+    return z["stream"], z["starts"], z["lengths"].tolist()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------ CPU arm
+
+def cpu_indexer_sample(stream: np.ndarray, K: int, sample_mbp: float, table=None):
+    """The oracle port (oracle/kmer_oracle.c, threaded rolling form) on a bounded prefix of
+    the same stream, with the full 4^K table, on all host cores.  The per-base part (scan +
+    count) is timed on the sample and scaled to the whole stream; the per-table part (zero +
+    hist/vals_* pass) is timed once in full: t_job = t_scan * L/n + t_table."""
+    from oracle import oracle
+    n = int(min(stream.size, sample_mbp * 1e6))
+    sample = np.ascontiguousarray(stream[:n])
+    cores = oracle.max_threads()
+    if table is None:
+        table = np.zeros(4 ** K, dtype=np.uint8)
+    t0 = time.perf_counter()
+    table[:] = 0
+    t1 = time.perf_counter()
+    oracle.index_stream(sample, K, method="mt", threads=cores, table=table)
+    t2 = time.perf_counter()
+    oracle.table_stats(table, threads=cores)
+    t3 = time.perf_counter()
+    t_job = (t2 - t1) * stream.size / n + (t1 - t0) + (t3 - t2)
+    what = (f"scan+count timed on the first {n / 1e6:.1f} Mbp of the same stream ({t2 - t1:.2f} s, "
+            f"{cores} threads) and scaled to {stream.size / 1e6:.1f} Mbp; zero + stats pass over the "
+            f"4^{K}-byte table timed in full ({(t1 - t0) + (t3 - t2):.2f} s)")
+    return stream.size / t_job, cores, what, (t3 - t0)
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    if args.workload == "merger":
+        return run_reference_merger(args)
+    K = args.kmer
+    stream, starts, lengths = load_stream(args.scale, 0, 1)
+    table = np.zeros(4 ** K, dtype=np.uint8)
+    vals, walls = [], []
+    for it in range(args.warmup + args.steps):
+        v, cores, what, wall = cpu_indexer_sample(stream, K, args.cpu_sample_mbp, table)
+        if it >= args.warmup:
+            vals.append(v); walls.append(wall)
+    value = len(vals) / sum(1.0 / v for v in vals)          # total bp / total estimated time
+    total, times, n = sum(walls), walls, int(min(stream.size, args.cpu_sample_mbp * 1e6))
+    name, unit = METRIC["indexer"]
+    line = {
+        "impl": "reference", "metric": name.format(K=K), "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"indexer K={K}, synthetic tomato-sized multi-FASTA stream "
+                               f"({stream.size / 1e6:.1f} Mbp), 4^{K}-byte table",
+                   "note": "CPU arm: C port of the reference algorithm (the reference itself is "
+                           "pure Python, ~0.5 Mbp/s under pypy per its README, and cannot travel)"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_merger(args):
+    from oracle import oracle
+    from pykmer_b200 import synth
+    K, N = args.kmer, args.samples
+    cores = oracle.max_threads()
+    T = 4 ** K
+    n = min(T, 1 << 24)                         # bounded slice of the k-mer axis
+    Ns = min(N, 16)
+    tables = np.stack([synth.synth_table_slice(s, 0, n) for s in range(Ns)])
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.merge_matrix(tables, 1, args.max_count, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    # the reference reads both tables of every pair: N(N-1)/2 pairs * 2 * n bytes; scale to the
+    # bitmask-read metric of the GPU arm by counting the same work units (sample-pairs * k-mers)
+    pair_positions = Ns * (Ns - 1) / 2 * n * len(times) / sum(times)
+    full_pairs = N * (N - 1) / 2
+    t_full = full_pairs * T / pair_positions
+    value = N * T / 8 / t_full / 1e9
+    name, unit = METRIC["merger"]
+    line = {
+        "impl": "reference", "metric": name, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"merger K={K}, N={N} synthetic samples, --max-count={args.max_count}",
+                   "note": "pair loop of the reference (C port), extrapolated from a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{Ns} samples x first {n} k-mers, all pairs; extrapolated to "
+                                   f"{int(full_pairs)} pairs x 4^{K}"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+
+def timed_steps(torch, dist, world, warmup, steps, body):
+    """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks."""
+    for _ in range(warmup):
+        body()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        body()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_indexer(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from pykmer_b200 import device as dev
+
+    K = args.kmer
+    T = 4 ** K
+    stream, starts, lengths = load_stream(args.scale, rank, world)
+    L = int(sum(lengths))
+    # k-mer-axis shard of this rank (contiguous range, multiple of 4 KiB)
+    lo = (T * rank // world) & ~4095
+    hi = T if rank == world - 1 else (T * (rank + 1) // world) & ~4095
+
+    d_stream = torch.from_numpy(stream).cuda()
+    ix = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=args.mode)
+    ix.set_records(starts)
+    red = torch.zeros(260, dtype=torch.int64, device="cuda")
+    last = {}
+
+    def step_device():
+        ix.reset()
+        ix.feed_device(d_stream)
+        hist, st = ix.finalize()
+        if world > 1:                                         # hist[255] + sums; min/max separately
+            red[:255] = torch.tensor(hist, dtype=torch.int64)
+            red[255] = st["num_kmers"]; red[256] = st["vals_sum"]; red[257] = st["vals_count"]
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            mm = torch.tensor([-st["vals_min"], st["vals_max"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+            r = red.cpu().tolist(); m2 = mm.cpu().tolist()
+            hist = r[:255]
+            st = {"num_kmers": r[255], "vals_sum": r[256], "vals_count": r[257],
+                  "vals_min": -m2[0], "vals_max": m2[1]}
+        last["hist"], last["st"] = hist, st
+
+    sampler = ClockSampler(local_rank)
+    launches0 = ix.launch_count()
+    sampler.start()
+    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step_device)
+    clocks = sampler.stop()
+    launches_all = ix.launch_count() - launches0
+    launches = launches_all * args.steps // (args.steps + args.warmup)
+    ms_step = ms / args.steps
+    value = L / (ms_step * 1e-3)
+    st = last["st"]
+
+    # dominant kernel alone (scan + count), timed live with events on the launching stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kms = []
+    for _ in range(3):
+        ix.reset()
+        torch.cuda.synchronize()
+        ev[0].record(); ix.feed_device(d_stream); ev[1].record()
+        torch.cuda.synchronize()
+        kms.append(ev[0].elapsed_time(ev[1]))
+    k_ms = statistics.median(kms)
+    # algorithmic bytes of the scan+count launch: 1 B per base read + one 32 B sector
+    # fetched and one written back per counted k-mer when the table exceeds L2
+    table_bytes = hi - lo
+    hist_l, st_l = ix.finalize()
+    n_k_local = st_l["num_kmers"]
+    alg = stream.size + (64 * n_k_local if table_bytes > 126e6 else 0)
+    peak, peak_src = measured_peak()
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_scan_count_direct", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": k_ms, "algorithmic_bytes": alg,
+                "step_algorithmic_bytes": stream.size + (64 * n_k_local if table_bytes > 126e6 else 0) + 2 * table_bytes,
+                "step_frac": (stream.size + (64 * n_k_local if table_bytes > 126e6 else 0) + 2 * table_bytes)
+                             / (ms_step * 1e-3) / 1e9 / peak}
+
+    # end to end through the C ABI with HOST buffers: pinned stream in, table + stats out
+    e2e = None
+    if not args.no_e2e:
+        h_stream = dev.pinned_empty(stream.size)
+        h_stream.numpy()[:] = stream
+        h_table = dev.pinned_empty(table_bytes)
+
+        def step_e2e():
+            ix.reset()
+            ix.feed_host(h_stream)
+            ix.finalize()
+            ix.table_to_host(h_table)
+
+        ms_e = timed_steps(torch, dist, world, 1, max(2, min(args.steps, 3)), step_e2e)
+        ms_e /= max(2, min(args.steps, 3))
+        e2e = {"value": L / (ms_e * 1e-3), "unit": "bp/s", "h2d_bytes_per_step": int(stream.size),
+               "d2h_bytes_per_step": int(table_bytes + 257 * 8), "ms_per_step": ms_e}
+        del h_table
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, what, _ = cpu_indexer_sample(stream, K, args.cpu_sample_mbp)
+        cpu = {"value": v, "unit": "bp/s", "cores": cores, "kind": "port", "sample": what,
+               "reference_published": "503,287 bp/s (pypy, K=15, reference README.md:49)"}
+
+    if rank == 0:
+        name, unit = METRIC["indexer"]
+        line = {
+            "metric": name.format(K=K), "value": value, "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"indexer K={K}, synthetic tomato-sized multi-FASTA stream "
+                                   f"({L} bp, 13 records), 4^{K}-byte table",
+                       "parallelism": f"kmer-range x{world}" if world > 1 else "single GPU",
+                       "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
+                       "vals_count": st["vals_count"], "vals_max": st["vals_max"]},
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ix.close()
+
+
+def run_merger(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from pykmer_b200 import device as dev
+
+    K, N = args.kmer, args.samples
+    T = 4 ** K
+    lo = (T * rank // world) & ~4095
+    hi = T if rank == world - 1 else (T * (rank + 1) // world) & ~4095
+    n = hi - lo
+    words = n // 32
+    stride = (words + 3) & ~3
+    bits = torch.zeros((N, stride), dtype=torch.int32, device="cuda")
+    raw = torch.empty(n, dtype=torch.uint8, device="cuda")
+    G = torch.zeros((N, N), dtype=torch.int64, device="cuda")
+    # pack stage timed separately (per sample: generate, then threshold + pack)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    pack_ms = 0.0
+    for s in range(N):
+        dev.synth_table(s, lo, hi, out=raw)
+        ev[0].record()
+        dev.threshold_pack(raw, 1, args.max_count, out=bits[s])
+        ev[1].record()
+        torch.cuda.synchronize()
+        pack_ms += ev[0].elapsed_time(ev[1])
+
+    def step():
+        dev.gram(bits, words=words, out=G, accumulate=False)
+        if world > 1:
+            dist.all_reduce(G, op=dist.ReduceOp.SUM)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step)
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    bytes_bits = N * T / 8
+    value = bytes_bits / (ms_step * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    pairs = N * (N + 1) / 2
+    popc = pairs * T / 32
+    if rank == 0:
+        name, unit = METRIC["merger"]
+        Gh = G.cpu().numpy()
+        line = {
+            "metric": name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount -> int64", "data": "synthetic",
+            "config": {"workload": f"merger K={K}, N={N} synthetic samples, --max-count={args.max_count}; "
+                                   f"Gram stage over {bytes_bits / 1e9:.2f} GB of presence bitmask",
+                       "parallelism": f"kmer-axis x{world}" if world > 1 else "single GPU",
+                       "l2": f"bitmask {bytes_bits / 1e9:.2f} GB >> 126 MB L2",
+                       "pack_ms_total": pack_ms, "pack_GBps": N * n * 1.125 / (pack_ms * 1e-3) / 1e9,
+                       "trace_G": int(np.trace(Gh)), "G01": int(Gh[0, 1])},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_gram_popc", "achieved": value, "peak": peak,
+                         "unit": "GB/s", "frac": value / peak, "traffic": None, "peak_source": peak_src,
+                         "and_popc_per_s": popc / (ms_step * 1e-3)},
+            "e2e": None, "gpu_launches": args.steps,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        if args.workload == "indexer":
+            run_indexer(args, rank, local_rank, world)
+        else:
+            run_merger(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

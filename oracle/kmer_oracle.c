@@ -239,6 +239,46 @@ OK_EXPORT int ok_table_stats(const uint8_t *table, size_t n, int64_t hist[255],
     return 0;
 }
 
+/* threaded form of ok_table_stats for the CPU baseline leg (private bins per slab) */
+typedef struct { const uint8_t *table; size_t n, slab; uint64_t (*bins)[256]; } ok_stats_ctx;
+static void ok_stats_item(long s, void *ctx) {
+    ok_stats_ctx *c = (ok_stats_ctx *)ctx;
+    size_t from = (size_t)s * c->slab, to = from + c->slab;
+    if (to > c->n) to = c->n;
+    uint64_t *b = c->bins[s];
+    for (size_t i = from; i < to; i++) b[c->table[i]]++;
+}
+OK_EXPORT int ok_table_stats_mt(const uint8_t *table, size_t n, int64_t hist[255],
+                                uint64_t stats[4], int threads) {
+    if (threads < 1) threads = 1;
+    long slabs = (long)threads * 4;
+    ok_stats_ctx c;
+    c.table = table; c.n = n; c.slab = (n + (size_t)slabs - 1) / (size_t)slabs;
+    if (c.slab == 0) c.slab = 1;
+    c.bins = (uint64_t (*)[256])calloc((size_t)slabs, sizeof(uint64_t[256]));
+    if (!c.bins) return -1;
+    ok_parallel_for(slabs, threads, ok_stats_item, &c);
+    uint64_t bins[256];
+    memset(bins, 0, sizeof bins);
+    for (long s = 0; s < slabs; s++)
+        for (int v = 0; v < 256; v++) bins[v] += c.bins[s][v];
+    free(c.bins);
+    uint64_t sum = 0, cnt = 0;
+    int mn = 255, mx = 0;
+    for (int v = 0; v < 256; v++) {
+        if (v > 0) hist[v - 1] = (int64_t)bins[v];
+        if (bins[v]) {
+            sum += bins[v] * (uint64_t)v;
+            if (v > 0) cnt += bins[v];
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
+        }
+    }
+    if (n == 0) { mn = 0; mx = 0; }
+    stats[0] = sum; stats[1] = cnt; stats[2] = (uint64_t)mn; stats[3] = (uint64_t)mx;
+    return 0;
+}
+
 /*
  * Header.calculate_distance (tools.py:439-493), the arithmetic of one pair:
  * s_valid = (s >= min) & (s <= max), o_valid likewise, c_valid = both

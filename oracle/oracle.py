@@ -53,6 +53,7 @@ def lib() -> ctypes.CDLL:
         L.ok_index_rolling_mt.argtypes = [u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64,
                                           ctypes.c_uint64, u8p, u64p, ctypes.c_int]
         L.ok_table_stats.argtypes = [u8p, ctypes.c_size_t, i64p, u64p]
+        L.ok_table_stats_mt.argtypes = [u8p, ctypes.c_size_t, i64p, u64p, ctypes.c_int]
         L.ok_pair_counts.argtypes = [u8p, u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, u64p]
         L.ok_merge_matrix.argtypes = [u8p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t,
                                       ctypes.c_int, ctypes.c_int, u64p, ctypes.c_int]
@@ -108,13 +109,17 @@ def index_stream(seq: np.ndarray, K: int, range_lo: int = 0, range_hi: Optional[
     return table, int(num[0]), (flags[:nrec] if flags is not None else None)
 
 
-def table_stats(table: np.ndarray):
+def table_stats(table: np.ndarray, threads: int = 1):
     """Header.update_stats (tools.py:246-263) -> (hist list[255], dict of 8 scalars)."""
     table = np.ascontiguousarray(table, dtype=np.uint8)
     hist = np.zeros(255, dtype=np.int64)
     st = np.zeros(4, dtype=np.uint64)
-    lib().ok_table_stats(_p(table, ctypes.c_uint8), table.size, _p(hist, ctypes.c_int64),
-                         _p(st, ctypes.c_uint64))
+    if threads > 1:
+        lib().ok_table_stats_mt(_p(table, ctypes.c_uint8), table.size, _p(hist, ctypes.c_int64),
+                                _p(st, ctypes.c_uint64), threads)
+    else:
+        lib().ok_table_stats(_p(table, ctypes.c_uint8), table.size, _p(hist, ctypes.c_int64),
+                             _p(st, ctypes.c_uint64))
     h = hist.tolist()
     return h, {
         "hist_sum": int(sum(h)), "hist_count": int(sum(1 for v in h if v)),

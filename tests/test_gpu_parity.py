@@ -1,0 +1,389 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+committed golden outputs of the reference.  Everything is integer work: the bar is
+bit-exact equality."""
+import glob
+import hashlib
+import json
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from oracle import oracle
+    from pykmer_b200 import device, _native
+    assert _native.device_count() >= 1
+    return {"torch": torch, "oracle": oracle, "dev": device, "nat": _native}
+
+
+def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0):
+    import torch
+    hi = 4 ** K if hi is None else hi
+    with dev.Indexer(K, device=0, range_lo=lo, range_hi=hi, mode=mode) as ix:
+        if starts is not None:
+            ix.set_records(starts)
+        cuts = [0, len(stream)] if not pieces else [0] + sorted(pieces) + [len(stream)]
+        keep = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = np.ascontiguousarray(stream[a:b])
+            if host:
+                ix.feed_host(part)
+            elif b > a:
+                t = torch.from_numpy(part.copy()).cuda()
+                keep.append(t)
+                ix.feed_device(t)
+        hist, st = ix.finalize()
+        flags = ix.record_flags() if starts is not None else None
+        table = ix.table_to_host().numpy().copy()
+    return table, hist, st, flags
+
+
+INDEXER_CASES = sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLD, "indexer", "*.json"))
+                       if not os.path.basename(p).startswith("syn10M"))
+
+
+@pytest.mark.parametrize("case", INDEXER_CASES)
+def test_indexer_stream_matches_reference_golden(env, case):
+    """cleaned stream -> CUDA -> table/stats == what the reference's indexer.py wrote."""
+    from pykmer_b200 import fasta
+    fname, kk = case.rsplit(".", 1)
+    K = int(kk)
+    gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
+    stream, names, starts, lengths = fasta.read_fasta_stream(os.path.join(GOLD, "inputs", fname))
+    table, hist, st, flags = _index_stream(env["dev"], stream, K, starts=starts)
+    assert st["num_kmers"] == gold["num_kmers"]
+    assert hist == gold["hist"]
+    for k in ("vals_sum", "vals_count", "vals_min", "vals_max"):
+        assert st[k] == gold[k], k
+    assert hashlib.sha256(table.tobytes()).hexdigest() == gold["output_file_cheksum"]
+    chrom = [[names[i], lengths[i]] for i in range(len(names)) if flags[i]]
+    assert chrom == gold["chromosomes"]
+
+
+@pytest.mark.parametrize("case", ["tiny_mixed.fa.07", "saturating.fa.gz.11", "rand200k.fa.bgz.13",
+                                  "allkmers_05.fasta.gz.05"])
+def test_indexer_cli_writes_reference_files(env, case, tmp_path):
+    """indexer.py CLI: .kin bytes and every deterministic .kin.json key equal the reference's."""
+    from pykmer_b200 import indexer
+    fname, kk = case.rsplit(".", 1)
+    K = int(kk)
+    gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
+    src = str(tmp_path / fname)
+    shutil.copy(os.path.join(GOLD, "inputs", fname), src)
+    indexer.main([src, "sample", str(K)])
+    kin = f"{src}.{K:02d}.kin"
+    assert os.path.exists(kin) and not os.path.exists(kin + ".tmp")
+    meta = json.load(open(kin + ".json"))
+    assert sorted(meta.keys()) == gold["all_keys"]
+    for k, v in gold.items():
+        if k in ("all_keys",):
+            continue
+        got = meta[k]
+        if k == "project_name":
+            got = os.path.basename(got)
+        assert got == v, k
+    assert gen_sha(kin) == gold["output_file_cheksum"] == meta["output_file_cheksum"]
+    # the reference's own self-check (read_fasta_index -> Header.check_data) passes
+    indexer.read_fasta_index(src, input_file=src, kmer_len=K)
+
+
+def gen_sha(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as fh:
+        for blk in iter(lambda: fh.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def test_indexer_config1_syn10M(env, tmp_path):
+    """BASELINE config 1 end to end through the CLI: 10 Mbp bgzip multi-FASTA, K=11."""
+    from pykmer_b200 import indexer, synth
+    gold = json.load(open(os.path.join(GOLD, "indexer", "syn10M.fa.bgz.11.json")))
+    src = str(tmp_path / "syn10M.fa.bgz")
+    synth.write_fasta(src, synth.syn10m_records(), line_width=60, level=1)
+    assert gen_sha(src) == gold["fasta_sha256"]
+    indexer.main([src, "syn10M", "11"])
+    meta = json.load(open(src + ".11.kin.json"))
+    for k in ("num_kmers", "chromosomes", "hist", "hist_sum", "hist_count", "hist_min", "hist_max",
+              "vals_sum", "vals_count", "vals_min", "vals_max", "output_file_cheksum",
+              "input_file_cheksum", "frag_size", "flush_every", "data_size"):
+        assert meta[k] == gold[k], k
+    assert gen_sha(src + ".11.kin") == gold["output_file_cheksum"]
+
+
+def _random_stream(rng, n, alphabet=b"ACGTacgtACGTACGTNn>", runs=True):
+    a = np.frombuffer(alphabet, dtype=np.uint8)
+    s = a[rng.integers(0, len(a), size=n)].copy()
+    if runs and n > 5000:
+        s[1000:2600] = ord("A")                       # saturates a counter
+        s[3000:4200] = np.frombuffer(b"AT" * 600, dtype=np.uint8)
+    return s
+
+
+@pytest.mark.parametrize("K", [1, 3, 5, 7, 9, 11, 13])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 495, 496, 497, 100_003])
+def test_indexer_random_streams_vs_oracle(env, K, n):
+    rng = np.random.default_rng(1000 * K + n)
+    s = _random_stream(rng, n)
+    want, num, _ = env["oracle"].index_stream(s, K)
+    table, hist, st, _ = _index_stream(env["dev"], s, K)
+    assert st["num_kmers"] == num
+    assert np.array_equal(table, want)
+    oh, ost = env["oracle"].table_stats(want)
+    assert hist == oh and all(st[k] == ost[k] for k in ("vals_sum", "vals_count", "vals_min", "vals_max"))
+
+
+@pytest.mark.parametrize("K", [15, 17, 19, 21, 25, 31])
+def test_indexer_wide_k_on_a_range_vs_oracle(env, K):
+    """K > 13: the table is too big for a unit test, so count one k-mer range
+    (exactly what a shard does) over a sequence built to land in it."""
+    rng = np.random.default_rng(K)
+    parts = []
+    for _ in range(400):
+        parts.append(np.full(int(rng.integers(K - 3, 3 * K)), ord("A"), dtype=np.uint8))
+        parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 12)))])
+        if rng.random() < 0.1:
+            parts.append(np.frombuffer(b"N", dtype=np.uint8))
+    s = np.concatenate(parts)
+    lo, hi = 0, 1 << 22
+    want, num, _ = env["oracle"].index_stream(s, K, range_lo=lo, range_hi=hi)
+    assert num > 1000
+    table, hist, st, _ = _index_stream(env["dev"], s, K, lo=lo, hi=hi)
+    assert st["num_kmers"] == num and np.array_equal(table, want)
+    lo2 = (4 ** K) // 2 - (1 << 20)
+    lo2 -= lo2 % 4
+    want2, num2, _ = env["oracle"].index_stream(s, K, range_lo=lo2, range_hi=lo2 + (1 << 21))
+    t2, _, st2, _ = _index_stream(env["dev"], s, K, lo=lo2, hi=lo2 + (1 << 21))
+    assert st2["num_kmers"] == num2 and np.array_equal(t2, want2)
+
+
+@pytest.mark.parametrize("K", [5, 11, 17])
+@pytest.mark.parametrize("host", [False, True])
+def test_indexer_chunked_feeds_carry_the_window(env, K, host):
+    rng = np.random.default_rng(77 + K)
+    s = _random_stream(rng, 50_000)
+    hi = min(4 ** K, 1 << 22)
+    want, num, _ = env["oracle"].index_stream(s, K, range_hi=hi)
+    cuts = sorted(set(rng.integers(1, len(s) - 1, size=40).tolist()) | {1, 2, 3, 17, 33, 48, 49, 64})
+    table, _, st, _ = _index_stream(env["dev"], s, K, hi=hi, pieces=cuts, host=host)
+    assert st["num_kmers"] == num and np.array_equal(table, want)
+
+
+def test_indexer_record_flags_many_records(env):
+    """test.py construction at K=7: 16384 records of exactly K bases, every one listed."""
+    from pykmer_b200 import fasta
+    stream, names, starts, lengths = fasta.read_fasta_stream(os.path.join(GOLD, "inputs", "allkmers_07.fasta.gz"))
+    for K, expect_all in ((7, True), (9, False)):
+        _, _, st, flags = _index_stream(env["dev"], stream, K, starts=starts)
+        _, num, oflags = env["oracle"].index_stream(stream, K, rec_starts=starts)
+        assert st["num_kmers"] == num and np.array_equal(flags, oflags)
+        assert bool(flags.all()) == expect_all
+
+
+def test_indexer_range_shards_concatenate(env):
+    rng = np.random.default_rng(5)
+    s = _random_stream(rng, 200_000)
+    K = 9
+    T = 4 ** K
+    full, _, st_full, _ = _index_stream(env["dev"], s, K)
+    cuts = [0, T // 8, T // 2 + 4, T]
+    parts, total = [], 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        t, _, st, _ = _index_stream(env["dev"], s, K, lo=lo, hi=hi)
+        parts.append(t)
+        total += st["num_kmers"]
+    assert np.array_equal(np.concatenate(parts), full) and total == st_full["num_kmers"]
+
+
+def test_indexer_reset_and_reuse(env):
+    import torch
+    rng = np.random.default_rng(9)
+    dev, oracle = env["dev"], env["oracle"]
+    with dev.Indexer(9) as ix:
+        for rep in range(3):
+            s = _random_stream(rng, 30_000 + rep)
+            t = torch.from_numpy(s).cuda()
+            ix.reset()
+            ix.feed_device(t)
+            hist, st = ix.finalize()
+            want, num, _ = oracle.index_stream(s, 9)
+            assert st["num_kmers"] == num
+            assert np.array_equal(ix.table_to_host().numpy(), want)
+        assert ix.launch_count() >= 9
+
+
+def test_indexer_rejects_bad_arguments(env):
+    dev, nat = env["dev"], env["nat"]
+    for K in (0, 4, 33, -3):
+        with pytest.raises(ValueError):
+            dev.Indexer(K)
+    with pytest.raises(ValueError):
+        dev.Indexer(5, range_lo=10, range_hi=5)
+    with pytest.raises(ValueError):
+        dev.Indexer(5, range_hi=4 ** 5 + 1)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 31, 4096, 1_000_003])
+def test_table_stats_vs_oracle(env, n):
+    rng = np.random.default_rng(n)
+    t = rng.integers(0, 256, size=n, dtype=np.uint8)
+    t[rng.random(n) < 0.7] = 0
+    t[rng.random(n) < 0.1] = 1
+    hist, st = env["dev"].table_stats(t)
+    oh, ost = env["oracle"].table_stats(t)
+    assert hist == oh
+    assert st == (ost["vals_sum"], ost["vals_count"], ost["vals_min"], ost["vals_max"])
+    full = np.full(max(n, 16), 7, dtype=np.uint8)            # no zero entry: vals_min = 7
+    assert env["dev"].table_stats(full)[1][2] == 7
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 65_536, 1_000_003])
+@pytest.mark.parametrize("lohi", [(1, 255), (2, 10), (255, 255), (1, 1), (7, 3)])
+def test_threshold_pack_vs_oracle(env, n, lohi):
+    import torch
+    rng = np.random.default_rng(n)
+    t = rng.integers(0, 256, size=n, dtype=np.uint8)
+    t[rng.random(n) < 0.5] = 0
+    lo, hi = lohi
+    bits = env["dev"].threshold_pack(torch.from_numpy(t).cuda(), lo, hi)
+    want = env["oracle"].threshold_pack(t, lo, hi)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("N,words", [(1, 1), (2, 3), (3, 64), (5, 65), (50, 1000), (64, 257),
+                                     (65, 130), (130, 70), (255, 33)])
+def test_gram_vs_oracle(env, N, words):
+    import torch
+    rng = np.random.default_rng(N * 1000 + words)
+    stride = (words + 3) & ~3
+    bits = rng.integers(0, 2 ** 32, size=(N, stride), dtype=np.uint64).astype(np.uint32)
+    bits[:, words:] = 0xFFFFFFFF                                  # padding must be ignored
+    d = torch.from_numpy(bits.view(np.int32)).cuda()
+    G = env["dev"].gram(d, words=words).cpu().numpy()
+    want = env["oracle"].gram_from_bits(bits[:, :words])
+    assert np.array_equal(G, want)
+    G2 = env["dev"].gram(d, words=words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
+    assert np.array_equal(G2.cpu().numpy(), 2 * want)
+
+
+MERGER_CASES = sorted(glob.glob(os.path.join(GOLD, "merger", "matrix_*.npz")))
+
+
+@pytest.mark.parametrize("path", MERGER_CASES, ids=[os.path.basename(p) for p in MERGER_CASES])
+def test_merge_matches_reference_golden(env, path):
+    gold = np.load(path)["matrix"]
+    meta = json.load(open(path[:-4] + ".json"))
+    tables = np.load(os.path.join(GOLD, "merger", "samples_K07.npz"))["tables"]
+    lo, hi = meta["min_count"], meta["max_count"]
+    m = env["dev"].merge_host(list(tables), lo, hi)
+    N = m.shape[0]
+    off = ~np.eye(N, dtype=bool)
+    assert m.dtype == np.uint64 and np.array_equal(m[off], gold[off])
+    assert np.array_equal(m, env["oracle"].merge_matrix(tables, lo, hi))
+    assert env["dev"].pair_counts(tables[1], tables[4], lo, hi) == tuple(int(v) for v in gold[1, 4])
+
+
+def test_merger_cli_writes_reference_files(env, tmp_path):
+    """merger.py CLI on .kin/.kin.bgz files: .kma matrix and .kma.json layout as the reference."""
+    import gzip
+    from pykmer_b200 import merger
+    from pykmer_b200.tools import Header
+    samples = np.load(os.path.join(GOLD, "merger", "samples_K07.npz"))
+    template = json.load(open(os.path.join(GOLD, "indexer", "tiny_mixed.fa.07.json")))
+    kins = []
+    for name, table in zip(samples["names"], samples["tables"]):
+        name = str(name)
+        packed = name.endswith(".bgz")
+        # same directory layout as the golden run, so that sorting the paths gives its order
+        sub = tmp_path / "merge" if name.startswith("synth") else tmp_path
+        sub.mkdir(exist_ok=True)
+        kin = str(sub / (name[:-4] if packed else name))
+        base = kin[:-len(".07.kin")]
+        open(base, "w").close()
+        meta = {k: template.get(k) for k in Header.HEADER_FIXED + Header.HEADER_DATA}
+        meta.update(input_file_path=base, input_file_name=os.path.basename(base), kmer_len=7)
+        json.dump(meta, open(kin + ".json", "w"))
+        if packed:
+            with gzip.open(kin + ".bgz", "wb") as fz:
+                fz.write(table.tobytes())
+            kins.append(kin + ".bgz")
+        else:
+            table.tofile(kin)
+            kins.append(kin)
+    for lo, hi in ((2, 10), (1, 255)):
+        gold = np.load(os.path.join(GOLD, "merger", f"matrix_K07_{lo:03d}-{hi:03d}.npz"))["matrix"]
+        gmeta = json.load(open(os.path.join(GOLD, "merger", f"matrix_K07_{lo:03d}-{hi:03d}.json")))
+        proj = str(tmp_path / f"proj{lo}")
+        merger.main([proj] + list(reversed(kins)) + [f"--min-count={lo}", f"--max-count={hi}"])
+        kma = f"{proj}.{lo:03d}-{hi:03d}.kma"
+        m = np.load(kma)["matrix"]
+        desc = json.load(open(kma + ".json"))
+        N = m.shape[0]
+        off = ~np.eye(N, dtype=bool)
+        assert m.dtype == np.uint64 and m.shape == gold.shape and np.array_equal(m[off], gold[off])
+        assert sorted(desc.keys()) == gmeta["top_keys"]
+        assert sorted(desc["data"][0].keys()) == gmeta["data_keys"]
+        assert sorted(desc["data"][0]["header"].keys()) == gmeta["header_keys"]
+        assert [os.path.basename(d["index_file"]) for d in desc["data"]] == gmeta["order"]
+        assert [d["pos"] for d in desc["data"]] == gmeta["pos"]
+        with pytest.raises(AssertionError):                     # refuses to overwrite (merger.py:99)
+            merger.main([proj] + kins + [f"--min-count={lo}", f"--max-count={hi}"])
+    # one pair through the mirror of merger.calculate_distance
+    assert merger.calculate_distance(kins[0], kins[1], 2, 10) == \
+        env["oracle"].pair_counts(samples["tables"][0], samples["tables"][1], 2, 10)
+
+
+def test_synth_table_kernel_matches_numpy(env):
+    from pykmer_b200 import synth
+    for s in (0, 3, 49, 254):
+        d = env["dev"].synth_table(s, 12_345, 12_345 + 200_000)
+        assert np.array_equal(d.cpu().numpy(), synth.synth_table_slice(s, 12_345, 12_345 + 200_000))
+
+
+def test_merge_pipeline_synthetic_k11_vs_oracle(env):
+    """50 synthetic samples at K=11, --max-count=50 (BASELINE config 3 at reduced K)."""
+    import torch
+    from pykmer_b200 import synth
+    dev = env["dev"]
+    K, N = 11, 50
+    T = 4 ** K
+    words = T // 32
+    bits = torch.zeros((N, words), dtype=torch.int32, device="cuda")
+    tables = np.empty((N, T), dtype=np.uint8)
+    for s in range(N):
+        d = dev.synth_table(s, 0, T)
+        dev.threshold_pack(d, 1, 50, out=bits[s])
+        tables[s] = d.cpu().numpy()
+    assert np.array_equal(tables[7], synth.synth_table(7, K))
+    m = dev.matrix_from_gram(dev.gram(bits).cpu().numpy())
+    want = env["oracle"].merge_matrix(tables, 1, 50, threads=env["oracle"].max_threads())
+    assert np.array_equal(m, want)
+
+
+def test_indexer_scaled_config2_vs_oracle(env):
+    """BASELINE config 2 at 1/16 scale (49 Mbp tomato-like multi-FASTA stream, K=15, full
+    1 GiB table): table bytes, num_kmers, record flags and statistics against the oracle."""
+    import torch
+    from pykmer_b200 import synth
+    dev, oracle = env["dev"], env["oracle"]
+    recs = synth.syn782m_records(scale=1 / 16)
+    stream, starts, lengths, names = synth.records_to_stream(recs)
+    want, num, _ = oracle.index_stream(stream, 15, method="mt", threads=oracle.max_threads())
+    table, hist, st, flags = _index_stream(dev, stream, 15, starts=starts, host=True)
+    assert st["num_kmers"] == num and flags.all()
+    assert np.array_equal(table, want)
+    oh, ost = oracle.table_stats(want)
+    assert hist == oh and st["vals_sum"] == ost["vals_sum"] and st["vals_max"] == 255
+    # size-independent properties of any index
+    assert st["vals_sum"] <= st["num_kmers"] and sum(hist) == st["vals_count"]
+    assert st["vals_min"] == 0

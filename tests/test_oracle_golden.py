@@ -49,7 +49,7 @@ def test_stats_numpy_and_c_agree():
     rng = np.random.default_rng(3)
     t = rng.integers(0, 256, size=100_003, dtype=np.uint8)
     t[rng.random(t.size) < 0.8] = 0
-    assert oracle.table_stats(t) == oracle.table_stats_numpy(t)
+    assert oracle.table_stats(t) == oracle.table_stats_numpy(t) == oracle.table_stats(t, threads=3)
 
 
 def test_frag_size_rule_known_values():
