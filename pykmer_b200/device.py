@@ -43,7 +43,8 @@ class Indexer:
         self.kmer_len = kmer_len
         self.device = device
         self.range_lo = range_lo
-        self.range_hi = 4 ** kmer_len if range_hi is None else range_hi
+        # range_hi = 0 lets the library pick 4^K (and reject a bad K with its own message)
+        self.range_hi = (4 ** kmer_len if 0 < kmer_len <= 31 else 0) if range_hi is None else range_hi
         self._h = ctypes.c_void_p()
         nat.check(lib.pk_indexer_create(ctypes.byref(self._h), kmer_len, device, range_lo,
                                         self.range_hi, mode))
