@@ -302,37 +302,49 @@ def run_indexer(args, rank, local_rank, world):
     value = L / (ms_step * 1e-3)
     st = last["st"]
 
-    # dominant kernel alone (scan + count), timed live with events on the launching stream
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kms = []
-    for _ in range(3):
-        ix.reset()
-        torch.cuda.synchronize()
-        ev[0].record(); ix.feed_device(d_stream); ev[1].record()
-        torch.cuda.synchronize()
-        kms.append(ev[0].elapsed_time(ev[1]))
-    k_ms = statistics.median(kms)
-    # algorithmic bytes of the scan+count launch: 1 B per base read + one 32 B sector
-    # fetched and one written back per counted k-mer when the table exceeds L2
-    table_bytes = hi - lo
+    # per-kernel-class device time of one extra (untimed) step, CUDA events on the launching
+    # stream around every launch (pk_indexer_set_profiling); the dominant class gets the roofline
+    ix.set_profiling(True)
+    ix.reset()
+    ix.feed_device(d_stream)
     hist_l, st_l = ix.finalize()
+    prof = ix.profile()
+    ix.set_profiling(False)
+    mode, windows = ix.mode()
     n_k_local = st_l["num_kmers"]
-    alg = stream.size + (64 * n_k_local if table_bytes > 126e6 else 0)
+    table_bytes = hi - lo
+    big = table_bytes > 126e6
+    # algorithmic bytes (SURVEY 8d / DESIGN.md): 1 B per base scanned, 64 B per counted k-mer
+    # when the table exceeds L2 (one 32 B sector fetched + written back), 2 B per table entry
+    alg_by_class = {
+        "scan_count_direct": stream.size + (64 * n_k_local if big else 0),
+        "scan_bucket_count": stream.size,
+        "scan_scatter": stream.size,
+        "window_count": 64 * n_k_local if big else 0,
+        "window_commit": 2 * table_bytes,
+        "table_stats": table_bytes,
+    }
+    step_alg = stream.size + (64 * n_k_local if big else 0) + 2 * table_bytes
     peak, peak_src = measured_peak()
-    achieved = alg / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_scan_count_direct", "achieved": achieved, "peak": peak,
+    dom = max((c for c in prof if c in alg_by_class), key=lambda c: prof[c][0])
+    dom_ms, dom_launches = prof[dom]
+    achieved = alg_by_class[dom] / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms": k_ms, "algorithmic_bytes": alg,
-                "step_algorithmic_bytes": stream.size + (64 * n_k_local if table_bytes > 126e6 else 0) + 2 * table_bytes,
-                "step_frac": (stream.size + (64 * n_k_local if table_bytes > 126e6 else 0) + 2 * table_bytes)
-                             / (ms_step * 1e-3) / 1e9 / peak}
+                "kernel_ms_total": dom_ms, "kernel_launches": dom_launches,
+                "algorithmic_bytes": alg_by_class[dom],
+                "counted_kmers_per_s": n_k_local / (dom_ms * 1e-3) if dom in ("window_count", "scan_count_direct") else None,
+                "step_algorithmic_bytes": step_alg,
+                "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
+                "kernel_ms_by_class": {c: round(v[0], 4) for c, v in prof.items()},
+                "mode": {1: "direct", 2: "partition"}.get(mode, str(mode)), "windows": windows}
 
     # end to end through the C ABI with HOST buffers: pinned stream in, table + stats out
     e2e = None
     if not args.no_e2e:
         h_stream = dev.pinned_empty(stream.size)
         h_stream.numpy()[:] = stream
-        h_table = dev.pinned_empty(table_bytes)
+        h_table = dev.pinned_empty(hi - lo)
 
         def step_e2e():
             ix.reset()

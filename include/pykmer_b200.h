@@ -64,9 +64,12 @@ int         pk_host_free(void *ptr);
  * windows whose canonical value falls outside are ignored.  range 0..4^K is the
  * whole .kin; a sub-range is one shard of the k-mer-axis partition.
  */
-#define PK_MODE_AUTO      0
+#define PK_MODE_AUTO      0   /* PARTITION for tables beyond 64 Mi entries, else DIRECT */
 #define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
-#define PK_MODE_PARTITION 2   /* bucket k-mers by table window, count window by window on chip */
+#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^24-entry table window, count each window
+                                 with L2-resident 32-bit counters, clamp and write it once.
+                                 (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 shrink the
+                                 window and the k-mer buffer; they exist for the tests.) */
 
 int pk_indexer_create(pk_indexer **out, int kmer_len, int device,
                       uint64_t range_lo, uint64_t range_hi, int mode);
@@ -95,7 +98,8 @@ int pk_indexer_sync(pk_indexer *ix);
  * handle's range.  hist_host[i] = #{table == i+1}, i in 0..254.
  * stats_host = {num_kmers (indexer.py:342), vals_sum, vals_count, vals_min,
  * vals_max}.  Synchronises.  Feeding after finalize is allowed (statistics are
- * recomputed by the next finalize). */
+ * recomputed by the next finalize).  In PARTITION mode the table is only
+ * complete after finalize. */
 int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]);
 int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec);
 
@@ -104,6 +108,15 @@ int pk_indexer_table_device(pk_indexer *ix, const uint8_t **table_dev, size_t *b
 int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t offset, size_t bytes);
 /* launches of this library's kernels issued through the handle so far */
 int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches);
+/* Per-kernel-class device time, measured with CUDA events on the launching stream
+ * around every launch made through the handle while enabled.  Classes (index into
+ * ms_host / launches_host): 0 scan_count_direct, 1 scan_bucket_count, 2 bucket_offsets,
+ * 3 scan_scatter, 4 window_count, 5 window_commit, 6 table_stats, 7 update_carry.
+ * pk_indexer_profile synchronises the device, returns the sums and clears them. */
+int pk_indexer_set_profiling(pk_indexer *ix, int enable);
+int pk_indexer_profile(pk_indexer *ix, double ms_host[8], uint32_t launches_host[8]);
+/* the counting scheme PK_MODE_AUTO resolved to, and its number of table windows */
+int pk_indexer_mode(pk_indexer *ix, int *mode, int *windows);
 
 /* Header.update_stats (tools.py:246-263) over any device table.
  * stats_host = {vals_sum, vals_count, vals_min, vals_max}.  Synchronises `stream`. */

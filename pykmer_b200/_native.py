@@ -21,7 +21,8 @@ SYMBOLS = (
     "pk_indexer_create", "pk_indexer_destroy", "pk_indexer_reset", "pk_indexer_set_records",
     "pk_indexer_feed_device", "pk_indexer_feed_host", "pk_indexer_sync", "pk_indexer_finalize",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
-    "pk_indexer_launch_count", "pk_table_stats_device",
+    "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_set_profiling", "pk_indexer_profile",
+    "pk_table_stats_device",
     "pk_threshold_pack_device", "pk_gram_device", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device",
 )
@@ -65,6 +66,9 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_table_device": [vp, c.POINTER(vp), c.POINTER(sz)],
         "pk_indexer_table_to_host": [vp, vp, sz, sz],
         "pk_indexer_launch_count": [vp, c.POINTER(u64)],
+        "pk_indexer_mode": [vp, c.POINTER(i32), c.POINTER(i32)],
+        "pk_indexer_set_profiling": [vp, i32],
+        "pk_indexer_profile": [vp, vp, vp],
         "pk_table_stats_device": [vp, sz, vp, vp, vp],
         "pk_threshold_pack_device": [vp, sz, i32, i32, vp, vp],
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],

@@ -6,16 +6,32 @@
 // process_kmers' saturating accumulate (indexer.py:239,262) and
 // Header.update_stats (tools.py:246-263).
 //
-// Kernels
-//   k_scan_count_direct<WIDE>  fused encode -> canonical k-mer -> saturating count.
-//       One thread encodes one 16-base group (one 16-byte coalesced load), gets the
-//       K-1 base halo from its neighbour lanes by warp shuffle, slices every window
-//       out of the 2-bit concatenation (kmer_bits.h) and bumps table[canon] with a
-//       byte-granular compare-and-swap that never touches a saturated counter.
-//   k_table_stats              one streaming pass: 256-bin histogram -> hist/vals_*.
+// Every scan kernel shares one front end: a thread encodes one 16-base group (one
+// coalesced 16-byte load, 256-byte LUT in shared memory), fetches the K-1 base halo
+// from its neighbour lanes with warp shuffles, and slices every window that ends in
+// its group out of the 2-bit concatenation (pk_scan_group, kmer_bits.h).
+//
+// Two counting schemes (measured on B200, profiles/r01_microbench_b200.txt):
+//   DIRECT     k_scan_count_direct: byte-granular compare-and-swap straight into the
+//              table.  Random DRAM sectors: ~20 G updates/s.  Used for small tables
+//              (they sit in L2) and as the fallback.
+//   PARTITION  the table is cut into WINDOWS of 2^24 entries whose 32-bit counters
+//              (64 MiB) stay resident in the 126 MB L2, where red.global.add.u32 runs
+//              at ~190 G/s instead of ~20 G/s:
+//                k_scan_bucket_count  pass 1: how many k-mers fall in each window
+//                k_bucket_offsets     exclusive scan -> segment offsets in the pool
+//                k_scan_scatter       pass 2: write (offset-in-window, run length)
+//                                     entries, coalesced, into per-window segments
+//                k_window_count       per window: L2-resident red.add.u32
+//                k_window_commit      per window: clamp to 255 (saturating accumulate),
+//                                     write the table once, re-zero the counters, and
+//                                     histogram the final bytes (fused update_stats)
+//   k_table_stats              stand-alone 256-bin histogram pass (DIRECT mode).
 //   k_update_carry             keeps the last 32 stream bytes for the next feed.
 #include <algorithm>
 #include <new>
+#include <vector>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -24,8 +40,13 @@
 namespace {
 
 constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
 constexpr size_t kStageBytes = 32u << 20;   // pinned-copy chunk of feed_host
 constexpr int kCarry = 32;                  // bytes of stream tail kept between feeds
+constexpr int kMaxBuckets = 4096;           // windows per handle in PARTITION mode
+constexpr int kMaxSegments = 128;           // feeds buffered between two flushes
+constexpr size_t kMaxFeed = 256u << 20;     // bases per partition pass
+constexpr int kTileEntries = kScanWarps * 31 * 16;   // most entries one block tile can emit
 
 struct ScanParams {
     const uint8_t *seq;       // this feed (16-byte aligned)
@@ -33,12 +54,18 @@ struct ScanParams {
     const uint8_t *carry;     // last kCarry bytes of everything fed before
     int K;
     uint64_t lo, hi;          // canonical range owned by this handle
-    uint8_t *table;           // [hi - lo]
+    uint8_t *table;           // [hi - lo]                               (DIRECT)
     unsigned long long *num_kmers;
     const uint64_t *rec_starts;
     size_t nrec;
     uint8_t *rec_flags;
     uint64_t stream_off;      // stream offset of seq[0]
+    // PARTITION
+    uint32_t win_log2, nbuckets;
+    uint32_t *seg_cnt;        // [nbuckets] entries of this feed per window (pass 1 out)
+    const uint32_t *seg_off;  // [nbuckets] pool index of each segment      (pass 2 in)
+    uint32_t *seg_fill;       // [nbuckets] fill cursors                    (pass 2)
+    uint32_t *pool;
 };
 
 __device__ __forceinline__ void load_group(const ScanParams &p, long long g, long long ngroups,
@@ -87,84 +114,314 @@ __device__ __forceinline__ long long find_record(const uint64_t *starts, size_t 
     return (long long)lo - 1;
 }
 
+// indexer.py:349-351: a record is listed once a k-mer of it has been counted
+struct RecordFlagger {
+    const ScanParams &p;
+    long long g;
+    __device__ __forceinline__ void operator()(int j, bool fresh) const {
+        if (!fresh || !p.rec_flags) return;
+        const long long r = find_record(p.rec_starts, p.nrec, p.stream_off + (uint64_t)g * 16 + j);
+        if (r >= 0 && !p.rec_flags[r]) p.rec_flags[r] = 1;
+    }
+};
+struct NoFlags {
+    __device__ __forceinline__ void operator()(int, bool) const {}
+};
+
+// One warp tile: lane l encodes group tile*GPW - H + l and receives its halo by shuffle.
+template <bool WIDE>
+struct WarpTile {
+    static constexpr int H = WIDE ? 2 : 1;      // halo groups: K-1 <= 16*H bases
+    static constexpr int GPW = 32 - H;          // groups a warp emits per tile
+    long long g;
+    uint32_t cc, cv, pc1, pv1, pc2, pv2;
+    bool emits;
+    __device__ __forceinline__ void load(const ScanParams &p, long long tile, long long ngroups,
+                                         const uint8_t *lut) {
+        const int lane = threadIdx.x & 31;
+        g = tile * GPW - H + lane;
+        uint32_t w[4];
+        load_group(p, g, ngroups, w);
+        pk_encode16(w, lut, cc, cv);
+        pc1 = __shfl_up_sync(0xFFFFFFFFu, cc, 1);
+        pv1 = __shfl_up_sync(0xFFFFFFFFu, cv, 1);
+        pc2 = 0; pv2 = 0;
+        if (WIDE) {
+            pc2 = __shfl_up_sync(0xFFFFFFFFu, cc, 2);
+            pv2 = __shfl_up_sync(0xFFFFFFFFu, cv, 2);
+        }
+        emits = lane >= H && g >= 0 && g < ngroups;
+    }
+};
+
+__device__ __forceinline__ void add_num_kmers(unsigned long long *dst, unsigned long long counted) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xFFFFFFFFu, counted, o);
+    if ((threadIdx.x & 31) == 0 && counted) atomicAdd(dst, counted);
+}
+
+// ------------------------------------------------------------------------------ DIRECT
 template <bool WIDE>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanParams p) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
     __syncthreads();
-
-    constexpr int H = WIDE ? 2 : 1;          // halo groups: K-1 <= 16*H bases
-    constexpr int GPW = 32 - H;              // groups a warp emits per tile
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    const int K = p.K;
+    using WT = WarpTile<WIDE>;
     const long long ngroups = (long long)((p.n + 15) / 16);
-    const long long ntiles = (ngroups + GPW - 1) / GPW;
+    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const uint64_t mask64 = pk_kmer_mask(K);
-    const uint32_t mask32 = (uint32_t)mask64;
     unsigned long long counted = 0;
-
     for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles;
          tile += nwarps) {
-        const long long g = tile * GPW - H + lane;
-        uint32_t w[4];
-        load_group(p, g, ngroups, w);
-        uint32_t cc, cv;
-        pk_encode16(w, lut, cc, cv);
-        const uint32_t pc1 = __shfl_up_sync(full, cc, 1);
-        const uint32_t pv1 = __shfl_up_sync(full, cv, 1);
-        uint32_t pc2 = 0, pv2 = 0;
-        if (WIDE) {
-            pc2 = __shfl_up_sync(full, cc, 2);
-            pv2 = __shfl_up_sync(full, cv, 2);
-        }
-        if (lane < H || g >= ngroups) continue;
-
-        const uint64_t vcat = ((uint64_t)pv2 << 32) | ((uint64_t)pv1 << 16) | cv;
-        const uint32_t Wm = (uint32_t)pk_valid_windows(vcat, K) & 0xFFFFu;
-        if (!Wm) continue;
-
-        const uint32_t r0 = pk_rcw(cc), r1 = pk_rcw(pc1), r2 = WIDE ? pk_rcw(pc2) : 0u;
-        const uint64_t cat = ((uint64_t)pc1 << 32) | cc;
-        const uint64_t rcat = ((uint64_t)r0 << 32) | r1;
-        uint64_t prev = ~0ull;
-        uint32_t pend = 0;
-        long long cur_rec = -1;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (!((cv >> (15 - j)) & 1u)) cur_rec = -1;      // a separator may have passed
-            if (!((Wm >> (15 - j)) & 1u)) continue;
-            uint64_t canon;
-            if (WIDE) {
-                const uint64_t f = pk_fwd_at(pc2, pc1, cc, j, K);
-                const uint64_t r = pk_rc_at(r2, r1, r0, j, K);
-                canon = f < r ? f : r;                        // indexer.py:341
-            } else {
-                const uint32_t f = pk_fwd32_at(cat, j, mask32);
-                const uint32_t r = pk_rc32_at(rcat, j, K, mask32);
-                canon = f < r ? f : r;
-            }
-            if (canon < p.lo || canon >= p.hi) continue;      // another shard's k-mer
-            counted++;                                        // indexer.py:342
-            if (canon == prev) {
-                pend++;                                       // homopolymer run: one update
-            } else {
-                if (pend) sat_add_u8(p.table, prev - p.lo, pend);
-                prev = canon;
-                pend = 1;
-            }
-            if (p.rec_flags && cur_rec < 0) {                 // indexer.py:349-351
-                cur_rec = find_record(p.rec_starts, p.nrec, p.stream_off + (uint64_t)g * 16 + j);
-                if (cur_rec >= 0 && !p.rec_flags[cur_rec]) p.rec_flags[cur_rec] = 1;
-            }
-        }
-        if (pend) sat_add_u8(p.table, prev - p.lo, pend);
+        WT t;
+        t.load(p, tile, ngroups, lut);
+        if (!t.emits) continue;
+        counted += pk_scan_group<WIDE>(
+            p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+            [&](int, uint64_t off, uint32_t cnt) { sat_add_u8(p.table, off, cnt); },
+            RecordFlagger{p, t.g});
     }
-    (void)mask64;
+    add_num_kmers(p.num_kmers, counted);
+}
+
+// ------------------------------------------------------------------------------ PARTITION
+// pass 1: per-window entry counts of this feed (+ num_kmers and record flags)
+template <bool WIDE>
+__global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanParams p) {
+    extern __shared__ uint32_t sm[];
+    uint32_t *s_cnt = sm;                                  // [nbuckets]
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
+    for (uint32_t b = threadIdx.x; b < p.nbuckets; b += blockDim.x) s_cnt[b] = 0;
+    __syncthreads();
+    using WT = WarpTile<WIDE>;
+    const long long ngroups = (long long)((p.n + 15) / 16);
+    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const uint32_t wl = p.win_log2;
+    unsigned long long counted = 0;
+    for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles;
+         tile += nwarps) {
+        WT t;
+        t.load(p, tile, ngroups, lut);
+        if (!t.emits) continue;
+        counted += pk_scan_group<WIDE>(
+            p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+            [&](int, uint64_t off, uint32_t) { atomicAdd(&s_cnt[(uint32_t)(off >> wl)], 1u); },
+            RecordFlagger{p, t.g});
+    }
+    add_num_kmers(p.num_kmers, counted);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < p.nbuckets; b += blockDim.x)
+        if (s_cnt[b]) atomicAdd(&p.seg_cnt[b], s_cnt[b]);
+}
+
+// exclusive scan of one feed's window counts -> pool offsets; advances the pool cursor
+__global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restrict__ cnt,
+                                                        uint32_t *__restrict__ off, uint32_t nb,
+                                                        uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t part[256];
+    const uint32_t per = (nb + 255) / 256;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+    uint32_t s = 0;
+    for (uint32_t b = b0; b < b1; b++) s += cnt[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = *cursor;
+        for (int i = 0; i < 256; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        *cursor = run;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t b = b0; b < b1; b++) { off[b] = run; run += cnt[b]; }
+}
+
+// pass 2: the same scan again; entries are ranked per window in shared memory, staged
+// window by window, and written out as contiguous runs into the segments pass 1 sized.
+// entry = (run length - 1) << 24 | offset inside the window.
+template <bool WIDE>
+__global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams p) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t nb = p.nbuckets;
+    uint32_t *s_cnt = sm;                                  // [nb] entries of this tile per window
+    uint32_t *s_toff = sm + nb;                            // [nb] exclusive offsets inside the tile
+    uint32_t *s_gbase = sm + 2 * nb;                       // [nb] pool index reserved for the tile
+    uint32_t *s_ent = sm + 3 * nb;                         // [kTileEntries]
+    uint16_t *s_bid = reinterpret_cast<uint16_t *>(s_ent + kTileEntries);   // [kTileEntries]
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t s_part[kScanThreads];
+    __shared__ uint32_t s_total;
+    lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
+
+    using WT = WarpTile<WIDE>;
+    const long long ngroups = (long long)((p.n + 15) / 16);
+    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
+    const long long nblock_tiles = (ntiles + kScanWarps - 1) / kScanWarps;
+    const uint32_t wl = p.win_log2, wmask = (1u << wl) - 1u;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t per = (nb + kScanThreads - 1) / kScanThreads;
+
+    for (long long bt = blockIdx.x; bt < nblock_tiles; bt += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) s_cnt[b] = 0;
+        __syncthreads();
+        // A: scan; keep every run in registers with its window and its rank in the tile
+        uint32_t ent[17], key[17];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(full, counted, o);
-    if (lane == 0 && counted) atomicAdd(p.num_kmers, counted);
+        for (int s = 0; s < 17; s++) key[s] = 0xFFFFFFFFu;
+        const long long tile = bt * kScanWarps + warp;
+        if (tile < ntiles) {
+            WT t;
+            t.load(p, tile, ngroups, lut);
+            if (t.emits)
+                pk_scan_group<WIDE>(
+                    p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+                    [&](int slot, uint64_t off, uint32_t cnt) {
+                        const uint32_t b = (uint32_t)(off >> wl);
+                        const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
+                        ent[slot] = ((uint32_t)off & wmask) | ((cnt - 1u) << 24);
+                        key[slot] = (b << 16) | rank;
+                    },
+                    NoFlags{});
+        }
+        __syncthreads();
+        // B: exclusive scan over the windows; reserve the tile's share of every segment
+        {
+            const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+            uint32_t s = 0;
+            for (uint32_t b = b0; b < b1; b++) s += s_cnt[b];
+            s_part[threadIdx.x] = s;
+            __syncthreads();
+            if (warp == 0) {                               // scan 256 partials with one warp
+                uint32_t v[8], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { v[i] = s_part[threadIdx.x * 8 + i]; sum += v[i]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if ((int)(threadIdx.x & 31) >= o) incl += up;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { s_part[threadIdx.x * 8 + i] = run; run += v[i]; }
+                if (threadIdx.x == 31) s_total = incl;
+            }
+            __syncthreads();
+            uint32_t run = s_part[threadIdx.x];
+            for (uint32_t b = b0; b < b1; b++) {
+                const uint32_t c = s_cnt[b];
+                s_toff[b] = run;
+                run += c;
+                if (c) s_gbase[b] = p.seg_off[b] + atomicAdd(&p.seg_fill[b], c);
+            }
+        }
+        __syncthreads();
+        // C: stage the runs window by window
+#pragma unroll
+        for (int s = 0; s < 17; s++) {
+            if (key[s] != 0xFFFFFFFFu) {
+                const uint32_t b = key[s] >> 16, pos = s_toff[b] + (key[s] & 0xFFFFu);
+                s_ent[pos] = ent[s];
+                s_bid[pos] = (uint16_t)b;
+            }
+        }
+        __syncthreads();
+        // D: contiguous runs go out with coalesced stores
+        const uint32_t total = s_total;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t b = s_bid[i];
+            p.pool[s_gbase[b] + (i - s_toff[b])] = s_ent[i];
+        }
+        // the next iteration only touches s_cnt before its first barrier
+    }
+}
+
+// per window: every buffered entry of the window bumps its L2-resident 32-bit counter
+__global__ void __launch_bounds__(256) k_window_count(const uint32_t *__restrict__ pool,
+                                                      const uint32_t *__restrict__ seg_off,
+                                                      const uint32_t *__restrict__ seg_cnt,
+                                                      int nseg, uint32_t nb, uint32_t b,
+                                                      uint32_t *__restrict__ scratch) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int f = 0; f < nseg; f++) {
+        const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) {
+            const uint32_t e = __ldcs(pool + off + i);
+            atomicAdd(&scratch[e & 0xFFFFFFu], (e >> 24) + 1u);
+        }
+    }
+}
+
+// per window: table = min(255, [table +] counters) (indexer.py:239,262), counters back to
+// zero, and -- when bins != NULL -- the histogram of the bytes just written
+// (tools.py:250), so the final table is never read back.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ scratch,
+                                                       uint8_t *__restrict__ table, size_t n,
+                                                       unsigned long long *__restrict__ bins) {
+    __shared__ uint32_t sh[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    uint32_t c1 = 0, c2 = 0, c3 = 0;
+    const size_t nvec = n / 16;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint4 *sv = reinterpret_cast<uint4 *>(scratch);
+    uint4 *tv = reinterpret_cast<uint4 *>(table);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint32_t out[4];
+        uint4 old = zero;
+        if (ACCUM) old = tv[i];
+        const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 c = sv[4 * i + k];
+            sv[4 * i + k] = zero;
+            const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t val = cw[b];
+                if (ACCUM) val += (ow[k] >> (8 * b)) & 0xFFu;
+                x |= min(val, 255u) << (8 * b);
+            }
+            out[k] = x;
+            if (bins && x) {
+                c1 += __popc(__vcmpeq4(x, 0x01010101u)) >> 3;
+                c2 += __popc(__vcmpeq4(x, 0x02020202u)) >> 3;
+                c3 += __popc(__vcmpeq4(x, 0x03030303u)) >> 3;
+                if (x & 0xFCFCFCFCu) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t val = (x >> (8 * b)) & 0xFFu;
+                        if (val > 3u) atomicAdd(&sh[warp][val], 1u);
+                    }
+                }
+            }
+        }
+        tv[i] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {            // < 16 tail entries
+        for (size_t i = nvec * 16; i < n; i++) {
+            uint32_t val = scratch[i];
+            scratch[i] = 0;
+            if (ACCUM) val += table[i];
+            val = min(val, 255u);
+            table[i] = (uint8_t)val;
+            if (bins && val) atomicAdd(&sh[0][val], 1u);
+        }
+    }
+    if (!bins) return;
+    if (c1) atomicAdd(&sh[warp][1], c1);
+    if (c2) atomicAdd(&sh[warp][2], c2);
+    if (c3) atomicAdd(&sh[warp][3], c3);
+    __syncthreads();
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += sh[k][threadIdx.x];
+    if (s && threadIdx.x) atomicAdd(&bins[threadIdx.x], s);
 }
 
 // new carry = last kCarry bytes of (old carry ++ seq[0..n))
@@ -243,6 +500,10 @@ int stats_from_bins(const unsigned long long bins_in[256], size_t n, int64_t his
     return PK_OK;
 }
 
+size_t scatter_smem_bytes(uint32_t nb) {
+    return (size_t)3 * nb * sizeof(uint32_t) + (size_t)kTileEntries * (sizeof(uint32_t) + sizeof(uint16_t));
+}
+
 }  // namespace
 
 struct pk_indexer {
@@ -265,11 +526,97 @@ struct pk_indexer {
     int sm_count = 148;
     uint64_t launches = 0;
     bool fed = false;
+    // PARTITION mode
+    uint32_t win_log2 = 24, nbuckets = 0;
+    uint32_t *pool = nullptr;                  // buffered entries
+    size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
+    uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
+    uint32_t *cursor = nullptr;                // device pool cursor
+    uint32_t *scratch = nullptr;               // one window of 32-bit counters
+    int nseg = 0;
+    bool table_valid = false;                  // every window has been written since reset
+    bool stats_valid = false;                  // bins hold the histogram of the current table
+    bool scatter_smem_set = false;
+    // optional per-kernel-class timing (pk_indexer_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
+    std::vector<int> prof_tags;
 };
+
+enum { PROF_SCAN_DIRECT = 0, PROF_BUCKET_COUNT, PROF_OFFSETS, PROF_SCATTER, PROF_WINDOW_COUNT,
+       PROF_WINDOW_COMMIT, PROF_TABLE_STATS, PROF_CARRY, PROF_CLASSES };
+
+// brackets one kernel launch with events on its stream when profiling is on
+struct prof_scope {
+    pk_indexer *ix; cudaStream_t st; cudaEvent_t end = nullptr;
+    prof_scope(pk_indexer *ix_, cudaStream_t st_, int tag) : ix(ix_), st(st_) {
+        if (!ix->profiling) return;
+        cudaEvent_t b = nullptr;
+        if (cudaEventCreate(&b) != cudaSuccess || cudaEventCreate(&end) != cudaSuccess) { end = nullptr; return; }
+        cudaEventRecord(b, st);
+        ix->prof_events.push_back(b);
+        ix->prof_events.push_back(end);
+        ix->prof_tags.push_back(tag);
+    }
+    ~prof_scope() { if (end) cudaEventRecord(end, st); }
+};
+
+// make work_stream wait for whatever the caller's stream was last given
+static int indexer_join(pk_indexer *ix) {
+    if (ix->last_stream != ix->work_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(ix->work_stream, ix->joined, 0));
+        ix->last_stream = ix->work_stream;
+    }
+    return PK_OK;
+}
+
+static uint32_t *seg_cnt(pk_indexer *ix, int f) { return ix->seg + (size_t)f * ix->nbuckets; }
+static uint32_t *seg_off(pk_indexer *ix, int f) {
+    return ix->seg + ((size_t)kMaxSegments + f) * ix->nbuckets;
+}
+static uint32_t *seg_fill(pk_indexer *ix, int f) {
+    return ix->seg + ((size_t)2 * kMaxSegments + f) * ix->nbuckets;
+}
+
+// PARTITION: drain the buffered entries window by window into the table
+static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats) {
+    const size_t win = (size_t)1 << ix->win_log2;
+    if (with_stats)
+        PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
+    unsigned long long *bins = with_stats ? ix->counters + 1 : nullptr;
+    const int grid = ix->sm_count * 8;
+    for (uint32_t b = 0; b < ix->nbuckets; b++) {
+        const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
+        if (ix->nseg) {
+            prof_scope ps(ix, st, PROF_WINDOW_COUNT);
+            k_window_count<<<grid, 256, 0, st>>>(ix->pool, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg,
+                                                 ix->nbuckets, b, ix->scratch);
+            ix->launches++;
+        }
+        uint8_t *tw = ix->table + (size_t)b * win;
+        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid, (n / 16 + 255) / 256));
+        {
+            prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
+            if (ix->table_valid) k_window_commit<true><<<cgrid, 256, 0, st>>>(ix->scratch, tw, n, bins);
+            else                 k_window_commit<false><<<cgrid, 256, 0, st>>>(ix->scratch, tw, n, bins);
+        }
+        ix->launches++;
+    }
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
+    PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
+    ix->nseg = 0;
+    ix->pool_ub = 0;
+    ix->table_valid = true;
+    ix->stats_valid = with_stats;
+    return PK_OK;
+}
 
 static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st) {
     if (n == 0) return PK_OK;
     ScanParams p;
+    memset(&p, 0, sizeof p);
     p.seq = seq_dev; p.n = n; p.carry = ix->carry; p.K = ix->K; p.lo = ix->lo; p.hi = ix->hi;
     p.table = ix->table; p.num_kmers = ix->counters;
     p.rec_starts = ix->rec_starts; p.nrec = ix->nrec; p.rec_flags = ix->nrec ? ix->rec_flags : nullptr;
@@ -278,26 +625,73 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     const long long gpw = wide ? 30 : 31;
     const long long ngroups = (long long)((n + 15) / 16);
     const long long ntiles = (ngroups + gpw - 1) / gpw;
-    const long long want = (ntiles + (kScanThreads / 32) - 1) / (kScanThreads / 32);
+    const long long want = (ntiles + kScanWarps - 1) / kScanWarps;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 8));
-    if (wide) k_scan_count_direct<true><<<grid, kScanThreads, 0, st>>>(p);
-    else      k_scan_count_direct<false><<<grid, kScanThreads, 0, st>>>(p);
+    if (ix->mode == PK_MODE_DIRECT) {
+        {
+            prof_scope ps(ix, st, PROF_SCAN_DIRECT);
+            if (wide) k_scan_count_direct<true><<<grid, kScanThreads, 0, st>>>(p);
+            else      k_scan_count_direct<false><<<grid, kScanThreads, 0, st>>>(p);
+        }
+        PK_CUDA(cudaGetLastError());
+        ix->launches += 1;
+    } else {
+        if (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap) {
+            const int rc = indexer_flush(ix, st, false);
+            if (rc != PK_OK) return rc;
+        }
+        const int f = ix->nseg;
+        p.win_log2 = ix->win_log2; p.nbuckets = ix->nbuckets; p.pool = ix->pool;
+        p.seg_cnt = seg_cnt(ix, f); p.seg_off = seg_off(ix, f); p.seg_fill = seg_fill(ix, f);
+        const size_t smem1 = (size_t)ix->nbuckets * sizeof(uint32_t);
+        const size_t smem2 = scatter_smem_bytes(ix->nbuckets);
+        if (!ix->scatter_smem_set) {
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            ix->scatter_smem_set = true;
+        }
+        {
+            prof_scope ps(ix, st, PROF_BUCKET_COUNT);
+            if (wide) k_scan_bucket_count<true><<<grid, kScanThreads, smem1, st>>>(p);
+            else      k_scan_bucket_count<false><<<grid, kScanThreads, smem1, st>>>(p);
+        }
+        {
+            prof_scope ps(ix, st, PROF_OFFSETS);
+            k_bucket_offsets<<<1, 256, 0, st>>>(p.seg_cnt, seg_off(ix, f), ix->nbuckets, ix->cursor);
+        }
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 4));
+        {
+            prof_scope ps(ix, st, PROF_SCATTER);
+            if (wide) k_scan_scatter<true><<<grid2, kScanThreads, smem2, st>>>(p);
+            else      k_scan_scatter<false><<<grid2, kScanThreads, smem2, st>>>(p);
+        }
+        PK_CUDA(cudaGetLastError());
+        ix->launches += 3;
+        ix->nseg++;
+        ix->pool_ub += n;
+        ix->stats_valid = false;
+    }
+    {
+        prof_scope ps(ix, st, PROF_CARRY);
+        k_update_carry<<<1, 32, 0, st>>>(ix->carry, seq_dev, n);
+    }
     PK_CUDA(cudaGetLastError());
-    k_update_carry<<<1, 32, 0, st>>>(ix->carry, seq_dev, n);
-    PK_CUDA(cudaGetLastError());
-    ix->launches += 2;
+    ix->launches += 1;
     ix->stream_off += n;
     ix->fed = true;
     ix->last_stream = st;
     return PK_OK;
 }
 
-// make work_stream wait for whatever the caller's stream was last given
-static int indexer_join(pk_indexer *ix) {
-    if (ix->last_stream != ix->work_stream) {
-        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
-        PK_CUDA(cudaStreamWaitEvent(ix->work_stream, ix->joined, 0));
-        ix->last_stream = ix->work_stream;
+// feeds are cut so that one partition pass never exceeds kMaxFeed bases
+static int indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st) {
+    const size_t step = ix->mode == PK_MODE_PARTITION ? std::min(kMaxFeed, ix->pool_cap) : n;
+    size_t off = 0;
+    while (off < n) {
+        const size_t len = std::min(step, n - off);
+        const int rc = indexer_launch_scan(ix, seq_dev + off, len, st);
+        if (rc != PK_OK) return rc;
+        off += len;
     }
     return PK_OK;
 }
@@ -313,8 +707,8 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     if (range_hi == 0) range_hi = T;
     PK_REQUIRE(range_lo < range_hi && range_hi <= T, "pk_indexer_create: bad range [%llu, %llu) for 4^K = %llu",
                (unsigned long long)range_lo, (unsigned long long)range_hi, (unsigned long long)T);
-    PK_REQUIRE(mode == PK_MODE_AUTO || mode == PK_MODE_DIRECT,
-               "pk_indexer_create: mode %d not available in this build", mode);
+    PK_REQUIRE(mode == PK_MODE_AUTO || mode == PK_MODE_DIRECT || mode == PK_MODE_PARTITION,
+               "pk_indexer_create: unknown mode %d", mode);
     int ndev = 0;
     PK_CUDA(cudaGetDeviceCount(&ndev));
     PK_REQUIRE(device >= 0 && device < ndev, "pk_indexer_create: device %d of %d", device, ndev);
@@ -324,9 +718,29 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     pk_indexer *ix = new (std::nothrow) pk_indexer();
     if (!ix) return pk_set_error(PK_ERR_NOMEM, "out of host memory");
     ix->K = kmer_len; ix->device = device; ix->lo = range_lo; ix->hi = range_hi;
-    ix->mode = PK_MODE_DIRECT;
     ix->table_bytes = (size_t)(range_hi - range_lo);
     ix->sm_count = pk_sm_count(device);
+
+    // window size: 2^24 counters (64 MiB of u32) stay L2-resident on B200; the
+    // environment override exists so that tests can force many windows on small tables
+    uint32_t win_log2 = 24;
+    if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
+        const int v = atoi(env);
+        if (v >= 4 && v <= 24) win_log2 = (uint32_t)v;
+    }
+    const uint64_t nb = (ix->table_bytes + ((1ull << win_log2) - 1)) >> win_log2;
+    if (mode == PK_MODE_AUTO)
+        mode = (ix->table_bytes > (1ull << 26) && nb <= (uint64_t)kMaxBuckets) ? PK_MODE_PARTITION
+                                                                              : PK_MODE_DIRECT;
+    if (mode == PK_MODE_PARTITION && nb > (uint64_t)kMaxBuckets) {
+        delete ix;
+        return pk_set_error(PK_ERR_ARG, "pk_indexer_create: range needs %llu windows, at most %d "
+                            "are supported in PARTITION mode", (unsigned long long)nb, kMaxBuckets);
+    }
+    ix->mode = mode;
+    ix->win_log2 = win_log2;
+    ix->nbuckets = (uint32_t)nb;
+
     const size_t alloc = (ix->table_bytes + 255) & ~(size_t)255;
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
@@ -342,8 +756,29 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     }
     step(cudaEventCreateWithFlags(&ix->joined, cudaEventDisableTiming));
     ix->last_stream = ix->work_stream;
+    if (mode == PK_MODE_PARTITION && e == cudaSuccess) {
+        size_t free_b = 0, total_b = 0;
+        step(cudaMemGetInfo(&free_b, &total_b));
+        size_t cap = (size_t)1 << 30;                      // 2^30 entries = 4 GiB
+        if (const char *env = getenv("PYKMER_B200_POOL_LOG2")) {
+            const int v = atoi(env);
+            if (v >= 12 && v <= 30) cap = (size_t)1 << v;
+        }
+        while (cap > ((size_t)1 << 20) && cap * sizeof(uint32_t) > free_b / 4) cap >>= 1;
+        ix->pool_cap = cap;
+        const size_t seg_bytes = (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t);
+        step(cudaMalloc(&ix->pool, cap * sizeof(uint32_t)));
+        step(cudaMalloc(&ix->seg, seg_bytes));
+        step(cudaMalloc(&ix->cursor, 256));
+        step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+        if (e == cudaSuccess) {
+            step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
+            step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));
+            step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
+        }
+    }
     if (e == cudaSuccess) {
-        step(cudaMemsetAsync(ix->table, 0, alloc, ix->work_stream));
+        if (mode == PK_MODE_DIRECT) step(cudaMemsetAsync(ix->table, 0, alloc, ix->work_stream));
         step(cudaMemsetAsync(ix->carry, 0, 64, ix->work_stream));
         step(cudaMemsetAsync(ix->counters, 0, 257 * sizeof(unsigned long long), ix->work_stream));
         step(cudaStreamSynchronize(ix->work_stream));
@@ -368,12 +803,14 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->table); cudaFree(ix->carry); cudaFree(ix->counters);
     cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
+    cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
     for (int i = 0; i < 2; i++) {
         if (ix->copied[i]) cudaEventDestroy(ix->copied[i]);
         if (ix->consumed[i]) cudaEventDestroy(ix->consumed[i]);
     }
     if (ix->joined) cudaEventDestroy(ix->joined);
+    for (cudaEvent_t e : ix->prof_events) cudaEventDestroy(e);
     if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->work_stream) cudaStreamDestroy(ix->work_stream);
     delete ix;
@@ -391,7 +828,17 @@ PK_API int pk_indexer_reset(pk_indexer *ix, pk_stream stream) {
     }
     PK_CUDA(cudaEventRecord(ix->joined, ix->work_stream));
     PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
-    PK_CUDA(cudaMemsetAsync(ix->table, 0, ix->table_bytes, st));
+    if (ix->mode == PK_MODE_DIRECT) {
+        PK_CUDA(cudaMemsetAsync(ix->table, 0, ix->table_bytes, st));
+    } else {
+        // the first flush rewrites every window, so the table itself needs no memset
+        PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
+        PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
+        ix->nseg = 0;
+        ix->pool_ub = 0;
+        ix->table_valid = false;
+        ix->stats_valid = false;
+    }
     PK_CUDA(cudaMemsetAsync(ix->carry, 0, 64, st));
     PK_CUDA(cudaMemsetAsync(ix->counters, 0, 257 * sizeof(unsigned long long), st));
     if (ix->nrec) PK_CUDA(cudaMemsetAsync(ix->rec_flags, 0, ix->nrec, st));
@@ -447,7 +894,7 @@ PK_API int pk_indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t
         PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
         PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
     }
-    return indexer_launch_scan(ix, seq_dev, n, st);
+    return indexer_feed_device(ix, seq_dev, n, st);
 }
 
 PK_API int pk_indexer_feed_host(pk_indexer *ix, const uint8_t *seq_host, size_t n) {
@@ -472,7 +919,7 @@ PK_API int pk_indexer_feed_host(pk_indexer *ix, const uint8_t *seq_host, size_t 
                                 ix->copy_stream));
         PK_CUDA(cudaEventRecord(ix->copied[buf], ix->copy_stream));
         PK_CUDA(cudaStreamWaitEvent(ix->work_stream, ix->copied[buf], 0));
-        const int rc = indexer_launch_scan(ix, ix->stage[buf], len, ix->work_stream);
+        const int rc = indexer_feed_device(ix, ix->stage[buf], len, ix->work_stream);
         if (rc != PK_OK) return rc;
         PK_CUDA(cudaEventRecord(ix->consumed[buf], ix->work_stream));
         off += len;
@@ -502,10 +949,18 @@ PK_API int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t 
         if (rc != PK_OK) return rc;
     }
     cudaStream_t st = ix->work_stream;
-    PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
-    k_table_stats<<<ix->sm_count * 8, 256, 0, st>>>(ix->table, ix->table_bytes, ix->counters + 1);
-    PK_CUDA(cudaGetLastError());
-    ix->launches += 1;
+    if (ix->mode == PK_MODE_PARTITION && (ix->nseg || !ix->table_valid || !ix->stats_valid)) {
+        const int rc = indexer_flush(ix, st, true);        // statistics fused into the commit
+        if (rc != PK_OK) return rc;
+    } else if (ix->mode == PK_MODE_DIRECT) {
+        PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
+        {
+            prof_scope ps(ix, st, PROF_TABLE_STATS);
+            k_table_stats<<<ix->sm_count * 8, 256, 0, st>>>(ix->table, ix->table_bytes, ix->counters + 1);
+        }
+        PK_CUDA(cudaGetLastError());
+        ix->launches += 1;
+    }
     PK_CUDA(cudaMemcpyAsync(ix->h_counters, ix->counters, 257 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaStreamSynchronize(st));
@@ -543,6 +998,9 @@ PK_API int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t of
     PK_REQUIRE(offset <= ix->table_bytes && bytes <= ix->table_bytes - offset,
                "pk_indexer_table_to_host: [%zu, +%zu) outside %zu table bytes", offset, bytes,
                ix->table_bytes);
+    if (ix->mode == PK_MODE_PARTITION && (ix->nseg || !ix->table_valid))
+        return pk_set_error(PK_ERR_STATE, "pk_indexer_table_to_host: call pk_indexer_finalize first "
+                            "(k-mers are still buffered)");
     pk_device_guard guard(ix->device);
     {
         const int rc = indexer_join(ix);
@@ -556,6 +1014,43 @@ PK_API int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t of
 PK_API int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches) {
     PK_REQUIRE(ix != nullptr && launches != nullptr, "pk_indexer_launch_count: NULL argument");
     *launches = ix->launches;
+    return PK_OK;
+}
+
+static void prof_clear(pk_indexer *ix) {
+    for (cudaEvent_t e : ix->prof_events) cudaEventDestroy(e);
+    ix->prof_events.clear();
+    ix->prof_tags.clear();
+}
+
+PK_API int pk_indexer_set_profiling(pk_indexer *ix, int enable) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_set_profiling: NULL handle");
+    pk_device_guard guard(ix->device);
+    prof_clear(ix);
+    ix->profiling = enable != 0;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_profile(pk_indexer *ix, double ms_host[8], uint32_t launches_host[8]) {
+    PK_REQUIRE(ix != nullptr && ms_host != nullptr && launches_host != nullptr,
+               "pk_indexer_profile: NULL argument");
+    pk_device_guard guard(ix->device);
+    PK_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 8; i++) { ms_host[i] = 0.0; launches_host[i] = 0; }
+    for (size_t i = 0; i < ix->prof_tags.size(); i++) {
+        float ms = 0.f;
+        PK_CUDA(cudaEventElapsedTime(&ms, ix->prof_events[2 * i], ix->prof_events[2 * i + 1]));
+        ms_host[ix->prof_tags[i]] += ms;
+        launches_host[ix->prof_tags[i]] += 1;
+    }
+    prof_clear(ix);
+    return PK_OK;
+}
+
+PK_API int pk_indexer_mode(pk_indexer *ix, int *mode, int *windows) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_mode: NULL handle");
+    if (mode) *mode = ix->mode;
+    if (windows) *windows = ix->mode == PK_MODE_PARTITION ? (int)ix->nbuckets : 0;
     return PK_OK;
 }
 

@@ -112,3 +112,58 @@ PK_HD uint32_t pk_fwd32_at(uint64_t cat /* pc1:cc */, int j, uint32_t mask) {
 PK_HD uint32_t pk_rc32_at(uint64_t rcat /* r0:r1 */, int j, int K, uint32_t mask) {
     return (uint32_t)(rcat >> (34 + 2 * j - 2 * K)) & mask;      // 2 <= shift <= 62 for K <= 16
 }
+
+// ---------------------------------------------------------------------------------------
+// All windows that END inside one 16-base group, given the group's own encoding
+// (cc, cv) and its one or two predecessors.  Windows whose canonical value lies in
+// [lo, hi) are counted; consecutive equal canonical values are merged into runs.
+//   emit(slot, off, cnt)   one run: off = canon - lo, cnt = 1..16 windows.  `slot`
+//                          (0..16) is a compile-time constant after unrolling, so a
+//                          caller may keep per-slot state in registers.
+//   on_window(j, fresh)    once per counted window; fresh = an invalid base (e.g. a
+//                          record separator) passed since the previous counted window
+//                          of this group, or this is the group's first one.
+// Returns the number of counted windows (indexer.py:342 num_kmers += 1).
+template <bool WIDE, typename Emit, typename OnWindow>
+PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t hi, uint32_t cc, uint32_t cv,
+                             uint32_t pc1, uint32_t pv1, uint32_t pc2, uint32_t pv2,
+                             Emit emit, OnWindow on_window) {
+    const uint64_t vcat = ((uint64_t)pv2 << 32) | ((uint64_t)pv1 << 16) | cv;
+    const uint32_t Wm = (uint32_t)pk_valid_windows(vcat, K) & 0xFFFFu;
+    if (!Wm) return 0;
+    const uint32_t r0 = pk_rcw(cc), r1 = pk_rcw(pc1), r2 = WIDE ? pk_rcw(pc2) : 0u;
+    const uint64_t cat = ((uint64_t)pc1 << 32) | cc;
+    const uint64_t rcat = ((uint64_t)r0 << 32) | r1;
+    const uint32_t mask32 = (uint32_t)pk_kmer_mask(K);
+    uint64_t prev = ~0ull;
+    uint32_t pend = 0, counted = 0;
+    bool fresh = true;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (!((cv >> (15 - j)) & 1u)) fresh = true;
+        if (!((Wm >> (15 - j)) & 1u)) continue;
+        uint64_t canon;
+        if (WIDE) {
+            const uint64_t f = pk_fwd_at(pc2, pc1, cc, j, K);
+            const uint64_t r = pk_rc_at(r2, r1, r0, j, K);
+            canon = f < r ? f : r;                               // indexer.py:341
+        } else {
+            const uint32_t f = pk_fwd32_at(cat, j, mask32);
+            const uint32_t r = pk_rc32_at(rcat, j, K, mask32);
+            canon = f < r ? f : r;
+        }
+        if (canon < lo || canon >= hi) continue;                 // another shard's k-mer
+        counted++;
+        on_window(j, fresh);
+        fresh = false;
+        if (canon == prev) {
+            pend++;
+        } else {
+            if (pend) emit(j, prev - lo, pend);
+            prev = canon;
+            pend = 1;
+        }
+    }
+    if (pend) emit(16, prev - lo, pend);
+    return counted;
+}

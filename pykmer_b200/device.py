@@ -126,6 +126,25 @@ class Indexer:
         nat.check(lib.pk_indexer_table_to_host(self._h, p, offset, nbytes))
         return dst
 
+    def mode(self) -> Tuple[int, int]:
+        """(counting scheme in use, number of table windows)."""
+        m, w = ctypes.c_int(0), ctypes.c_int(0)
+        nat.check(lib.pk_indexer_mode(self._h, ctypes.byref(m), ctypes.byref(w)))
+        return m.value, w.value
+
+    PROFILE_CLASSES = ("scan_count_direct", "scan_bucket_count", "bucket_offsets", "scan_scatter",
+                       "window_count", "window_commit", "table_stats", "update_carry")
+
+    def set_profiling(self, enable: bool) -> None:
+        nat.check(lib.pk_indexer_set_profiling(self._h, 1 if enable else 0))
+
+    def profile(self) -> dict:
+        """{kernel class: (total ms, launches)} since profiling was enabled / last read."""
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.uint32)
+        nat.check(lib.pk_indexer_profile(self._h, ms.ctypes.data, cnt.ctypes.data))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.PROFILE_CLASSES) if cnt[i]}
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64(0)
         nat.check(lib.pk_indexer_launch_count(self._h, ctypes.byref(n)))

@@ -71,6 +71,59 @@ int main() {
             }
         }
     }
-    printf("ok: %ld windows checked, %ld valid\n", checked, valid);
+    // pk_scan_group: runs expanded back must equal the per-window brute force, per group
+    long runs = 0, slots_ok = 0;
+    for (int K = 1; K <= 31; K += 2) {
+        const uint64_t T = 1ull << (2 * K);
+        const uint64_t los[2] = {0, T / 4}, his[2] = {T, T / 2 + 7};
+        for (int rg = 0; rg < 2; rg++) {
+            const uint64_t lo = los[rg], hi = his[rg];
+            for (size_t g = 2; g < groups; g++) {
+                std::vector<uint64_t> want, got;
+                std::vector<int> fresh_want, fresh_got;
+                bool fresh = true;
+                for (int j = 0; j < 16; j++) {
+                    size_t e = 16 * g + j;
+                    if (code_of(seq[e]) < 0) fresh = true;
+                    bool ok = true;
+                    uint64_t fwd = 0, rev = 0;
+                    for (int p = 0; p < K; p++) {
+                        int c = code_of(seq[e - K + 1 + p]);
+                        if (c < 0) { ok = false; break; }
+                        fwd += ((uint64_t)c) << (2 * (K - 1 - p));
+                        rev += ((uint64_t)(3 - c)) << (2 * p);
+                    }
+                    if (!ok) continue;
+                    uint64_t canon = fwd < rev ? fwd : rev;
+                    if (canon < lo || canon >= hi) continue;
+                    want.push_back(canon - lo);
+                    fresh_want.push_back(fresh ? 1 : 0);
+                    fresh = false;
+                }
+                int last_slot = -1;
+                bool slot_order = true;
+                auto emit = [&](int slot, uint64_t off, uint32_t cnt) {
+                    if (slot <= last_slot || slot > 16 || cnt < 1 || cnt > 16) slot_order = false;
+                    last_slot = slot;
+                    runs++;
+                    for (uint32_t c = 0; c < cnt; c++) got.push_back(off);
+                };
+                auto onw = [&](int, bool f) { fresh_got.push_back(f ? 1 : 0); };
+                uint32_t n;
+                if (K > 16)
+                    n = pk_scan_group<true>(K, lo, hi, codes[g], vm[g], codes[g - 1], vm[g - 1],
+                                            codes[g - 2], vm[g - 2], emit, onw);
+                else
+                    n = pk_scan_group<false>(K, lo, hi, codes[g], vm[g], codes[g - 1], vm[g - 1],
+                                             0u, 0u, emit, onw);
+                if (!slot_order || n != want.size() || got != want || fresh_got != fresh_want) {
+                    printf("scan_group mismatch K=%d g=%zu range %d: n=%u want=%zu\n", K, g, rg, n, want.size());
+                    return 1;
+                }
+                slots_ok++;
+            }
+        }
+    }
+    printf("ok: %ld windows checked, %ld valid; %ld groups scanned, %ld runs\n", checked, valid, slots_ok, runs);
     return 0;
 }

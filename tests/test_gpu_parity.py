@@ -26,10 +26,22 @@ def env():
     return {"torch": torch, "oracle": oracle, "dev": device, "nat": _native}
 
 
-def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0):
+def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0,
+                  window_log2=None, pool_log2=None):
     import torch
     hi = 4 ** K if hi is None else hi
-    with dev.Indexer(K, device=0, range_lo=lo, range_hi=hi, mode=mode) as ix:
+    # test hooks of the library: small table windows / small k-mer buffer (read at create time)
+    for name, val in (("PYKMER_B200_WINDOW_LOG2", window_log2), ("PYKMER_B200_POOL_LOG2", pool_log2)):
+        if val is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = str(val)
+    try:
+        ix = dev.Indexer(K, device=0, range_lo=lo, range_hi=hi, mode=mode)
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+        os.environ.pop("PYKMER_B200_POOL_LOG2", None)
+    with ix:
         if starts is not None:
             ix.set_records(starts)
         cuts = [0, len(stream)] if not pieces else [0] + sorted(pieces) + [len(stream)]
@@ -387,3 +399,146 @@ def test_indexer_scaled_config2_vs_oracle(env):
     # size-independent properties of any index
     assert st["vals_sum"] <= st["num_kmers"] and sum(hist) == st["vals_count"]
     assert st["vals_min"] == 0
+
+
+# ------------------------------------------------------------------ PARTITION counting mode
+
+PART = 2   # PK_MODE_PARTITION
+
+
+@pytest.mark.parametrize("K,wlog", [(5, 4), (5, 24), (9, 6), (9, 10), (11, 10), (11, 16), (13, 14), (13, 24)])
+@pytest.mark.parametrize("n", [0, 17, 4000, 100_003, 1_000_003])
+@pytest.mark.parametrize("plog", [12, 30])
+def test_partition_mode_random_streams_vs_oracle(env, K, wlog, n, plog):
+    """Window-partitioned counting (many windows, and a tiny k-mer buffer that forces
+    repeated saturating flushes) gives the oracle's table, statistics and num_kmers."""
+    if plog == 12 and n > 200_000:
+        pytest.skip("tiny buffer only on the smaller streams")
+    rng = np.random.default_rng(31 * K + n + wlog)
+    s = _random_stream(rng, n)
+    want, num, _ = env["oracle"].index_stream(s, K)
+    table, hist, st, _ = _index_stream(env["dev"], s, K, mode=PART, window_log2=wlog, pool_log2=plog)
+    assert st["num_kmers"] == num
+    assert np.array_equal(table, want)
+    oh, ost = env["oracle"].table_stats(want)
+    assert hist == oh and all(st[k] == ost[k] for k in ("vals_sum", "vals_count", "vals_min", "vals_max"))
+
+
+@pytest.mark.parametrize("case", ["tiny_mixed.fa.07", "saturating.fa.gz.11", "allkmers_07.fasta.gz.07",
+                                  "rand200k.fa.bgz.11"])
+def test_partition_mode_matches_reference_golden(env, case):
+    from pykmer_b200 import fasta
+    fname, kk = case.rsplit(".", 1)
+    K = int(kk)
+    gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
+    stream, names, starts, lengths = fasta.read_fasta_stream(os.path.join(GOLD, "inputs", fname))
+    wlog = 4 if K <= 7 else 12
+    for pieces in (None, [7, 100, 101, 5000]):
+        pieces = [c for c in (pieces or []) if c < len(stream)] or None
+        table, hist, st, flags = _index_stream(env["dev"], stream, K, starts=starts, mode=PART,
+                                               window_log2=wlog, pieces=pieces)
+        assert st["num_kmers"] == gold["num_kmers"] and hist == gold["hist"]
+        assert hashlib.sha256(table.tobytes()).hexdigest() == gold["output_file_cheksum"]
+        chrom = [[names[i], lengths[i]] for i in range(len(names)) if flags[i]]
+        assert chrom == gold["chromosomes"]
+
+
+@pytest.mark.parametrize("K", [17, 19, 31])
+def test_partition_mode_wide_k_range(env, K):
+    rng = np.random.default_rng(K + 500)
+    parts = []
+    for _ in range(600):
+        parts.append(np.full(int(rng.integers(K - 3, 3 * K)), ord("A"), dtype=np.uint8))
+        parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 12)))])
+    s = np.concatenate(parts)
+    hi = 1 << 22
+    want, num, _ = env["oracle"].index_stream(s, K, range_hi=hi)
+    for host in (False, True):
+        table, hist, st, _ = _index_stream(env["dev"], s, K, hi=hi, mode=PART, window_log2=12, host=host,
+                                           pieces=[1000, 1001, 20_000])
+        assert st["num_kmers"] == num and np.array_equal(table, want)
+
+
+def test_partition_mode_feed_after_finalize_and_reset(env):
+    import torch
+    rng = np.random.default_rng(12)
+    dev, oracle = env["dev"], env["oracle"]
+    a, b = _random_stream(rng, 40_000), _random_stream(rng, 30_000)
+    os.environ["PYKMER_B200_WINDOW_LOG2"] = "10"
+    try:
+        ix = dev.Indexer(9, mode=PART)
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+    with ix:
+        assert ix.mode() == (PART, 4 ** 9 >> 10)
+        ix.feed_device(torch.from_numpy(a).cuda())
+        h1, s1 = ix.finalize()
+        w1, n1, _ = oracle.index_stream(a, 9)
+        assert np.array_equal(ix.table_to_host().numpy(), w1) and s1["num_kmers"] == n1
+        assert ix.finalize() == (h1, s1)                       # idempotent
+        ix.feed_device(torch.from_numpy(b).cuda())             # keeps accumulating (saturating)
+        with pytest.raises(RuntimeError):
+            ix.table_to_host()                                 # k-mers still buffered
+        h2, s2 = ix.finalize()
+        w2, n2, _ = oracle.index_stream(np.concatenate([a, b]), 9)
+        assert np.array_equal(ix.table_to_host().numpy(), w2) and s2["num_kmers"] == n2
+        assert h2 == oracle.table_stats(w2)[0]
+        ix.reset()
+        ix.feed_device(torch.from_numpy(b).cuda())
+        h3, s3 = ix.finalize()
+        w3, n3, _ = oracle.index_stream(b, 9)
+        assert np.array_equal(ix.table_to_host().numpy(), w3) and s3["num_kmers"] == n3
+
+
+def test_auto_mode_picks_partition_for_k15(env):
+    with env["dev"].Indexer(15) as ix:
+        assert ix.mode() == (PART, 64)
+    with env["dev"].Indexer(11) as ix:
+        assert ix.mode()[0] == 1
+
+
+def test_indexer_scaled_config2_both_modes(env):
+    """1/16-scale config 2 stream, K=15, full table: DIRECT == PARTITION == oracle."""
+    from pykmer_b200 import synth
+    dev, oracle = env["dev"], env["oracle"]
+    recs = synth.syn782m_records(scale=1 / 16)
+    stream, starts, lengths, names = synth.records_to_stream(recs)
+    want, num, _ = oracle.index_stream(stream, 15, method="mt", threads=oracle.max_threads())
+    for mode in (1, 2):
+        table, hist, st, flags = _index_stream(dev, stream, 15, starts=starts, mode=mode)
+        assert st["num_kmers"] == num and flags.all()
+        assert np.array_equal(table, want), f"mode {mode}"
+        assert hist == oracle.table_stats(want, threads=oracle.max_threads())[0]
+
+
+def test_full_size_config2_modes_agree(env):
+    """BASELINE config 2 at full size (782.5 Mbp, K=15, 1 GiB table): the two independent
+    counting schemes produce the same table; size-independent invariants hold."""
+    import torch
+    import bench
+    dev = env["dev"]
+    stream, starts, lengths = bench.load_stream(1.0, 0, 1)
+    d = torch.from_numpy(stream).cuda()
+    digests, stats = [], []
+    for mode in (1, 2):
+        with dev.Indexer(15, mode=mode) as ix:
+            ix.set_records(starts)
+            ix.feed_device(d)
+            hist, st = ix.finalize()
+            assert ix.record_flags().all()
+            p, n = ix.table_ptr()
+            t = torch.empty(0, dtype=torch.uint8, device="cuda")
+            host = ix.table_to_host().numpy()
+            digests.append(hashlib.sha256(host.tobytes()).hexdigest())
+            stats.append((hist, st))
+            assert st["vals_sum"] <= st["num_kmers"] and sum(hist) == st["vals_count"]
+            assert st["vals_sum"] == sum((i + 1) * h for i, h in enumerate(hist))
+            assert st["vals_min"] == 0 and st["vals_max"] == 255
+            assert st["num_kmers"] <= sum(max(0, l - 14) for l in lengths)
+            # canonical k-mers only: an entry whose reverse complement is smaller must be 0
+            idx = np.random.default_rng(0).integers(0, 4 ** 15, size=200_000)
+            rc = np.zeros_like(idx)
+            for q in range(15):
+                rc |= (3 - ((idx >> (2 * q)) & 3)) << (2 * (14 - q))
+            assert not host[idx[idx > rc]].any()
+    assert digests[0] == digests[1] and stats[0] == stats[1]
