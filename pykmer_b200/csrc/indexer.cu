@@ -53,8 +53,8 @@ struct ScanParams {
     size_t n;
     const uint8_t *carry;     // last kCarry bytes of everything fed before
     int K;
-    uint64_t lo, hi;          // canonical range owned by this handle
-    uint8_t *table;           // [hi - lo]                               (DIRECT)
+    uint64_t lo, span;        // canonical range [lo, lo + span) owned by this handle
+    uint8_t *table;           // [span]                                  (DIRECT)
     unsigned long long *num_kmers;
     const uint64_t *rec_starts;
     size_t nrec;
@@ -114,19 +114,16 @@ __device__ __forceinline__ long long find_record(const uint64_t *starts, size_t 
     return (long long)lo - 1;
 }
 
-// indexer.py:349-351: a record is listed once a k-mer of it has been counted
-struct RecordFlagger {
-    const ScanParams &p;
-    long long g;
-    __device__ __forceinline__ void operator()(int j, bool fresh) const {
-        if (!fresh || !p.rec_flags) return;
+// indexer.py:349-351: a record is listed once a k-mer of it has been counted.  Runs of
+// counted windows separated by an invalid base (a separator, maybe) are looked up apart.
+__device__ __forceinline__ void flag_records(const ScanParams &p, long long g, uint32_t cv,
+                                             uint32_t counted) {
+    if (!p.rec_flags || !counted) return;
+    pk_for_each_record_run(cv, counted, [&](int j) {
         const long long r = find_record(p.rec_starts, p.nrec, p.stream_off + (uint64_t)g * 16 + j);
         if (r >= 0 && !p.rec_flags[r]) p.rec_flags[r] = 1;
-    }
-};
-struct NoFlags {
-    __device__ __forceinline__ void operator()(int, bool) const {}
-};
+    });
+}
 
 // One warp tile: lane l encodes group tile*GPW - H + l and receives its halo by shuffle.
 template <bool WIDE>
@@ -161,7 +158,7 @@ __device__ __forceinline__ void add_num_kmers(unsigned long long *dst, unsigned 
 }
 
 // ------------------------------------------------------------------------------ DIRECT
-template <bool WIDE>
+template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanParams p) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
@@ -176,17 +173,18 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanPa
         WT t;
         t.load(p, tile, ngroups, lut);
         if (!t.emits) continue;
-        counted += pk_scan_group<WIDE>(
-            p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
-            [&](int, uint64_t off, uint32_t cnt) { sat_add_u8(p.table, off, cnt); },
-            RecordFlagger{p, t.g});
+        const uint32_t cm = pk_scan_group<WIDE, FULL>(
+            p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+            [&](int, uint64_t off, uint32_t cnt) { sat_add_u8(p.table, off, cnt); });
+        counted += __popc(cm);
+        flag_records(p, t.g, t.cv, cm);
     }
     add_num_kmers(p.num_kmers, counted);
 }
 
 // ------------------------------------------------------------------------------ PARTITION
 // pass 1: per-window entry counts of this feed (+ num_kmers and record flags)
-template <bool WIDE>
+template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanParams p) {
     extern __shared__ uint32_t sm[];
     uint32_t *s_cnt = sm;                                  // [nbuckets]
@@ -205,10 +203,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanPa
         WT t;
         t.load(p, tile, ngroups, lut);
         if (!t.emits) continue;
-        counted += pk_scan_group<WIDE>(
-            p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
-            [&](int, uint64_t off, uint32_t) { atomicAdd(&s_cnt[(uint32_t)(off >> wl)], 1u); },
-            RecordFlagger{p, t.g});
+        const uint32_t cm = pk_scan_group<WIDE, FULL>(
+            p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+            [&](int, auto off, uint32_t) { atomicAdd(&s_cnt[(uint32_t)(off >> wl)], 1u); });
+        counted += __popc(cm);
+        flag_records(p, t.g, t.cv, cm);
     }
     add_num_kmers(p.num_kmers, counted);
     __syncthreads();
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restri
 // pass 2: the same scan again; entries are ranked per window in shared memory, staged
 // window by window, and written out as contiguous runs into the segments pass 1 sized.
 // entry = (run length - 1) << 24 | offset inside the window.
-template <bool WIDE>
+template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams p) {
     extern __shared__ uint32_t sm[];
     const uint32_t nb = p.nbuckets;
@@ -274,15 +273,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams 
             WT t;
             t.load(p, tile, ngroups, lut);
             if (t.emits)
-                pk_scan_group<WIDE>(
-                    p.K, p.lo, p.hi, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
-                    [&](int slot, uint64_t off, uint32_t cnt) {
+                pk_scan_group<WIDE, FULL>(
+                    p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+                    [&](int slot, auto off, uint32_t cnt) {
                         const uint32_t b = (uint32_t)(off >> wl);
                         const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
                         ent[slot] = ((uint32_t)off & wmask) | ((cnt - 1u) << 24);
                         key[slot] = (b << 16) | rank;
-                    },
-                    NoFlags{});
+                    });
         }
         __syncthreads();
         // B: exclusive scan over the windows; reserve the tile's share of every segment
@@ -355,61 +353,78 @@ __global__ void __launch_bounds__(256) k_window_count(const uint32_t *__restrict
 
 // per window: table = min(255, [table +] counters) (indexer.py:239,262), counters back to
 // zero, and -- when bins != NULL -- the histogram of the bytes just written
-// (tools.py:250), so the final table is never read back.
+// (tools.py:250), so the final table is never read back.  One thread turns four
+// consecutive counters (one 16-byte load, coalesced across the warp) into four table
+// bytes; four independent loads are in flight per thread.
+__device__ __forceinline__ uint32_t commit_quad(const uint4 c, uint32_t old, bool accum) {
+    uint32_t v0 = c.x, v1 = c.y, v2 = c.z, v3 = c.w;
+    if (accum) {
+        v0 += old & 0xFFu; v1 += (old >> 8) & 0xFFu; v2 += (old >> 16) & 0xFFu; v3 += old >> 24;
+    }
+    return min(v0, 255u) | (min(v1, 255u) << 8) | (min(v2, 255u) << 16) | (min(v3, 255u) << 24);
+}
+
 template <bool ACCUM>
 __global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ scratch,
                                                        uint8_t *__restrict__ table, size_t n,
                                                        unsigned long long *__restrict__ bins) {
     __shared__ uint32_t sh[8][256];
-    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
-    __syncthreads();
+    if (bins) {
+        for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5;
     uint32_t c1 = 0, c2 = 0, c3 = 0;
-    const size_t nvec = n / 16;
+    const size_t nq = n / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     uint4 *sv = reinterpret_cast<uint4 *>(scratch);
-    uint4 *tv = reinterpret_cast<uint4 *>(table);
+    uint32_t *tw = reinterpret_cast<uint32_t *>(table);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        uint32_t out[4];
-        uint4 old = zero;
-        if (ACCUM) old = tv[i];
-        const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint4 c = sv[4 * i + k];
-            sv[4 * i + k] = zero;
-            const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-            uint32_t x = 0;
+    constexpr int U = 4;
+    auto tally = [&](uint32_t x) {
+        if (!bins || !x) return;
+        c1 += __popc(__vcmpeq4(x, 0x01010101u)) >> 3;
+        c2 += __popc(__vcmpeq4(x, 0x02020202u)) >> 3;
+        c3 += __popc(__vcmpeq4(x, 0x03030303u)) >> 3;
+        if (x & 0xFCFCFCFCu) {
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                uint32_t val = cw[b];
-                if (ACCUM) val += (ow[k] >> (8 * b)) & 0xFFu;
-                x |= min(val, 255u) << (8 * b);
-            }
-            out[k] = x;
-            if (bins && x) {
-                c1 += __popc(__vcmpeq4(x, 0x01010101u)) >> 3;
-                c2 += __popc(__vcmpeq4(x, 0x02020202u)) >> 3;
-                c3 += __popc(__vcmpeq4(x, 0x03030303u)) >> 3;
-                if (x & 0xFCFCFCFCu) {
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const uint32_t val = (x >> (8 * b)) & 0xFFu;
-                        if (val > 3u) atomicAdd(&sh[warp][val], 1u);
-                    }
-                }
+                const uint32_t val = (x >> (8 * b)) & 0xFFu;
+                if (val > 3u) atomicAdd(&sh[warp][val], 1u);
             }
         }
-        tv[i] = make_uint4(out[0], out[1], out[2], out[3]);
+    };
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < nq; i += U * stride) {
+        uint4 c[U];
+        uint32_t old[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            c[u] = __ldcg(sv + i + u * stride);
+            old[u] = ACCUM ? tw[i + u * stride] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t x = commit_quad(c[u], old[u], ACCUM);
+            sv[i + u * stride] = zero;
+            __stcs(tw + i + u * stride, x);
+            tally(x);
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {            // < 16 tail entries
-        for (size_t i = nvec * 16; i < n; i++) {
-            uint32_t val = scratch[i];
-            scratch[i] = 0;
-            if (ACCUM) val += table[i];
+    for (; i < nq; i += stride) {
+        const uint4 c = __ldcg(sv + i);
+        const uint32_t x = commit_quad(c, ACCUM ? tw[i] : 0u, ACCUM);
+        sv[i] = zero;
+        __stcs(tw + i, x);
+        tally(x);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {            // < 4 tail entries
+        for (size_t k = nq * 4; k < n; k++) {
+            uint32_t val = scratch[k];
+            scratch[k] = 0;
+            if (ACCUM) val += table[k];
             val = min(val, 255u);
-            table[i] = (uint8_t)val;
+            table[k] = (uint8_t)val;
             if (bins && val) atomicAdd(&sh[0][val], 1u);
         }
     }
@@ -534,6 +549,7 @@ struct pk_indexer {
     uint32_t *cursor = nullptr;                // device pool cursor
     uint32_t *scratch = nullptr;               // one window of 32-bit counters
     int nseg = 0;
+    size_t l2_persist_bytes = 0;               // persisting-L2 carve-out granted for `scratch`
     bool table_valid = false;                  // every window has been written since reset
     bool stats_valid = false;                  // bins hold the histogram of the current table
     bool scatter_smem_set = false;
@@ -579,9 +595,32 @@ static uint32_t *seg_fill(pk_indexer *ix, int f) {
     return ix->seg + ((size_t)2 * kMaxSegments + f) * ix->nbuckets;
 }
 
+// The window's 32-bit counters must stay in L2 while the k-mer entries and the table
+// stream past them: mark them persisting (and everything that misses the carve-out
+// streaming) for the two window kernels.
+static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
+    if (!ix->l2_persist_bytes) return 0;
+    const size_t bytes = sizeof(uint32_t) << ix->win_log2;
+    attr->id = cudaLaunchAttributeAccessPolicyWindow;
+    attr->val.accessPolicyWindow.base_ptr = ix->scratch;
+    attr->val.accessPolicyWindow.num_bytes = bytes;
+    attr->val.accessPolicyWindow.hitRatio =
+        ix->l2_persist_bytes >= bytes ? 1.0f : (float)ix->l2_persist_bytes / (float)bytes;
+    attr->val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr->val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    return 1;
+}
+
 // PARTITION: drain the buffered entries window by window into the table
 static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats) {
     const size_t win = (size_t)1 << ix->win_log2;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = window_launch_attr(ix, attr);
     if (with_stats)
         PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->counters + 1 : nullptr;
@@ -590,16 +629,19 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats) {
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
-            k_window_count<<<grid, 256, 0, st>>>(ix->pool, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg,
-                                                 ix->nbuckets, b, ix->scratch);
+            cfg.gridDim = dim3(grid);
+            PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, (const uint32_t *)ix->pool,
+                                       (const uint32_t *)seg_off(ix, 0), (const uint32_t *)seg_cnt(ix, 0),
+                                       ix->nseg, ix->nbuckets, b, ix->scratch));
             ix->launches++;
         }
         uint8_t *tw = ix->table + (size_t)b * win;
         const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid, (n / 16 + 255) / 256));
         {
             prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
-            if (ix->table_valid) k_window_commit<true><<<cgrid, 256, 0, st>>>(ix->scratch, tw, n, bins);
-            else                 k_window_commit<false><<<cgrid, 256, 0, st>>>(ix->scratch, tw, n, bins);
+            cfg.gridDim = dim3(cgrid);
+            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, ix->scratch, tw, n, bins));
+            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, ix->scratch, tw, n, bins));
         }
         ix->launches++;
     }
@@ -617,11 +659,19 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     if (n == 0) return PK_OK;
     ScanParams p;
     memset(&p, 0, sizeof p);
-    p.seq = seq_dev; p.n = n; p.carry = ix->carry; p.K = ix->K; p.lo = ix->lo; p.hi = ix->hi;
+    p.seq = seq_dev; p.n = n; p.carry = ix->carry; p.K = ix->K; p.lo = ix->lo; p.span = ix->hi - ix->lo;
     p.table = ix->table; p.num_kmers = ix->counters;
     p.rec_starts = ix->rec_starts; p.nrec = ix->nrec; p.rec_flags = ix->nrec ? ix->rec_flags : nullptr;
     p.stream_off = ix->stream_off;
     const bool wide = ix->K > 16;
+    const bool full = ix->lo == 0 && ix->hi == (1ull << (2 * ix->K));
+#define PK_LAUNCH_SCAN(KERNEL, GRID, SMEM)                                                     \
+    do {                                                                                       \
+        if (wide) { if (full) KERNEL<true, true><<<GRID, kScanThreads, SMEM, st>>>(p);         \
+                    else      KERNEL<true, false><<<GRID, kScanThreads, SMEM, st>>>(p); }      \
+        else      { if (full) KERNEL<false, true><<<GRID, kScanThreads, SMEM, st>>>(p);        \
+                    else      KERNEL<false, false><<<GRID, kScanThreads, SMEM, st>>>(p); }     \
+    } while (0)
     const long long gpw = wide ? 30 : 31;
     const long long ngroups = (long long)((n + 15) / 16);
     const long long ntiles = (ngroups + gpw - 1) / gpw;
@@ -630,8 +680,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     if (ix->mode == PK_MODE_DIRECT) {
         {
             prof_scope ps(ix, st, PROF_SCAN_DIRECT);
-            if (wide) k_scan_count_direct<true><<<grid, kScanThreads, 0, st>>>(p);
-            else      k_scan_count_direct<false><<<grid, kScanThreads, 0, st>>>(p);
+            PK_LAUNCH_SCAN(k_scan_count_direct, grid, 0);
         }
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
@@ -646,14 +695,15 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         const size_t smem1 = (size_t)ix->nbuckets * sizeof(uint32_t);
         const size_t smem2 = scatter_smem_bytes(ix->nbuckets);
         if (!ix->scatter_smem_set) {
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             ix->scatter_smem_set = true;
         }
         {
             prof_scope ps(ix, st, PROF_BUCKET_COUNT);
-            if (wide) k_scan_bucket_count<true><<<grid, kScanThreads, smem1, st>>>(p);
-            else      k_scan_bucket_count<false><<<grid, kScanThreads, smem1, st>>>(p);
+            PK_LAUNCH_SCAN(k_scan_bucket_count, grid, smem1);
         }
         {
             prof_scope ps(ix, st, PROF_OFFSETS);
@@ -662,8 +712,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 4));
         {
             prof_scope ps(ix, st, PROF_SCATTER);
-            if (wide) k_scan_scatter<true><<<grid2, kScanThreads, smem2, st>>>(p);
-            else      k_scan_scatter<false><<<grid2, kScanThreads, smem2, st>>>(p);
+            PK_LAUNCH_SCAN(k_scan_scatter, grid2, smem2);
         }
         PK_CUDA(cudaGetLastError());
         ix->launches += 3;
@@ -681,6 +730,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     ix->fed = true;
     ix->last_stream = st;
     return PK_OK;
+#undef PK_LAUNCH_SCAN
 }
 
 // feeds are cut so that one partition pass never exceeds kMaxFeed bases
@@ -771,6 +821,23 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
         step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+        // persisting-L2 carve-out for the counters (PYKMER_B200_L2_PERSIST=0 disables it)
+        const char *pe = getenv("PYKMER_B200_L2_PERSIST");
+        if (e == cudaSuccess && !(pe && atoi(pe) == 0)) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+            const size_t want = sizeof(uint32_t) << win_log2;
+            size_t grant = std::min<size_t>(want, (size_t)std::max(max_persist, 0));
+            if (grant && (size_t)max_window >= want &&
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess)
+                ix->l2_persist_bytes = grant;
+            else
+                cudaGetLastError();
+            if (getenv("PYKMER_B200_VERBOSE"))
+                fprintf(stderr, "[pykmer_b200] L2 persist: max %d B, max window %d B, window counters "
+                        "%zu B, granted %zu B\n", max_persist, max_window, want, ix->l2_persist_bytes);
+        }
         if (e == cudaSuccess) {
             step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
             step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));

@@ -116,54 +116,88 @@ PK_HD uint32_t pk_rc32_at(uint64_t rcat /* r0:r1 */, int j, int K, uint32_t mask
 // ---------------------------------------------------------------------------------------
 // All windows that END inside one 16-base group, given the group's own encoding
 // (cc, cv) and its one or two predecessors.  Windows whose canonical value lies in
-// [lo, hi) are counted; consecutive equal canonical values are merged into runs.
+// [lo, lo + span) are counted; consecutive equal canonical values are merged into runs.
 //   emit(slot, off, cnt)   one run: off = canon - lo, cnt = 1..16 windows.  `slot`
 //                          (0..16) is a compile-time constant after unrolling, so a
-//                          caller may keep per-slot state in registers.
-//   on_window(j, fresh)    once per counted window; fresh = an invalid base (e.g. a
-//                          record separator) passed since the previous counted window
-//                          of this group, or this is the group's first one.
-// Returns the number of counted windows (indexer.py:342 num_kmers += 1).
-template <bool WIDE, typename Emit, typename OnWindow>
-PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t hi, uint32_t cc, uint32_t cv,
-                             uint32_t pc1, uint32_t pv1, uint32_t pc2, uint32_t pv2,
-                             Emit emit, OnWindow on_window) {
+//                          caller may keep per-slot state in registers.  off is uint32_t
+//                          when !WIDE (K <= 16), uint64_t otherwise.
+// FULL = the whole table (lo = 0, span = 4^K): no range test at all.
+// Returns the 16-bit mask of counted windows (bit 15-j = the window ending at base j);
+// its popcount is the contribution to num_kmers (indexer.py:342).
+template <bool WIDE, bool FULL, typename Emit>
+PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t span, uint32_t cc, uint32_t cv,
+                             uint32_t pc1, uint32_t pv1, uint32_t pc2, uint32_t pv2, Emit emit) {
     const uint64_t vcat = ((uint64_t)pv2 << 32) | ((uint64_t)pv1 << 16) | cv;
     const uint32_t Wm = (uint32_t)pk_valid_windows(vcat, K) & 0xFFFFu;
     if (!Wm) return 0;
-    const uint32_t r0 = pk_rcw(cc), r1 = pk_rcw(pc1), r2 = WIDE ? pk_rcw(pc2) : 0u;
-    const uint64_t cat = ((uint64_t)pc1 << 32) | cc;
-    const uint64_t rcat = ((uint64_t)r0 << 32) | r1;
-    const uint32_t mask32 = (uint32_t)pk_kmer_mask(K);
-    uint64_t prev = ~0ull;
-    uint32_t pend = 0, counted = 0;
-    bool fresh = true;
+    const uint32_t r0 = pk_rcw(cc), r1 = pk_rcw(pc1);
+    uint32_t counted = 0, pend = 0;
+    if (WIDE) {
+        const uint32_t r2 = pk_rcw(pc2);
+        uint64_t prev = ~0ull;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        if (!((cv >> (15 - j)) & 1u)) fresh = true;
-        if (!((Wm >> (15 - j)) & 1u)) continue;
-        uint64_t canon;
-        if (WIDE) {
+        for (int j = 0; j < 16; j++) {
+            if (!((Wm >> (15 - j)) & 1u)) continue;
             const uint64_t f = pk_fwd_at(pc2, pc1, cc, j, K);
             const uint64_t r = pk_rc_at(r2, r1, r0, j, K);
-            canon = f < r ? f : r;                               // indexer.py:341
-        } else {
-            const uint32_t f = pk_fwd32_at(cat, j, mask32);
-            const uint32_t r = pk_rc32_at(rcat, j, K, mask32);
-            canon = f < r ? f : r;
+            const uint64_t off = (f < r ? f : r) - lo;            // indexer.py:341
+            if (!FULL && off >= span) continue;                   // another shard's k-mer
+            counted |= 1u << (15 - j);
+            if (off == prev) {
+                pend++;
+            } else {
+                if (pend) emit(j, prev, pend);
+                prev = off;
+                pend = 1;
+            }
         }
-        if (canon < lo || canon >= hi) continue;                 // another shard's k-mer
-        counted++;
-        on_window(j, fresh);
-        fresh = false;
-        if (canon == prev) {
-            pend++;
-        } else {
-            if (pend) emit(j, prev - lo, pend);
-            prev = canon;
-            pend = 1;
+        if (pend) emit(16, prev, pend);
+    } else {
+        // K <= 16: everything fits 32 bits; the window slices are funnel shifts by constants
+        const uint32_t mask = (uint32_t)pk_kmer_mask(K);
+        const uint64_t cat = ((uint64_t)pc1 << 32) | cc;
+        const uint64_t rsh = (((uint64_t)r0 << 32) | r1) >> (34 - 2 * K);
+        const uint32_t lo32 = (uint32_t)lo;
+        const uint32_t span_m1 = (uint32_t)(span - 1);           // span <= 2^32
+        uint32_t prev = 0xFFFFFFFFu;                             // no run yet (never a valid offset + count)
+        bool have = false;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (!((Wm >> (15 - j)) & 1u)) continue;
+            const uint32_t f = (uint32_t)(cat >> (2 * (15 - j))) & mask;
+            const uint32_t r = (uint32_t)(rsh >> (2 * j)) & mask;
+            const uint32_t off = (f < r ? f : r) - lo32;          // indexer.py:341
+            if (!FULL && off > span_m1) continue;                 // another shard's k-mer
+            counted |= 1u << (15 - j);
+            if (have && off == prev) {
+                pend++;
+            } else {
+                if (have) emit(j, prev, pend);
+                prev = off;
+                pend = 1;
+                have = true;
+            }
         }
+        if (have) emit(16, prev, pend);
     }
-    if (pend) emit(16, prev - lo, pend);
     return counted;
+}
+
+// Which runs of counted windows may lie in different records: calls visit(j) once for the
+// first counted window after every invalid base of the group (and for the group's first
+// counted window).  cv = validity bits of the group, counted = mask from pk_scan_group.
+template <typename Visit>
+PK_HD void pk_for_each_record_run(uint32_t cv, uint32_t counted, Visit visit) {
+    while (counted) {
+        int top = 31;
+        while (!((counted >> top) & 1u)) top--;                  // earliest remaining window
+        const int j = 15 - top;
+        visit(j);
+        // drop every counted window up to the next invalid base after j
+        uint32_t inv = (~cv) & ((1u << top) - 1u) & 0xFFFFu;     // invalid bases later than j
+        if (!inv) break;
+        int q = 31;
+        while (!((inv >> q) & 1u)) q--;                          // first invalid base after j
+        counted &= (1u << q) - 1u;                               // keep windows ending after it
+    }
 }

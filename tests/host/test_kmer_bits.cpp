@@ -80,7 +80,7 @@ int main() {
             const uint64_t lo = los[rg], hi = his[rg];
             for (size_t g = 2; g < groups; g++) {
                 std::vector<uint64_t> want, got;
-                std::vector<int> fresh_want, fresh_got;
+                std::vector<int> fresh_want;
                 bool fresh = true;
                 for (int j = 0; j < 16; j++) {
                     size_t e = 16 * g + j;
@@ -108,15 +108,26 @@ int main() {
                     runs++;
                     for (uint32_t c = 0; c < cnt; c++) got.push_back(off);
                 };
-                auto onw = [&](int, bool f) { fresh_got.push_back(f ? 1 : 0); };
-                uint32_t n;
-                if (K > 16)
-                    n = pk_scan_group<true>(K, lo, hi, codes[g], vm[g], codes[g - 1], vm[g - 1],
-                                            codes[g - 2], vm[g - 2], emit, onw);
-                else
-                    n = pk_scan_group<false>(K, lo, hi, codes[g], vm[g], codes[g - 1], vm[g - 1],
-                                             0u, 0u, emit, onw);
-                if (!slot_order || n != want.size() || got != want || fresh_got != fresh_want) {
+                const bool full = (rg == 0);
+                uint32_t cm;
+                if (K > 16) {
+                    cm = full ? pk_scan_group<true, true>(K, lo, hi - lo, codes[g], vm[g], codes[g - 1], vm[g - 1], codes[g - 2], vm[g - 2], emit)
+                              : pk_scan_group<true, false>(K, lo, hi - lo, codes[g], vm[g], codes[g - 1], vm[g - 1], codes[g - 2], vm[g - 2], emit);
+                } else {
+                    cm = full ? pk_scan_group<false, true>(K, lo, hi - lo, codes[g], vm[g], codes[g - 1], vm[g - 1], 0u, 0u, emit)
+                              : pk_scan_group<false, false>(K, lo, hi - lo, codes[g], vm[g], codes[g - 1], vm[g - 1], 0u, 0u, emit);
+                }
+                // counted mask -> fresh positions, as the record flagger will visit them
+                std::vector<int> visit_want, visit_got;
+                {
+                    int wi = 0;
+                    for (int j = 0; j < 16; j++)
+                        if ((cm >> (15 - j)) & 1u) { if (fresh_want[wi]) visit_want.push_back(j); wi++; }
+                }
+                pk_for_each_record_run(vm[g], cm, [&](int j) { visit_got.push_back(j); });
+                uint32_t n = 0;
+                for (int b = 0; b < 16; b++) n += (cm >> b) & 1u;
+                if (!slot_order || n != want.size() || got != want || visit_got != visit_want) {
                     printf("scan_group mismatch K=%d g=%zu range %d: n=%u want=%zu\n", K, g, rg, n, want.size());
                     return 1;
                 }
