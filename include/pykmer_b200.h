@@ -66,7 +66,7 @@ int         pk_host_free(void *ptr);
  */
 #define PK_MODE_AUTO      0   /* PARTITION for tables beyond 64 Mi entries, else DIRECT */
 #define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
-#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^24-entry table window, count each window
+#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^23-entry table window, count each window
                                  with L2-resident 32-bit counters, clamp and write it once.
                                  (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 shrink the
                                  window and the k-mer buffer; they exist for the tests.) */

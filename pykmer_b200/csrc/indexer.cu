@@ -335,18 +335,42 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams 
     }
 }
 
-// per window: every buffered entry of the window bumps its L2-resident 32-bit counter
+// per window: every buffered entry of the window bumps its L2-resident 32-bit counter.
+// The L2 atomic units are the bottleneck (~190 G/s on distinct addresses, far less on one
+// address), the SMs idle: so a warp first merges its equal addresses (microsatellites put
+// the same two or three k-mers into every lane) and issues one red.add per distinct one.
+__device__ __forceinline__ void window_add(uint32_t *scratch, uint32_t e, bool live, uint32_t lane) {
+    const uint32_t addr = live ? (e & 0xFFFFFFu) : (0x80000000u | lane);   // dead lanes: unique
+    uint32_t val = live ? (e >> 24) + 1u : 0u;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, addr);
+    if (peers != (1u << lane)) val = __reduce_add_sync(peers, val);
+    if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&scratch[addr], val);
+}
+
 __global__ void __launch_bounds__(256) k_window_count(const uint32_t *__restrict__ pool,
                                                       const uint32_t *__restrict__ seg_off,
                                                       const uint32_t *__restrict__ seg_cnt,
                                                       int nseg, uint32_t nb, uint32_t b,
                                                       uint32_t *__restrict__ scratch) {
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t span = gridDim.x * blockDim.x;                 // entries per grid sweep
+    constexpr int U = 4;
     for (int f = 0; f < nseg; f++) {
         const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) {
-            const uint32_t e = __ldcs(pool + off + i);
-            atomicAdd(&scratch[e & 0xFFFFFFu], (e >> 24) + 1u);
+        const uint32_t *src = pool + off;
+        // warp-uniform trip count: every lane of a warp runs the same iterations
+        for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cnt; base += U * span) {
+            uint32_t e[U];
+            bool live[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = base + u * span + lane;
+                live[u] = i < cnt;
+                e[u] = live[u] ? __ldcs(src + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (base + u * span < cnt) window_add(scratch, e[u], live[u], lane);
         }
     }
 }
@@ -368,6 +392,8 @@ template <bool ACCUM>
 __global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ scratch,
                                                        uint8_t *__restrict__ table, size_t n,
                                                        unsigned long long *__restrict__ bins) {
+    // bins: [gridDim.x][256] partial histograms, one row per block (launches of one flush are
+    // serialised on one stream, so a block owns its row); k_reduce_bins sums the rows.
     __shared__ uint32_t sh[8][256];
     if (bins) {
         for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
@@ -436,7 +462,14 @@ __global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ sc
     unsigned long long s = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) s += sh[k][threadIdx.x];
-    if (s && threadIdx.x) atomicAdd(&bins[threadIdx.x], s);
+    if (s && threadIdx.x) bins[(size_t)blockIdx.x * 256 + threadIdx.x] += s;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_bins(const unsigned long long *__restrict__ part,
+                                                     int rows, unsigned long long *__restrict__ bins) {
+    unsigned long long s = 0;
+    for (int r = 0; r < rows; r++) s += part[(size_t)r * 256 + threadIdx.x];
+    bins[threadIdx.x] = s;
 }
 
 // new carry = last kCarry bytes of (old carry ++ seq[0..n))
@@ -547,7 +580,10 @@ struct pk_indexer {
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
     uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
     uint32_t *cursor = nullptr;                // device pool cursor
-    uint32_t *scratch = nullptr;               // one window of 32-bit counters
+    uint32_t *scratch = nullptr;               // two windows of 32-bit counters (double buffer)
+    unsigned long long *bins_part = nullptr;   // [2 * sm_count][256] partial histograms
+    cudaStream_t aux_stream = nullptr;         // commits run here, beside the counting
+    cudaEvent_t counted[2] = {nullptr, nullptr}, committed[2] = {nullptr, nullptr};
     int nseg = 0;
     size_t l2_persist_bytes = 0;               // persisting-L2 carve-out granted for `scratch`
     bool table_valid = false;                  // every window has been written since reset
@@ -600,7 +636,7 @@ static uint32_t *seg_fill(pk_indexer *ix, int f) {
 // streaming) for the two window kernels.
 static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     if (!ix->l2_persist_bytes) return 0;
-    const size_t bytes = sizeof(uint32_t) << ix->win_log2;
+    const size_t bytes = (size_t)2 * (sizeof(uint32_t) << ix->win_log2);   // both counter buffers
     attr->id = cudaLaunchAttributeAccessPolicyWindow;
     attr->val.accessPolicyWindow.base_ptr = ix->scratch;
     attr->val.accessPolicyWindow.num_bytes = bytes;
@@ -611,41 +647,74 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     return 1;
 }
 
-// PARTITION: drain the buffered entries window by window into the table
+// PARTITION: drain the buffered entries window by window into the table.  Two counter
+// buffers alternate: while window b is being counted on `st` (L2-atomic bound), window
+// b-1 is committed on the auxiliary stream (L2-bandwidth bound); the grids are sized so
+// that both kernels are resident together.
 static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats) {
     const size_t win = (size_t)1 << ix->win_log2;
+    cudaStream_t aux = ix->aux_stream;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.blockDim = dim3(256);
-    cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = window_launch_attr(ix, attr);
+    const int rows = ix->sm_count * 2;                      // commit grid = rows of partial bins
     if (with_stats)
-        PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
-    unsigned long long *bins = with_stats ? ix->counters + 1 : nullptr;
-    const int grid = ix->sm_count * 8;
+        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
+    unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
+    const int grid = ix->sm_count * 6;
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
+        const int buf = (int)(b & 1u);
+        uint32_t *scratch = ix->scratch + (size_t)buf * win;
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
+        if (b >= 2) PK_CUDA(cudaStreamWaitEvent(st, ix->committed[buf], 0));   // buffer is free again
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
             cfg.gridDim = dim3(grid);
+            cfg.stream = st;
             PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, (const uint32_t *)ix->pool,
                                        (const uint32_t *)seg_off(ix, 0), (const uint32_t *)seg_cnt(ix, 0),
-                                       ix->nseg, ix->nbuckets, b, ix->scratch));
+                                       ix->nseg, ix->nbuckets, b, scratch));
             ix->launches++;
         }
+        PK_CUDA(cudaEventRecord(ix->counted[buf], st));
+        PK_CUDA(cudaStreamWaitEvent(aux, ix->counted[buf], 0));
         uint8_t *tw = ix->table + (size_t)b * win;
-        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid, (n / 16 + 255) / 256));
+        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows, (n / 4 + 255) / 256));
         {
-            prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
+            prof_scope ps(ix, aux, PROF_WINDOW_COMMIT);
             cfg.gridDim = dim3(cgrid);
-            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, ix->scratch, tw, n, bins));
-            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, ix->scratch, tw, n, bins));
+            cfg.stream = aux;
+            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, scratch, tw, n, bins));
+            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, scratch, tw, n, bins));
         }
+        PK_CUDA(cudaEventRecord(ix->committed[buf], aux));
+        ix->launches++;
+    }
+    PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
+    if (ix->nbuckets > 1) PK_CUDA(cudaStreamWaitEvent(st, ix->committed[1], 0));
+    if (with_stats) {
+        k_reduce_bins<<<1, 256, 0, st>>>(ix->bins_part, rows, ix->counters + 1);
         ix->launches++;
     }
     PK_CUDA(cudaGetLastError());
+    if (const char *v = getenv("PYKMER_B200_VERBOSE")) {
+        if (atoi(v) >= 2) {                                // debugging aid: synchronises
+            uint32_t used = 0;
+            std::vector<uint32_t> cnt((size_t)kMaxSegments * ix->nbuckets);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(&used, ix->cursor, sizeof used, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cnt.data(), seg_cnt(ix, 0), cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[pykmer_b200] flush: %u entries in %d segments, %u windows\n", used, ix->nseg, ix->nbuckets);
+            for (uint32_t b = 0; b < ix->nbuckets; b++) {
+                unsigned long long t = 0;
+                for (int f = 0; f < ix->nseg; f++) t += cnt[(size_t)f * ix->nbuckets + b];
+                fprintf(stderr, "[pykmer_b200] window %u entries %llu\n", b, t);
+            }
+        }
+    }
     PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
     ix->nseg = 0;
@@ -771,9 +840,9 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     ix->table_bytes = (size_t)(range_hi - range_lo);
     ix->sm_count = pk_sm_count(device);
 
-    // window size: 2^24 counters (64 MiB of u32) stay L2-resident on B200; the
+    // window size: two buffers of 2^23 counters (2 x 32 MiB of u32) stay L2-resident on B200; the
     // environment override exists so that tests can force many windows on small tables
-    uint32_t win_log2 = 24;
+    uint32_t win_log2 = 23;
     if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
         const int v = atoi(env);
         if (v >= 4 && v <= 24) win_log2 = (uint32_t)v;
@@ -820,14 +889,20 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->pool, cap * sizeof(uint32_t)));
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
-        step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+        step(cudaMalloc(&ix->scratch, (size_t)2 * (sizeof(uint32_t) << win_log2)));
+        step(cudaMalloc(&ix->bins_part, (size_t)2 * ix->sm_count * 256 * sizeof(unsigned long long)));
+        step(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            step(cudaEventCreateWithFlags(&ix->counted[i], cudaEventDisableTiming));
+            step(cudaEventCreateWithFlags(&ix->committed[i], cudaEventDisableTiming));
+        }
         // persisting-L2 carve-out for the counters (PYKMER_B200_L2_PERSIST=0 disables it)
         const char *pe = getenv("PYKMER_B200_L2_PERSIST");
         if (e == cudaSuccess && !(pe && atoi(pe) == 0)) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            const size_t want = sizeof(uint32_t) << win_log2;
+            const size_t want = (size_t)2 * (sizeof(uint32_t) << win_log2);
             size_t grant = std::min<size_t>(want, (size_t)std::max(max_persist, 0));
             if (grant && (size_t)max_window >= want &&
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess)
@@ -841,7 +916,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         if (e == cudaSuccess) {
             step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
             step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));
-            step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
+            step(cudaMemsetAsync(ix->scratch, 0, (size_t)2 * (sizeof(uint32_t) << win_log2), ix->work_stream));
         }
     }
     if (e == cudaSuccess) {
@@ -870,7 +945,14 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->table); cudaFree(ix->carry); cudaFree(ix->counters);
     cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
+    if (ix->aux_stream) cudaStreamSynchronize(ix->aux_stream);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
+    cudaFree(ix->bins_part);
+    for (int i = 0; i < 2; i++) {
+        if (ix->counted[i]) cudaEventDestroy(ix->counted[i]);
+        if (ix->committed[i]) cudaEventDestroy(ix->committed[i]);
+    }
+    if (ix->aux_stream) cudaStreamDestroy(ix->aux_stream);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
     for (int i = 0; i < 2; i++) {
         if (ix->copied[i]) cudaEventDestroy(ix->copied[i]);
@@ -1109,6 +1191,8 @@ PK_API int pk_indexer_profile(pk_indexer *ix, double ms_host[8], uint32_t launch
         PK_CUDA(cudaEventElapsedTime(&ms, ix->prof_events[2 * i], ix->prof_events[2 * i + 1]));
         ms_host[ix->prof_tags[i]] += ms;
         launches_host[ix->prof_tags[i]] += 1;
+        if (const char *v = getenv("PYKMER_B200_VERBOSE"))
+            if (atoi(v) >= 2) fprintf(stderr, "[pykmer_b200] launch %zu class %d %.4f ms\n", i, ix->prof_tags[i], ms);
     }
     prof_clear(ix);
     return PK_OK;

@@ -492,7 +492,7 @@ def test_partition_mode_feed_after_finalize_and_reset(env):
 
 def test_auto_mode_picks_partition_for_k15(env):
     with env["dev"].Indexer(15) as ix:
-        assert ix.mode() == (PART, 64)
+        assert ix.mode() == (PART, 128)
     with env["dev"].Indexer(11) as ix:
         assert ix.mode()[0] == 1
 
