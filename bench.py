@@ -349,8 +349,7 @@ def run_indexer(args, rank, local_rank, world):
         def step_e2e():
             ix.reset()
             ix.feed_host(h_stream)
-            ix.finalize()
-            ix.table_to_host(h_table)
+            ix.finalize(table_out=h_table)
 
         ms_e = timed_steps(torch, dist, world, 1, max(2, min(args.steps, 3)), step_e2e)
         ms_e /= max(2, min(args.steps, 3))

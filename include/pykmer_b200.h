@@ -66,7 +66,7 @@ int         pk_host_free(void *ptr);
  */
 #define PK_MODE_AUTO      0   /* PARTITION for tables beyond 64 Mi entries, else DIRECT */
 #define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
-#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^23-entry table window, count each window
+#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^24-entry table window, count each window
                                  with L2-resident 32-bit counters, clamp and write it once.
                                  (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 shrink the
                                  window and the k-mer buffer; they exist for the tests.) */
@@ -101,6 +101,11 @@ int pk_indexer_sync(pk_indexer *ix);
  * recomputed by the next finalize).  In PARTITION mode the table is only
  * complete after finalize. */
 int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]);
+/* Same, and the whole table (range_hi - range_lo bytes) lands in table_host (pinned
+ * memory for full speed).  In PARTITION mode each table window is copied out as soon
+ * as it is committed, so the transfer overlaps the counting of the later windows. */
+int pk_indexer_finalize_to_host(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5],
+                                uint8_t *table_host);
 int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec);
 
 /* Device view of the table (valid after finalize), and a copy to host memory. */

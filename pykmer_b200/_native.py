@@ -20,6 +20,7 @@ SYMBOLS = (
     "pk_host_alloc", "pk_host_free",
     "pk_indexer_create", "pk_indexer_destroy", "pk_indexer_reset", "pk_indexer_set_records",
     "pk_indexer_feed_device", "pk_indexer_feed_host", "pk_indexer_sync", "pk_indexer_finalize",
+    "pk_indexer_finalize_to_host",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
     "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_set_profiling", "pk_indexer_profile",
     "pk_table_stats_device",
@@ -62,6 +63,7 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_feed_host": [vp, vp, sz],
         "pk_indexer_sync": [vp],
         "pk_indexer_finalize": [vp, vp, vp],
+        "pk_indexer_finalize_to_host": [vp, vp, vp, vp],
         "pk_indexer_record_flags": [vp, vp, sz],
         "pk_indexer_table_device": [vp, c.POINTER(vp), c.POINTER(sz)],
         "pk_indexer_table_to_host": [vp, vp, sz, sz],

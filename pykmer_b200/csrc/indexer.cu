@@ -580,10 +580,9 @@ struct pk_indexer {
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
     uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
     uint32_t *cursor = nullptr;                // device pool cursor
-    uint32_t *scratch = nullptr;               // two windows of 32-bit counters (double buffer)
-    unsigned long long *bins_part = nullptr;   // [2 * sm_count][256] partial histograms
-    cudaStream_t aux_stream = nullptr;         // commits run here, beside the counting
-    cudaEvent_t counted[2] = {nullptr, nullptr}, committed[2] = {nullptr, nullptr};
+    uint32_t *scratch = nullptr;               // one window of 32-bit counters
+    unsigned long long *bins_part = nullptr;   // [4 * sm_count][256] partial histograms
+    cudaEvent_t committed[2] = {nullptr, nullptr};
     int nseg = 0;
     size_t l2_persist_bytes = 0;               // persisting-L2 carve-out granted for `scratch`
     bool table_valid = false;                  // every window has been written since reset
@@ -636,7 +635,7 @@ static uint32_t *seg_fill(pk_indexer *ix, int f) {
 // streaming) for the two window kernels.
 static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     if (!ix->l2_persist_bytes) return 0;
-    const size_t bytes = (size_t)2 * (sizeof(uint32_t) << ix->win_log2);   // both counter buffers
+    const size_t bytes = sizeof(uint32_t) << ix->win_log2;
     attr->id = cudaLaunchAttributeAccessPolicyWindow;
     attr->val.accessPolicyWindow.base_ptr = ix->scratch;
     attr->val.accessPolicyWindow.num_bytes = bytes;
@@ -647,54 +646,55 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     return 1;
 }
 
-// PARTITION: drain the buffered entries window by window into the table.  Two counter
-// buffers alternate: while window b is being counted on `st` (L2-atomic bound), window
-// b-1 is committed on the auxiliary stream (L2-bandwidth bound); the grids are sized so
-// that both kernels are resident together.
-static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats) {
+// PARTITION: drain the buffered entries window by window into the table: count the
+// window's entries into the L2-resident counters, then commit them (clamp, write the
+// table slice once, re-zero, histogram).  Counting and committing two windows side by
+// side on two streams was measured and is slower: both live off the same L2.
+// When table_host != NULL every committed window is copied out at once on the copy
+// stream, so the device-to-host transfer of the table overlaps the rest of the flush.
+static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
     const size_t win = (size_t)1 << ix->win_log2;
-    cudaStream_t aux = ix->aux_stream;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.blockDim = dim3(256);
+    cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = window_launch_attr(ix, attr);
-    const int rows = ix->sm_count * 2;                      // commit grid = rows of partial bins
+    const int rows = ix->sm_count * 4;                      // commit grid = rows of partial bins
     if (with_stats)
         PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
-    const int grid = ix->sm_count * 6;
+    const int grid = ix->sm_count * 8;
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
-        const int buf = (int)(b & 1u);
-        uint32_t *scratch = ix->scratch + (size_t)buf * win;
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
-        if (b >= 2) PK_CUDA(cudaStreamWaitEvent(st, ix->committed[buf], 0));   // buffer is free again
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
             cfg.gridDim = dim3(grid);
-            cfg.stream = st;
             PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, (const uint32_t *)ix->pool,
                                        (const uint32_t *)seg_off(ix, 0), (const uint32_t *)seg_cnt(ix, 0),
-                                       ix->nseg, ix->nbuckets, b, scratch));
+                                       ix->nseg, ix->nbuckets, b, ix->scratch));
             ix->launches++;
         }
-        PK_CUDA(cudaEventRecord(ix->counted[buf], st));
-        PK_CUDA(cudaStreamWaitEvent(aux, ix->counted[buf], 0));
         uint8_t *tw = ix->table + (size_t)b * win;
         const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows, (n / 4 + 255) / 256));
         {
-            prof_scope ps(ix, aux, PROF_WINDOW_COMMIT);
+            prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
             cfg.gridDim = dim3(cgrid);
-            cfg.stream = aux;
-            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, scratch, tw, n, bins));
-            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, scratch, tw, n, bins));
+            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, ix->scratch, tw, n, bins));
+            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, ix->scratch, tw, n, bins));
         }
-        PK_CUDA(cudaEventRecord(ix->committed[buf], aux));
         ix->launches++;
+        if (table_host) {                                   // ship this window while the next is counted
+            PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
+            PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
+            PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+        }
     }
-    PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
-    if (ix->nbuckets > 1) PK_CUDA(cudaStreamWaitEvent(st, ix->committed[1], 0));
+    if (table_host) {
+        PK_CUDA(cudaEventRecord(ix->committed[0], ix->copy_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
+    }
     if (with_stats) {
         k_reduce_bins<<<1, 256, 0, st>>>(ix->bins_part, rows, ix->counters + 1);
         ix->launches++;
@@ -755,7 +755,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         ix->launches += 1;
     } else {
         if (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap) {
-            const int rc = indexer_flush(ix, st, false);
+            const int rc = indexer_flush(ix, st, false, nullptr);
             if (rc != PK_OK) return rc;
         }
         const int f = ix->nseg;
@@ -840,9 +840,9 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     ix->table_bytes = (size_t)(range_hi - range_lo);
     ix->sm_count = pk_sm_count(device);
 
-    // window size: two buffers of 2^23 counters (2 x 32 MiB of u32) stay L2-resident on B200; the
+    // window size: 2^24 counters (64 MiB of u32) stay L2-resident on B200; the
     // environment override exists so that tests can force many windows on small tables
-    uint32_t win_log2 = 23;
+    uint32_t win_log2 = 24;
     if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
         const int v = atoi(env);
         if (v >= 4 && v <= 24) win_log2 = (uint32_t)v;
@@ -889,20 +889,17 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->pool, cap * sizeof(uint32_t)));
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
-        step(cudaMalloc(&ix->scratch, (size_t)2 * (sizeof(uint32_t) << win_log2)));
-        step(cudaMalloc(&ix->bins_part, (size_t)2 * ix->sm_count * 256 * sizeof(unsigned long long)));
-        step(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            step(cudaEventCreateWithFlags(&ix->counted[i], cudaEventDisableTiming));
+        step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+        step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
+        for (int i = 0; i < 2; i++)
             step(cudaEventCreateWithFlags(&ix->committed[i], cudaEventDisableTiming));
-        }
         // persisting-L2 carve-out for the counters (PYKMER_B200_L2_PERSIST=0 disables it)
         const char *pe = getenv("PYKMER_B200_L2_PERSIST");
         if (e == cudaSuccess && !(pe && atoi(pe) == 0)) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            const size_t want = (size_t)2 * (sizeof(uint32_t) << win_log2);
+            const size_t want = sizeof(uint32_t) << win_log2;
             size_t grant = std::min<size_t>(want, (size_t)std::max(max_persist, 0));
             if (grant && (size_t)max_window >= want &&
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess)
@@ -916,7 +913,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         if (e == cudaSuccess) {
             step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
             step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));
-            step(cudaMemsetAsync(ix->scratch, 0, (size_t)2 * (sizeof(uint32_t) << win_log2), ix->work_stream));
+            step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
         }
     }
     if (e == cudaSuccess) {
@@ -945,14 +942,10 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->table); cudaFree(ix->carry); cudaFree(ix->counters);
     cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
-    if (ix->aux_stream) cudaStreamSynchronize(ix->aux_stream);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part);
-    for (int i = 0; i < 2; i++) {
-        if (ix->counted[i]) cudaEventDestroy(ix->counted[i]);
+    for (int i = 0; i < 2; i++)
         if (ix->committed[i]) cudaEventDestroy(ix->committed[i]);
-    }
-    if (ix->aux_stream) cudaStreamDestroy(ix->aux_stream);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
     for (int i = 0; i < 2; i++) {
         if (ix->copied[i]) cudaEventDestroy(ix->copied[i]);
@@ -1089,18 +1082,21 @@ PK_API int pk_indexer_sync(pk_indexer *ix) {
     return PK_OK;
 }
 
-PK_API int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]) {
+static int indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5],
+                            uint8_t *table_host) {
     PK_REQUIRE(ix != nullptr, "pk_indexer_finalize: NULL handle");
     PK_REQUIRE(hist_host != nullptr && stats_host != nullptr, "pk_indexer_finalize: NULL output");
     pk_device_guard guard(ix->device);
+    bool copied = false;
     {
         const int rc = indexer_join(ix);                   // feeds may sit on the caller's stream
         if (rc != PK_OK) return rc;
     }
     cudaStream_t st = ix->work_stream;
     if (ix->mode == PK_MODE_PARTITION && (ix->nseg || !ix->table_valid || !ix->stats_valid)) {
-        const int rc = indexer_flush(ix, st, true);        // statistics fused into the commit
+        const int rc = indexer_flush(ix, st, true, table_host);   // statistics fused into the commit
         if (rc != PK_OK) return rc;
+        copied = table_host != nullptr;
     } else if (ix->mode == PK_MODE_DIRECT) {
         PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
         {
@@ -1110,6 +1106,8 @@ PK_API int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t 
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
     }
+    if (table_host && !copied)
+        PK_CUDA(cudaMemcpyAsync(table_host, ix->table, ix->table_bytes, cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaMemcpyAsync(ix->h_counters, ix->counters, 257 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaStreamSynchronize(st));
@@ -1118,6 +1116,16 @@ PK_API int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t 
     stats_host[0] = ix->h_counters[0];
     for (int i = 0; i < 4; i++) stats_host[1 + i] = st4[i];
     return PK_OK;
+}
+
+PK_API int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]) {
+    return indexer_finalize(ix, hist_host, stats_host, nullptr);
+}
+
+PK_API int pk_indexer_finalize_to_host(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5],
+                                       uint8_t *table_host) {
+    PK_REQUIRE(table_host != nullptr, "pk_indexer_finalize_to_host: NULL table buffer");
+    return indexer_finalize(ix, hist_host, stats_host, table_host);
 }
 
 PK_API int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec) {

@@ -97,10 +97,19 @@ class Indexer:
         nat.check(lib.pk_indexer_sync(self._h))
         self._keep.clear()
 
-    def finalize(self) -> Tuple[List[int], dict]:
+    def finalize(self, table_out=None) -> Tuple[List[int], dict]:
+        """Finish counting -> (hist[255], statistics).  table_out (CPU tensor / numpy array of
+        range_hi - range_lo bytes, ideally pinned) also receives the table, window by window
+        while the rest is still being counted."""
         hist = np.zeros(255, dtype=np.int64)
         st = np.zeros(5, dtype=np.uint64)
-        nat.check(lib.pk_indexer_finalize(self._h, hist.ctypes.data, st.ctypes.data))
+        if table_out is None:
+            nat.check(lib.pk_indexer_finalize(self._h, hist.ctypes.data, st.ctypes.data))
+        else:
+            n = table_out.numel() if isinstance(table_out, torch.Tensor) else table_out.size
+            assert n >= self.range_hi - self.range_lo
+            p = table_out.data_ptr() if isinstance(table_out, torch.Tensor) else table_out.ctypes.data
+            nat.check(lib.pk_indexer_finalize_to_host(self._h, hist.ctypes.data, st.ctypes.data, p))
         self._keep.clear()
         return hist.tolist(), {"num_kmers": int(st[0]), "vals_sum": int(st[1]),
                                "vals_count": int(st[2]), "vals_min": int(st[3]),

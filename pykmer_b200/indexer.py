@@ -71,9 +71,10 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
             turn ^= 1
             bases = sum(fs.lengths)
             header.timer.update(bases)
-        hist, st = ix.finalize()
+        out = dev.pinned_empty(header.data_size)
+        hist, st = ix.finalize(table_out=out)      # table windows stream out as they are committed
         flags = ix.record_flags() if fs.starts else np.zeros(0, dtype=np.uint8)
-        table = ix.table_to_host().numpy()
+        table = out.numpy()
 
     header.num_kmers = st["num_kmers"]
     # indexer.py:349-351: a record is listed once its first k-mer arrives

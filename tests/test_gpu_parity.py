@@ -492,7 +492,7 @@ def test_partition_mode_feed_after_finalize_and_reset(env):
 
 def test_auto_mode_picks_partition_for_k15(env):
     with env["dev"].Indexer(15) as ix:
-        assert ix.mode() == (PART, 128)
+        assert ix.mode() == (PART, 64)
     with env["dev"].Indexer(11) as ix:
         assert ix.mode()[0] == 1
 
@@ -542,3 +542,29 @@ def test_full_size_config2_modes_agree(env):
                 rc |= (3 - ((idx >> (2 * q)) & 3)) << (2 * (14 - q))
             assert not host[idx[idx > rc]].any()
     assert digests[0] == digests[1] and stats[0] == stats[1]
+
+
+@pytest.mark.parametrize("mode,wlog", [(1, None), (2, 10), (2, 24)])
+def test_finalize_to_host_streams_the_table(env, mode, wlog):
+    rng = np.random.default_rng(321)
+    s = _random_stream(rng, 300_000)
+    K = 11
+    want, num, _ = env["oracle"].index_stream(s, K)
+    dev = env["dev"]
+    if wlog is not None:
+        os.environ["PYKMER_B200_WINDOW_LOG2"] = str(wlog)
+    try:
+        ix = dev.Indexer(K, mode=mode)
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+    with ix:
+        out = dev.pinned_empty(4 ** K)
+        for rep in range(2):
+            out.zero_()
+            ix.reset()
+            ix.feed_host(s)
+            hist, st = ix.finalize(table_out=out)
+            assert st["num_kmers"] == num and np.array_equal(out.numpy(), want)
+            assert hist == env["oracle"].table_stats(want)[0]
+        hist2, st2 = ix.finalize(table_out=out)              # nothing pending: plain copy
+        assert (hist2, st2) == (hist, st) and np.array_equal(out.numpy(), want)
