@@ -342,9 +342,18 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams 
 __device__ __forceinline__ void window_add(uint32_t *scratch, uint32_t e, bool live, uint32_t lane) {
     const uint32_t addr = live ? (e & 0xFFFFFFu) : (0x80000000u | lane);   // dead lanes: unique
     uint32_t val = live ? (e >> 24) + 1u : 0u;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, addr);
-    if (peers != (1u << lane)) val = __reduce_add_sync(peers, val);
-    if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&scratch[addr], val);
+    // cheap screen first (MATCH.ANY is slow): short-period repeats show up as an equal
+    // address one, two or three lanes away
+    const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, addr, 1), a2 = __shfl_up_sync(0xFFFFFFFFu, addr, 2),
+                   a3 = __shfl_up_sync(0xFFFFFFFFu, addr, 3);
+    const bool dup = (lane >= 1 && a1 == addr) || (lane >= 2 && a2 == addr) || (lane >= 3 && a3 == addr);
+    if (__any_sync(0xFFFFFFFFu, dup)) {
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, addr);
+        if (peers != (1u << lane)) val = __reduce_add_sync(peers, val);
+        if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&scratch[addr], val);
+    } else if (live) {
+        atomicAdd(&scratch[addr], val);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_window_count(const uint32_t *__restrict__ pool,
