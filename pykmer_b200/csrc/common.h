@@ -11,6 +11,11 @@
 
 int pk_set_error(int code, const char *fmt, ...);
 
+// gram_i8.cu: gram (int64 N x N, zeroed or holding a partial sum) += B * B^T on the
+// tensor cores (tcgen05 kind::i8); nsamples <= 256.
+int pk_gram_i8_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
+                      int64_t *gram_dev, int device, cudaStream_t st);
+
 #define PK_CUDA(call)                                                                   \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \

@@ -1,0 +1,287 @@
+// gram_i8.cu -- the merger's Gram matrix on the 5th-generation tensor cores.
+//
+// Replaces the pair loop of merge (merger.py:136-176) over Header.calculate_distance
+// (tools.py:439-493): G = B * B^T with B the N x 4^K matrix of 0/1 presence bits.  This
+// really is a dense contraction, so it runs as tcgen05.mma kind::i8 (u8 x u8 -> s32 in
+// TMEM): exact, because every product is 0 or 1 and one CTA accumulates fewer than 2^31
+// of them.
+//
+// One persistent CTA per SM walks a contiguous slab of the k-mer axis:
+//   warps 0-3  producers: read the packed bitmask words (32 k-mers each) of every sample,
+//              blow every bit up to one byte (0/1) straight into the canonical K-major,
+//              no-swizzle UMMA core-matrix layout in shared memory -- a 32-bit word is
+//              exactly one 32-byte row of one K=32 MMA step -- then fence.proxy.async
+//              and arrive on the stage's "full" mbarrier.
+//   warp 4     one thread issues the MMAs: A and B descriptors point at the SAME tile
+//              (it is a Gram matrix), D[128 x NP] s32 accumulates in TMEM;
+//              tcgen05.commit frees the stage.
+//   warps 0-3  epilogue: tcgen05.ld the accumulator rows, add them into the global
+//              int64 Gram matrix.
+// NP (samples padded) is 64, 128 or 256; 256 uses two M=128 accumulators (all 512 TMEM
+// columns).  M=64 would not be faster than M=128 (half-rate), so for NP=64 the A
+// descriptor simply runs on into the next tile and rows 64..127 of D are ignored.
+#include <algorithm>
+
+#include "common.h"
+
+namespace {
+
+constexpr int kKB = 8;                     // K=32 steps (= bitmask words) per pipeline stage
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = kProducerThreads + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes,
+// LBO = bytes between the two 16-byte K chunks, SBO = bytes between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    return d;                                             // layout_type 0 = no swizzle
+}
+
+// instruction descriptor, kind::i8: D = S32, A = B = unsigned 8 bit, both K-major, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {
+    return (nib * 0x00204081u) & 0x01010101u;
+}
+// one bitmask word -> one 32-byte K-major row: k-mers 0..15 in chunk 0, 16..31 in chunk 1
+__device__ __forceinline__ void expand_word(uint32_t w, uint8_t *row_chunk0, uint32_t lbo) {
+    uint4 lo, hi;
+    lo.x = spread4(w & 15u);         lo.y = spread4((w >> 4) & 15u);
+    lo.z = spread4((w >> 8) & 15u);  lo.w = spread4((w >> 12) & 15u);
+    hi.x = spread4((w >> 16) & 15u); hi.y = spread4((w >> 20) & 15u);
+    hi.z = spread4((w >> 24) & 15u); hi.w = spread4(w >> 28);
+    *reinterpret_cast<uint4 *>(row_chunk0) = lo;
+    *reinterpret_cast<uint4 *>(row_chunk0 + lbo) = hi;
+}
+
+template <int NP>
+struct GramCfg {
+    static constexpr int kStages = NP == 256 ? 3 : 4;
+    static constexpr int kTileBytes = NP * 32;            // one K=32 step of all NP rows
+    static constexpr int kStageBytes = kKB * kTileBytes;
+    static constexpr int kMTiles = NP == 256 ? 2 : 1;
+    static constexpr int kTmemCols = NP == 256 ? 512 : NP;
+    static constexpr int kPad = 4096;                     // the M=128 descriptor of a 64-row tile overruns
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kPad + 256 + 1024;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restrict__ bits, int nsamples,
+                                                          size_t words, size_t stride_words,
+                                                          unsigned long long *__restrict__ gram) {
+    using C = GramCfg<NP>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *ctrl = smem + (size_t)C::kStages * C::kStageBytes + C::kPad;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);               // [kStages]
+    uint64_t *empty_bar = full_bar + C::kStages;                            // [kStages]
+    uint64_t *done_bar = empty_bar + C::kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // this CTA's slab of words, in whole stages of kKB words
+    const size_t total_stages = (words + kKB - 1) / kKB;
+    const size_t per_cta = (total_stages + gridDim.x - 1) / gridDim.x;
+    const size_t st0 = min(total_stages, (size_t)blockIdx.x * per_cta);
+    const size_t st1 = min(total_stages, st0 + per_cta);
+    const size_t nst = st1 - st0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; s++) {
+            mbar_init(smem_u32(&full_bar[s]), kProducerThreads);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero the pad once: it is read (and ignored) by the over-running A descriptor
+    for (int i = threadIdx.x; i < C::kPad / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem + (size_t)C::kStages * C::kStageBytes)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(C::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------ producers
+        // thread -> (row, K-step subset).  NP=64: 2 threads per row, 4 words each;
+        // NP=128: 1 thread per row, 8 words; NP=256: 2 rows per thread, 8 words each.
+        constexpr int kRowsPerThread = NP == 256 ? 2 : 1;
+        constexpr int kWordsPerThread = NP == 64 ? 4 : 8;
+        const int t = threadIdx.x;
+        const int kb0 = NP == 64 ? (t >> 6) * 4 : 0;
+        const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
+        for (size_t it = 0; it < nst; it++) {
+            const int s = (int)(it % C::kStages);
+            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
+            mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+            uint8_t *stage = smem + (size_t)s * C::kStageBytes;
+            const size_t w0 = (st0 + it) * kKB + kb0;
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerThread; rr++) {
+                const int row = (NP == 64 ? (t & 63) : t) + rr * 128;
+                uint32_t wv[kWordsPerThread];
+#pragma unroll
+                for (int k = 0; k < kWordsPerThread; k++) wv[k] = 0;
+                if (row < nsamples) {
+                    const uint32_t *src = bits + (size_t)row * stride_words + w0;
+                    if (vec_ok && w0 + kWordsPerThread <= words) {
+#pragma unroll
+                        for (int k = 0; k < kWordsPerThread; k += 4) {
+                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + k));
+                            wv[k] = q.x; wv[k + 1] = q.y; wv[k + 2] = q.z; wv[k + 3] = q.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kWordsPerThread; k++)
+                            if (w0 + k < words) wv[k] = __ldg(src + k);
+                    }
+                }
+                uint8_t *dst = stage + (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
+#pragma unroll
+                for (int k = 0; k < kWordsPerThread; k++)
+                    expand_word(wv[k], dst + (size_t)(kb0 + k) * C::kTileBytes, 128);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&full_bar[s]));
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = make_idesc(NP);
+        for (size_t it = 0; it < nst; it++) {
+            const int s = (int)(it % C::kStages);
+            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
+            mbar_wait(smem_u32(&full_bar[s]), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t stage = smem_u32(smem + (size_t)s * C::kStageBytes);
+#pragma unroll
+            for (int kb = 0; kb < kKB; kb++) {
+                const uint32_t tile = stage + kb * C::kTileBytes;
+                const uint64_t bdesc = make_desc(tile, 128, 256);
+#pragma unroll
+                for (int mt = 0; mt < C::kMTiles; mt++) {
+                    const uint64_t adesc = make_desc(tile + mt * 128 * 32, 128, 256);
+                    mma_i8(tmem_base + mt * NP, adesc, bdesc, idesc, (it | kb) ? 1u : 0u);
+                }
+            }
+            mma_commit(smem_u32(&empty_bar[s]));          // frees the stage when the MMAs retire
+        }
+        mma_commit(smem_u32(done_bar));
+    }
+
+    if (warp < 4 && nst) {
+        // ------------------------------------------------------------ epilogue
+        mbar_wait(smem_u32(done_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int mt = 0; mt < C::kMTiles; mt++) {
+            const int row = mt * 128 + warp * 32 + lane;
+            if (mt * 128 + warp * 32 >= nsamples) continue;       // warp-uniform
+#pragma unroll 1
+            for (int c0 = 0; c0 < NP; c0 += 32) {
+                if (c0 >= nsamples) break;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NP + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                      "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                      "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                      "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+                      "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < nsamples) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++)
+                        if (c0 + c < nsamples && v[c])
+                            atomicAdd(&gram[(size_t)row * nsamples + c0 + c], (unsigned long long)v[c]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "n"(C::kTmemCols));
+    }
+}
+
+template <int NP>
+int launch_gram_i8(const uint32_t *bits, int nsamples, size_t words, size_t stride_words,
+                   unsigned long long *gram, int device, cudaStream_t st) {
+    using C = GramCfg<NP>;
+    PK_CUDA(cudaFuncSetAttribute(k_gram_i8<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    const size_t total_stages = (words + kKB - 1) / kKB;
+    // a CTA's s32 accumulators must stay below 2^31: at most 2^31 / 32 words each
+    const size_t min_ctas = (words + ((1ull << 25) - 1)) >> 25;
+    size_t grid = (size_t)pk_sm_count(device);
+    grid = std::max(grid, min_ctas);
+    grid = std::max<size_t>(1, std::min(grid, total_stages));
+    k_gram_i8<NP><<<(unsigned)grid, kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+}  // namespace
+
+// gram (int64, nsamples x nsamples, already zeroed or holding a partial sum) += B * B^T
+int pk_gram_i8_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
+                      int64_t *gram_dev, int device, cudaStream_t st) {
+    unsigned long long *g = reinterpret_cast<unsigned long long *>(gram_dev);
+    if (nsamples <= 64) return launch_gram_i8<64>(bits_dev, nsamples, words, stride_words, g, device, st);
+    if (nsamples <= 128) return launch_gram_i8<128>(bits_dev, nsamples, words, stride_words, g, device, st);
+    if (nsamples <= 256) return launch_gram_i8<256>(bits_dev, nsamples, words, stride_words, g, device, st);
+    return pk_set_error(PK_ERR_ARG, "pk_gram_i8_launch: %d samples exceed one tensor-core tile (256)", nsamples);
+}

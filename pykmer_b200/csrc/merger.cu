@@ -9,6 +9,8 @@
 //   k_pair_counts      the literal three sums for one pair of tables
 //   k_synth_table      deterministic synthetic tables for the benchmark
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "common.h"
@@ -271,6 +273,12 @@ PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, 
     if (!accumulate)
         PK_CUDA(cudaMemsetAsync(gram_dev, 0, (size_t)nsamples * nsamples * sizeof(int64_t), st));
     if (words == 0) return PK_OK;
+    // Two exact implementations: tcgen05 kind::i8 tensor-core contraction (N <= 256, the
+    // default: 7x faster at N = 50, profiles/) and AND + popcount on the ALUs (any N).
+    const char *algo = getenv("PYKMER_B200_GRAM");
+    const bool want_popc = algo && strcmp(algo, "popc") == 0;
+    if (!want_popc && nsamples <= 256)
+        return pk_gram_i8_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
     const int npanels = (nsamples + kPanel - 1) / kPanel;
     const int npairs = npanels * (npanels + 1) / 2;
     const size_t nchunks = (words + kWT - 1) / kWT;

@@ -272,9 +272,18 @@ def test_threshold_pack_vs_oracle(env, n, lohi):
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), want)
 
 
+@pytest.fixture(params=["i8", "popc"])
+def gram_algo(request):
+    """Both exact Gram implementations: tcgen05 kind::i8 tensor cores and AND + popcount."""
+    os.environ["PYKMER_B200_GRAM"] = request.param
+    yield request.param
+    os.environ.pop("PYKMER_B200_GRAM", None)
+
+
 @pytest.mark.parametrize("N,words", [(1, 1), (2, 3), (3, 64), (5, 65), (50, 1000), (64, 257),
-                                     (65, 130), (130, 70), (255, 33)])
-def test_gram_vs_oracle(env, N, words):
+                                     (65, 130), (130, 70), (255, 33), (50, 150_001), (128, 40_000),
+                                     (255, 30_000), (256, 9_999)])
+def test_gram_vs_oracle(env, gram_algo, N, words):
     import torch
     rng = np.random.default_rng(N * 1000 + words)
     stride = (words + 3) & ~3
@@ -282,7 +291,11 @@ def test_gram_vs_oracle(env, N, words):
     bits[:, words:] = 0xFFFFFFFF                                  # padding must be ignored
     d = torch.from_numpy(bits.view(np.int32)).cuda()
     G = env["dev"].gram(d, words=words).cpu().numpy()
-    want = env["oracle"].gram_from_bits(bits[:, :words])
+    if N * words > 2_000_000:                                     # big cases: exact Gram by float64 matmul
+        B = np.unpackbits(bits[:, :words].view(np.uint8), axis=1, bitorder="little").astype(np.float32)
+        want = (B.astype(np.float64) @ B.T.astype(np.float64)).astype(np.int64)
+    else:
+        want = env["oracle"].gram_from_bits(bits[:, :words])
     assert np.array_equal(G, want)
     G2 = env["dev"].gram(d, words=words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
     assert np.array_equal(G2.cpu().numpy(), 2 * want)
