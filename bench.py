@@ -191,38 +191,25 @@ def run_reference_arm(args, rank: int, world: int):
 
 
 def run_reference_merger(args):
-    from oracle import oracle
-    from pykmer_b200 import synth
     K, N = args.kmer, args.samples
-    cores = oracle.max_threads()
-    T = 4 ** K
-    n = min(T, 1 << 24)                         # bounded slice of the k-mer axis
-    Ns = min(N, 16)
-    tables = np.stack([synth.synth_table_slice(s, 0, n) for s in range(Ns)])
-    times = []
+    vals = []
+    t0 = time.perf_counter()
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        oracle.merge_matrix(tables, 1, args.max_count, threads=cores)
-        dt = time.perf_counter() - t0
+        v, cores, what = cpu_merger_sample(K, N, args.max_count)
         if it >= args.warmup:
-            times.append(dt)
-    # the reference reads both tables of every pair: N(N-1)/2 pairs * 2 * n bytes; scale to the
-    # bitmask-read metric of the GPU arm by counting the same work units (sample-pairs * k-mers)
-    pair_positions = Ns * (Ns - 1) / 2 * n * len(times) / sum(times)
-    full_pairs = N * (N - 1) / 2
-    t_full = full_pairs * T / pair_positions
-    value = N * T / 8 / t_full / 1e9
+            vals.append(v)
+    wall = time.perf_counter() - t0
+    value = len(vals) / sum(1.0 / v for v in vals)
     name, unit = METRIC["merger"]
     line = {
         "impl": "reference", "metric": name, "value": value, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / (args.warmup + args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": f"merger K={K}, N={N} synthetic samples, --max-count={args.max_count}",
                    "note": "pair loop of the reference (C port), extrapolated from a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": f"{Ns} samples x first {n} k-mers, all pairs; extrapolated to "
-                                   f"{int(full_pairs)} pairs x 4^{K}"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,6 +370,35 @@ def run_indexer(args, rank, local_rank, world):
     ix.close()
 
 
+_MERGER_SAMPLE = {}
+
+
+def cpu_merger_sample(K, N, max_count, repeats=24):
+    """Pair loop of the reference (C port, all host cores) on a bounded slice of the k-mer axis
+    and a subset of the samples, extrapolated to all N(N-1)/2 pairs over 4^K positions."""
+    from oracle import oracle
+    from pykmer_b200 import synth
+    cores = oracle.max_threads()
+    T = 4 ** K
+    n = min(T, 1 << 22)
+    Ns = min(N, 12)
+    key = (K, Ns, n)
+    if key not in _MERGER_SAMPLE:
+        _MERGER_SAMPLE[key] = np.stack([synth.synth_table_slice(s, 0, n) for s in range(Ns)])
+    tables = _MERGER_SAMPLE[key]
+    oracle.merge_matrix(tables[:2], 1, max_count, threads=cores)      # warm the thread pool / pages
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        oracle.merge_matrix(tables, 1, max_count, threads=cores)
+    dt = (time.perf_counter() - t0) / repeats
+    pair_positions = Ns * (Ns - 1) / 2 * n / dt
+    full_pairs = N * (N - 1) / 2
+    t_full = full_pairs * T / pair_positions
+    what = (f"{Ns} samples x first {n} k-mers, all {Ns * (Ns - 1) // 2} pairs, {repeats} repeats of {dt:.3f} s on {cores} "
+            f"threads; extrapolated to {int(full_pairs)} pairs x 4^{K} positions ({t_full:.0f} s)")
+    return N * T / 8 / t_full / 1e9, cores, what
+
+
 def run_merger(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -421,28 +437,70 @@ def run_merger(args, rank, local_rank, world):
     ms_step = ms / args.steps
     bytes_bits = N * T / 8
     value = bytes_bits / (ms_step * 1e-3) / 1e9
-    peak, peak_src = measured_peak()
-    pairs = N * (N + 1) / 2
-    popc = pairs * T / 32
+    hbm_peak, peak_src = measured_peak()
+    algo = os.environ.get("PYKMER_B200_GRAM", "i8" if N <= 256 else "popc")
+    Gh = G.cpu().numpy()
+
+    # end to end through the C ABI with HOST tables (pk_merge_host): pinned copy in, pack, Gram
+    e2e = None
+    if not args.no_e2e and world == 1:
+        host = []
+        for s in range(N):
+            dev.synth_table(s, 0, T, out=raw)
+            h = dev.pinned_empty(T)
+            h.copy_(raw)
+            host.append(h.numpy())
+        torch.cuda.synchronize()
+        reps = 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m = dev.merge_host(host, 1, args.max_count, device=local_rank)
+        dt = (time.perf_counter() - t0) / reps
+        assert int(m[0, 1, 2]) == int(Gh[0, 1]) and int(m[0, 0, 0]) == int(Gh[0, 0])
+        e2e = {"value": bytes_bits / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(N * T),
+               "d2h_bytes_per_step": int(N * N * 8), "ms_per_step": dt * 1e3,
+               "table_bytes_per_s": N * T / dt}
+        del host
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, what = cpu_merger_sample(K, N, args.max_count)
+        cpu = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port", "sample": what,
+               "reference_published": "25.7 s per K=15 pair incl. gunzip (pypy, reference README.md:75-77)"}
+
     if rank == 0:
         name, unit = METRIC["merger"]
-        Gh = G.cpu().numpy()
+        if algo == "i8":
+            # dense contraction on the tensor pipe: 2 * N^2 * 4^K int8 ops (true N, no padding credit)
+            ops = 2.0 * N * N * T
+            peak_t = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 2.0 * 1590.0
+            ach = ops / (ms_step * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_gram_i8", "achieved": ach, "peak": peak_t,
+                    "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": None,
+                    "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json); int8 ops, nominal dense 4500",
+                    "hbm_GBps": value, "hbm_frac": value / hbm_peak}
+        else:
+            popc = N * (N + 1) / 2 * T / 32
+            roof = {"bound": "hbm", "kernel": "k_gram_popc", "achieved": value, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": value / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "and_popc_per_s": popc / (ms_step * 1e-3), "and_popc_peak_measured": 4.378e12}
         line = {
             "metric": name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount -> int64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 x u8 -> s32 (tcgen05 kind::i8) -> int64" if algo == "i8" else "u32 popcount -> int64",
+            "data": "synthetic",
             "config": {"workload": f"merger K={K}, N={N} synthetic samples, --max-count={args.max_count}; "
                                    f"Gram stage over {bytes_bits / 1e9:.2f} GB of presence bitmask",
                        "parallelism": f"kmer-axis x{world}" if world > 1 else "single GPU",
-                       "l2": f"bitmask {bytes_bits / 1e9:.2f} GB >> 126 MB L2",
+                       "l2": f"bitmask {bytes_bits / 1e9:.2f} GB >> 126 MB L2", "algo": algo,
                        "pack_ms_total": pack_ms, "pack_GBps": N * n * 1.125 / (pack_ms * 1e-3) / 1e9,
                        "trace_G": int(np.trace(Gh)), "G01": int(Gh[0, 1])},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_gram_popc", "achieved": value, "peak": peak,
-                         "unit": "GB/s", "frac": value / peak, "traffic": None, "peak_source": peak_src,
-                         "and_popc_per_s": popc / (ms_step * 1e-3)},
-            "e2e": None, "gpu_launches": args.steps,
+            "clocks": clocks, "roofline": roof, "e2e": e2e, "gpu_launches": args.steps,
         }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
 
 
