@@ -156,42 +156,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
         // NP=128: 1 thread per row, 8 words; NP=256: 2 rows per thread, 8 words each.
         constexpr int kRowsPerThread = NP == 256 ? 2 : 1;
         constexpr int kWordsPerThread = NP == 64 ? 4 : 8;
+        // global-load lookahead, in stages: a stage lasts 8 x 32 MMA cycles at NP=64 but a
+        // DRAM round trip is ~1500 cycles, so the words of several stages are kept in flight
+        constexpr int kAhead = NP == 64 ? 6 : (NP == 128 ? 3 : 2);
         const int t = threadIdx.x;
         const int kb0 = NP == 64 ? (t >> 6) * 4 : 0;
         const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
-        for (size_t it = 0; it < nst; it++) {
-            const int s = (int)(it % C::kStages);
-            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
-            mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-            uint8_t *stage = smem + (size_t)s * C::kStageBytes;
+        uint32_t wv[kAhead][kRowsPerThread][kWordsPerThread];
+
+        auto fetch = [&](uint32_t (&dst)[kRowsPerThread][kWordsPerThread], size_t it) {
             const size_t w0 = (st0 + it) * kKB + kb0;
 #pragma unroll
             for (int rr = 0; rr < kRowsPerThread; rr++) {
                 const int row = (NP == 64 ? (t & 63) : t) + rr * 128;
-                uint32_t wv[kWordsPerThread];
 #pragma unroll
-                for (int k = 0; k < kWordsPerThread; k++) wv[k] = 0;
-                if (row < nsamples) {
+                for (int k = 0; k < kWordsPerThread; k++) dst[rr][k] = 0;
+                if (row < nsamples && it < nst) {
                     const uint32_t *src = bits + (size_t)row * stride_words + w0;
                     if (vec_ok && w0 + kWordsPerThread <= words) {
 #pragma unroll
                         for (int k = 0; k < kWordsPerThread; k += 4) {
                             const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + k));
-                            wv[k] = q.x; wv[k + 1] = q.y; wv[k + 2] = q.z; wv[k + 3] = q.w;
+                            dst[rr][k] = q.x; dst[rr][k + 1] = q.y; dst[rr][k + 2] = q.z; dst[rr][k + 3] = q.w;
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < kWordsPerThread; k++)
-                            if (w0 + k < words) wv[k] = __ldg(src + k);
+                            if (w0 + k < words) dst[rr][k] = __ldg(src + k);
                     }
                 }
+            }
+        };
+        auto produce = [&](const uint32_t (&src)[kRowsPerThread][kWordsPerThread], size_t it) {
+            const int s = (int)(it % C::kStages);
+            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
+            mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+            uint8_t *stage = smem + (size_t)s * C::kStageBytes;
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerThread; rr++) {
+                const int row = (NP == 64 ? (t & 63) : t) + rr * 128;
                 uint8_t *dst = stage + (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
 #pragma unroll
                 for (int k = 0; k < kWordsPerThread; k++)
-                    expand_word(wv[k], dst + (size_t)(kb0 + k) * C::kTileBytes, 128);
+                    expand_word(src[rr][k], dst + (size_t)(kb0 + k) * C::kTileBytes, 128);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&full_bar[s]));
+        };
+
+#pragma unroll
+        for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)p);
+        for (size_t it = 0; it < nst; it += kAhead) {
+#pragma unroll
+            for (int p = 0; p < kAhead; p++) {
+                if (it + p < nst) {
+                    produce(wv[p], it + p);
+                    fetch(wv[p], it + p + kAhead);
+                }
+            }
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------ MMA issuer
