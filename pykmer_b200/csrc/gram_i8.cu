@@ -98,7 +98,8 @@ __device__ __forceinline__ void expand_word(uint32_t w, uint8_t *row_chunk0, uin
 
 template <int NP>
 struct GramCfg {
-    static constexpr int kStages = NP == 256 ? 3 : 4;
+    static constexpr int kGroups = NP == 256 ? 1 : 4;     // producer groups filling stages in parallel
+    static constexpr int kStages = NP == 256 ? 3 : (NP == 128 ? 4 : 8);
     static constexpr int kTileBytes = NP * 32;            // one K=32 step of all NP rows
     static constexpr int kStageBytes = kKB * kTileBytes;
     static constexpr int kMTiles = NP == 256 ? 2 : 1;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; s++) {
-            mbar_init(smem_u32(&full_bar[s]), kProducerThreads);
+            mbar_init(smem_u32(&full_bar[s]), kProducerThreads / C::kGroups);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(done_bar), 1);
@@ -152,66 +153,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
 
     if (warp < 4) {
         // ------------------------------------------------------------ producers
-        // thread -> (row, K-step subset).  NP=64: 2 threads per row, 4 words each;
-        // NP=128: 1 thread per row, 8 words; NP=256: 2 rows per thread, 8 words each.
-        constexpr int kRowsPerThread = NP == 256 ? 2 : 1;
-        constexpr int kWordsPerThread = NP == 64 ? 4 : 8;
-        // global-load lookahead, in stages: a stage lasts 8 x 32 MMA cycles at NP=64 but a
-        // DRAM round trip is ~1500 cycles, so the words of several stages are kept in flight
-        constexpr int kAhead = NP == 64 ? 6 : (NP == 128 ? 3 : 2);
-        const int t = threadIdx.x;
-        const int kb0 = NP == 64 ? (t >> 6) * 4 : 0;
+        // Producer GROUPS work on different stages at the same time (a stage's latency chain
+        // -- wait, expand, proxy fence, arrive -- is much longer than its 8 x 32 MMA cycles at
+        // NP=64): for NP <= 128 every warp is a group and fills whole stages on its own, for
+        // NP = 256 the four warps fill one stage together.  Group g takes stages g, g+G, ...
+        constexpr int kGroups = C::kGroups;
+        constexpr int kGroupThreads = kProducerThreads / kGroups;
+        constexpr int kRowsPerThread = NP / kGroupThreads;
+        constexpr int kAhead = 2;                  // stages of global loads in flight per group
+        const int group = threadIdx.x / kGroupThreads, tg = threadIdx.x % kGroupThreads;
         const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
-        uint32_t wv[kAhead][kRowsPerThread][kWordsPerThread];
+        uint32_t wv[kAhead][kRowsPerThread][kKB];
 
-        auto fetch = [&](uint32_t (&dst)[kRowsPerThread][kWordsPerThread], size_t it) {
-            const size_t w0 = (st0 + it) * kKB + kb0;
+        auto fetch = [&](uint32_t (&dst)[kRowsPerThread][kKB], size_t it) {
+            const size_t w0 = (st0 + it) * kKB;
 #pragma unroll
             for (int rr = 0; rr < kRowsPerThread; rr++) {
-                const int row = (NP == 64 ? (t & 63) : t) + rr * 128;
+                const int row = tg + rr * kGroupThreads;
 #pragma unroll
-                for (int k = 0; k < kWordsPerThread; k++) dst[rr][k] = 0;
+                for (int k = 0; k < kKB; k++) dst[rr][k] = 0;
                 if (row < nsamples && it < nst) {
                     const uint32_t *src = bits + (size_t)row * stride_words + w0;
-                    if (vec_ok && w0 + kWordsPerThread <= words) {
+                    if (vec_ok && w0 + kKB <= words) {
 #pragma unroll
-                        for (int k = 0; k < kWordsPerThread; k += 4) {
+                        for (int k = 0; k < kKB; k += 4) {
                             const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + k));
                             dst[rr][k] = q.x; dst[rr][k + 1] = q.y; dst[rr][k + 2] = q.z; dst[rr][k + 3] = q.w;
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < kWordsPerThread; k++)
+                        for (int k = 0; k < kKB; k++)
                             if (w0 + k < words) dst[rr][k] = __ldg(src + k);
                     }
                 }
             }
         };
-        auto produce = [&](const uint32_t (&src)[kRowsPerThread][kWordsPerThread], size_t it) {
+        auto produce = [&](const uint32_t (&src)[kRowsPerThread][kKB], size_t it) {
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
             uint8_t *stage = smem + (size_t)s * C::kStageBytes;
 #pragma unroll
             for (int rr = 0; rr < kRowsPerThread; rr++) {
-                const int row = (NP == 64 ? (t & 63) : t) + rr * 128;
+                const int row = tg + rr * kGroupThreads;
                 uint8_t *dst = stage + (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
 #pragma unroll
-                for (int k = 0; k < kWordsPerThread; k++)
-                    expand_word(src[rr][k], dst + (size_t)(kb0 + k) * C::kTileBytes, 128);
+                for (int k = 0; k < kKB; k++)
+                    expand_word(src[rr][k], dst + (size_t)k * C::kTileBytes, 128);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&full_bar[s]));
         };
 
 #pragma unroll
-        for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)p);
-        for (size_t it = 0; it < nst; it += kAhead) {
+        for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)group + (size_t)p * kGroups);
+        for (size_t it = group; it < nst; it += (size_t)kAhead * kGroups) {
 #pragma unroll
             for (int p = 0; p < kAhead; p++) {
-                if (it + p < nst) {
-                    produce(wv[p], it + p);
-                    fetch(wv[p], it + p + kAhead);
+                const size_t cur = it + (size_t)p * kGroups;
+                if (cur < nst) {
+                    produce(wv[p], cur);
+                    fetch(wv[p], cur + (size_t)kAhead * kGroups);
                 }
             }
         }
