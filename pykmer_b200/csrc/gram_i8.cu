@@ -26,9 +26,8 @@
 
 namespace {
 
-constexpr int kKB = 8;                     // K=32 steps (= bitmask words) per pipeline stage
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = kProducerThreads + 32;
+// per-config constants live in GramCfg<NP>: K=32 steps (= bitmask words) per pipeline stage,
+// producer warps, stage ring depth
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -98,8 +97,15 @@ __device__ __forceinline__ void expand_word(uint32_t w, uint8_t *row_chunk0, uin
 
 template <int NP>
 struct GramCfg {
-    static constexpr int kGroups = NP == 256 ? 1 : 4;     // producer groups filling stages in parallel
-    static constexpr int kStages = NP == 256 ? 3 : (NP == 128 ? 4 : 8);
+    // The bit -> byte expansion is ALU work with short dependent chains: it needs several warps per
+    // scheduler to run near issue rate, so small NP (cheap MMAs, 8 x 32 cycles per stage at NP=64)
+    // gets 8 producer warps, each filling whole stages on its own.
+    static constexpr int kProducerWarps = NP == 256 ? 4 : 8;
+    static constexpr int kProducerThreads = kProducerWarps * 32;
+    static constexpr int kThreads = kProducerThreads + 32;            // + the MMA-issuing warp
+    static constexpr int kGroups = NP == 256 ? 1 : 8;     // producer groups filling stages in parallel
+    static constexpr int kKB = NP == 128 ? 4 : 8;         // K=32 steps (bitmask words) per stage
+    static constexpr int kStages = NP == 256 ? 3 : 8;
     static constexpr int kTileBytes = NP * 32;            // one K=32 step of all NP rows
     static constexpr int kStageBytes = kKB * kTileBytes;
     static constexpr int kMTiles = NP == 256 ? 2 : 1;
@@ -109,10 +115,13 @@ struct GramCfg {
 };
 
 template <int NP>
-__global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restrict__ bits, int nsamples,
+__global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint32_t *__restrict__ bits, int nsamples,
                                                           size_t words, size_t stride_words,
                                                           unsigned long long *__restrict__ gram) {
     using C = GramCfg<NP>;
+    constexpr int kKB = C::kKB;
+    constexpr int kProducerThreads = C::kProducerThreads;
+    constexpr int kMmaWarp = C::kProducerWarps;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *ctrl = smem + (size_t)C::kStages * C::kStageBytes + C::kPad;
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
     // zero the pad once: it is read (and ignored) by the over-running A descriptor
     for (int i = threadIdx.x; i < C::kPad / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + (size_t)C::kStages * C::kStageBytes)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)), "n"(C::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < kMmaWarp) {
         // ------------------------------------------------------------ producers
         // Producer GROUPS work on different stages at the same time (a stage's latency chain
         // -- wait, expand, proxy fence, arrive -- is much longer than its 8 x 32 MMA cycles at
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_i8(const uint32_t *__restr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "n"(C::kTmemCols));
     }
@@ -286,6 +295,7 @@ template <int NP>
 int launch_gram_i8(const uint32_t *bits, int nsamples, size_t words, size_t stride_words,
                    unsigned long long *gram, int device, cudaStream_t st) {
     using C = GramCfg<NP>;
+    constexpr int kKB = C::kKB;
     PK_CUDA(cudaFuncSetAttribute(k_gram_i8<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const size_t total_stages = (words + kKB - 1) / kKB;
     // a CTA's s32 accumulators must stay below 2^31: at most 2^31 / 32 words each
@@ -293,7 +303,7 @@ int launch_gram_i8(const uint32_t *bits, int nsamples, size_t words, size_t stri
     size_t grid = (size_t)pk_sm_count(device);
     grid = std::max(grid, min_ctas);
     grid = std::max<size_t>(1, std::min(grid, total_stages));
-    k_gram_i8<NP><<<(unsigned)grid, kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
+    k_gram_i8<NP><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
