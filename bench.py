@@ -252,30 +252,19 @@ def run_indexer(args, rank, local_rank, world):
     T = 4 ** K
     stream, starts, lengths = load_stream(args.scale, rank, world)
     L = int(sum(lengths))
-    # k-mer-axis shard of this rank (contiguous range, multiple of 4 KiB)
-    lo = (T * rank // world) & ~4095
-    hi = T if rank == world - 1 else (T * (rank + 1) // world) & ~4095
+    from pykmer_b200 import dist as pdist
+    lo, hi = pdist.shard_range(T, rank, world)               # k-mer-axis shard of this rank
 
     d_stream = torch.from_numpy(stream).cuda()
     ix = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=args.mode)
     ix.set_records(starts)
-    red = torch.zeros(260, dtype=torch.int64, device="cuda")
     last = {}
 
     def step_device():
         ix.reset()
         ix.feed_device(d_stream)
         hist, st = ix.finalize()
-        if world > 1:                                         # hist[255] + sums; min/max separately
-            red[:255] = torch.tensor(hist, dtype=torch.int64)
-            red[255] = st["num_kmers"]; red[256] = st["vals_sum"]; red[257] = st["vals_count"]
-            dist.all_reduce(red, op=dist.ReduceOp.SUM)
-            mm = torch.tensor([-st["vals_min"], st["vals_max"]], dtype=torch.int64, device="cuda")
-            dist.all_reduce(mm, op=dist.ReduceOp.MAX)
-            r = red.cpu().tolist(); m2 = mm.cpu().tolist()
-            hist = r[:255]
-            st = {"num_kmers": r[255], "vals_sum": r[256], "vals_count": r[257],
-                  "vals_min": -m2[0], "vals_max": m2[1]}
+        hist, st = pdist.reduce_index_stats(hist, st)         # one small NCCL all-reduce
         last["hist"], last["st"] = hist, st
 
     sampler = ClockSampler(local_rank)
@@ -406,8 +395,8 @@ def run_merger(args, rank, local_rank, world):
 
     K, N = args.kmer, args.samples
     T = 4 ** K
-    lo = (T * rank // world) & ~4095
-    hi = T if rank == world - 1 else (T * (rank + 1) // world) & ~4095
+    from pykmer_b200 import dist as pdist
+    lo, hi = pdist.shard_range(T, rank, world)
     n = hi - lo
     words = n // 32
     stride = (words + 3) & ~3
@@ -427,8 +416,7 @@ def run_merger(args, rank, local_rank, world):
 
     def step():
         dev.gram(bits, words=words, out=G, accumulate=False)
-        if world > 1:
-            dist.all_reduce(G, op=dist.ReduceOp.SUM)
+        pdist.reduce_gram(G)                                  # N x N int64 partials, NCCL all-reduce
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -1,0 +1,100 @@
+"""world_size-2 gloo test (CPU): the host-side logic of the k-mer-axis sharding -- shard
+ranges tile the axis, per-shard statistics / record flags / partial Gram matrices reduce to
+those of the whole job.  The per-shard numbers come from the CPU oracle (this is a test of
+the reduction logic, not of the kernels)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %(root)r)
+    import numpy as np, torch, torch.distributed as dist
+    from oracle import oracle
+    from pykmer_b200 import dist as pdist
+    dist.init_process_group("gloo")
+    rank, world = pdist.world()
+    K = 9
+    T = 4 ** K
+    rng = np.random.default_rng(11)
+    seq = np.frombuffer(b"ACGTNacgt>", dtype=np.uint8)[rng.integers(0, 10, size=60_000)].copy()
+    seq[5000:6000] = ord("A")
+    starts = np.array([0, 10_000, 10_001, 40_000], dtype=np.uint64)
+    lo, hi = pdist.shard_range(T, rank, world, align=64)
+    table, num, flags = oracle.index_stream(seq, K, range_lo=lo, range_hi=hi, rec_starts=starts)
+    hist, st = oracle.table_stats(table)
+    st = {"num_kmers": num, "vals_sum": st["vals_sum"], "vals_count": st["vals_count"],
+          "vals_min": st["vals_min"], "vals_max": st["vals_max"]}
+    hist_all, st_all = pdist.reduce_index_stats(hist, st)
+    flags_all = pdist.reduce_flags(flags)
+    # merger: each rank contracts its slice of the k-mer axis
+    tables = np.stack([np.random.default_rng(100 + s).integers(0, 4, size=T, dtype=np.uint8) for s in range(5)])
+    bits = np.stack([oracle.threshold_pack(t[lo:hi], 1, 2) for t in tables])
+    G = torch.from_numpy(oracle.gram_from_bits(bits))
+    pdist.reduce_gram(G)
+    # stream broadcast
+    chunk = torch.from_numpy(seq.copy()) if rank == 0 else None
+    got = pdist.broadcast_stream(chunk, seq.size)
+    out = {"rank": rank, "lo": lo, "hi": hi, "hist": hist_all, "st": st_all, "flags": flags_all.tolist(),
+           "G": G.tolist(), "bcast_ok": bool(np.array_equal(got.numpy(), seq))}
+    json.dump(out, open(os.path.join(%(out)r, f"rank{rank}.json"), "w"))
+    dist.destroy_process_group()
+""")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_ranges_tile_the_axis():
+    from pykmer_b200 import dist as pdist
+    for total in (4 ** 5, 4 ** 9, 4 ** 15, 4 ** 19):
+        for n in (1, 2, 3, 4, 8):
+            cuts = [pdist.shard_range(total, r, n) for r in range(n)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+            assert all(lo % 4096 == 0 for lo, _ in cuts)
+
+
+def test_two_rank_reductions_equal_the_whole_job(tmp_path):
+    import json
+    from oracle import oracle
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out
+    res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
+    # the whole job on one "rank"
+    K, T = 9, 4 ** 9
+    rng = np.random.default_rng(11)
+    seq = np.frombuffer(b"ACGTNacgt>", dtype=np.uint8)[rng.integers(0, 10, size=60_000)].copy()
+    seq[5000:6000] = ord("A")
+    starts = np.array([0, 10_000, 10_001, 40_000], dtype=np.uint64)
+    table, num, flags = oracle.index_stream(seq, K, rec_starts=starts)
+    hist, st = oracle.table_stats(table)
+    tables = np.stack([np.random.default_rng(100 + s).integers(0, 4, size=T, dtype=np.uint8) for s in range(5)])
+    G = oracle.gram_from_bits(np.stack([oracle.threshold_pack(t, 1, 2) for t in tables]))
+    assert res[0]["hi"] == res[1]["lo"] and res[0]["lo"] == 0 and res[1]["hi"] == T
+    for r in res:
+        assert r["bcast_ok"]
+        assert r["hist"] == hist
+        assert r["st"] == {"num_kmers": num, "vals_sum": st["vals_sum"], "vals_count": st["vals_count"],
+                           "vals_min": st["vals_min"], "vals_max": st["vals_max"]}
+        assert r["flags"] == flags.tolist()
+        assert np.array_equal(np.array(r["G"]), G)
