@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ sc
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t x = commit_quad(c[u], old[u], ACCUM);
-            sv[i + u * stride] = zero;
+            if (c[u].x | c[u].y | c[u].z | c[u].w) sv[i + u * stride] = zero;   // sparse tables: mostly clean
             __stcs(tw + i + u * stride, x);
             tally(x);
         }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) k_window_commit(uint32_t *__restrict__ sc
     for (; i < nq; i += stride) {
         const uint4 c = __ldcg(sv + i);
         const uint32_t x = commit_quad(c, ACCUM ? tw[i] : 0u, ACCUM);
-        sv[i] = zero;
+        if (c.x | c.y | c.z | c.w) sv[i] = zero;
         __stcs(tw + i, x);
         tally(x);
     }
