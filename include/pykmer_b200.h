@@ -71,6 +71,9 @@ int         pk_host_free(void *ptr);
                                  (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 shrink the
                                  window and the k-mer buffer; they exist for the tests.) */
 
+#define PK_MODE_SCAN      3   /* scan + bucket only (no table): the scanning half of the
+                                 sequence-sharded multi-GPU path, see pk_indexer_export_segments */
+
 int pk_indexer_create(pk_indexer **out, int kmer_len, int device,
                       uint64_t range_lo, uint64_t range_hi, int mode);
 int pk_indexer_destroy(pk_indexer *ix);
@@ -113,6 +116,33 @@ int pk_indexer_table_device(pk_indexer *ix, const uint8_t **table_dev, size_t *b
 int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t offset, size_t bytes);
 /* launches of this library's kernels issued through the handle so far */
 int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches);
+/* ---- sequence-sharded multi-GPU indexing -----------------------------------------------
+ * Instead of every GPU scanning the whole sequence, each rank scans 1/N of it with a
+ * PK_MODE_SCAN handle over the FULL k-mer range, the bucketed k-mer entries are exchanged
+ * (all-to-all over NVLink, done by the caller, e.g. torch.distributed / NCCL) so that every
+ * entry reaches the rank that owns its table window, and a PK_MODE_PARTITION handle over the
+ * rank's own k-mer range counts them.  Window w of the scanner covers k-mers
+ * [range_lo + w * 2^24, +2^24); shard boundaries must be multiples of 2^24.
+ *
+ * pk_indexer_prime: start a slice in the middle of the stream -- the up-to-32 bytes that
+ *   precede it become the window carry (no k-mer is counted for them) and stream_off is the
+ *   stream offset of the next byte fed (record flags use it).
+ * pk_indexer_export_segments: device pointer of the entry buffer and, per fed segment and
+ *   window, the offset and count of its entries (host arrays of nseg * nwindows uint32;
+ *   pass NULL arrays to query nseg / nwindows).  Synchronises.
+ * pk_indexer_import_segments: hand a PARTITION handle entries gathered elsewhere: segment s,
+ *   local window w has seg_cnt[s * nwindows + w] entries at entries_dev + seg_off[...].
+ *   entries_dev must stay valid until the next finalize.
+ * pk_indexer_scan_result: number of windows counted by a scanner (its share of num_kmers). */
+int pk_indexer_prime(pk_indexer *ix, const uint8_t *halo_dev, size_t n, uint64_t stream_off,
+                     pk_stream stream);
+int pk_indexer_scan_result(pk_indexer *ix, uint64_t *num_kmers);
+int pk_indexer_export_segments(pk_indexer *ix, const uint32_t **entries_dev, uint32_t *nseg,
+                               uint32_t *nwindows, uint32_t *seg_off_host, uint32_t *seg_cnt_host,
+                               size_t capacity);
+int pk_indexer_import_segments(pk_indexer *ix, const uint32_t *entries_dev, uint32_t nseg,
+                               const uint32_t *seg_off_host, const uint32_t *seg_cnt_host);
+
 /* Per-kernel-class device time, measured with CUDA events on the launching stream
  * around every launch made through the handle while enabled.  Classes (index into
  * ms_host / launches_host): 0 scan_count_direct, 1 scan_bucket_count, 2 bucket_offsets,

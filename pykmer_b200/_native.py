@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpykmer_b200.so")
 
-PK_MODE_AUTO, PK_MODE_DIRECT, PK_MODE_PARTITION = 0, 1, 2
+PK_MODE_AUTO, PK_MODE_DIRECT, PK_MODE_PARTITION, PK_MODE_SCAN = 0, 1, 2, 3
 
 # every symbol include/pykmer_b200.h declares (tests check that all of them resolve)
 SYMBOLS = (
@@ -23,6 +23,8 @@ SYMBOLS = (
     "pk_indexer_finalize_to_host",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
     "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_set_profiling", "pk_indexer_profile",
+    "pk_indexer_prime", "pk_indexer_scan_result", "pk_indexer_export_segments",
+    "pk_indexer_import_segments",
     "pk_table_stats_device",
     "pk_threshold_pack_device", "pk_gram_device", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device",
@@ -71,6 +73,11 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_mode": [vp, c.POINTER(i32), c.POINTER(i32)],
         "pk_indexer_set_profiling": [vp, i32],
         "pk_indexer_profile": [vp, vp, vp],
+        "pk_indexer_prime": [vp, vp, sz, u64, vp],
+        "pk_indexer_scan_result": [vp, c.POINTER(u64)],
+        "pk_indexer_export_segments": [vp, c.POINTER(vp), c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
+                                       vp, vp, sz],
+        "pk_indexer_import_segments": [vp, vp, c.c_uint32, vp, vp],
         "pk_table_stats_device": [vp, sz, vp, vp, vp],
         "pk_threshold_pack_device": [vp, sz, i32, i32, vp, vp],
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],

@@ -43,7 +43,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr size_t kStageBytes = 32u << 20;   // pinned-copy chunk of feed_host
 constexpr int kCarry = 32;                  // bytes of stream tail kept between feeds
-constexpr int kMaxBuckets = 4096;           // windows per handle in PARTITION mode
+constexpr int kMaxBuckets = 16384;          // windows per handle in PARTITION / SCAN mode
 constexpr int kMaxSegments = 128;           // feeds buffered between two flushes
 constexpr size_t kMaxFeed = 256u << 20;     // bases per partition pass
 constexpr int kTileEntries = kScanWarps * 31 * 16;   // most entries one block tile can emit
@@ -586,6 +586,7 @@ struct pk_indexer {
     // PARTITION mode
     uint32_t win_log2 = 24, nbuckets = 0;
     uint32_t *pool = nullptr;                  // buffered entries
+    const uint32_t *pool_ext = nullptr;        // entries imported from other ranks (pk_indexer_import_segments)
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
     uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
     uint32_t *cursor = nullptr;                // device pool cursor
@@ -680,7 +681,7 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
             cfg.gridDim = dim3(grid);
-            PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, (const uint32_t *)ix->pool,
+            PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool,
                                        (const uint32_t *)seg_off(ix, 0), (const uint32_t *)seg_cnt(ix, 0),
                                        ix->nseg, ix->nbuckets, b, ix->scratch));
             ix->launches++;
@@ -728,6 +729,7 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
     PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
     ix->nseg = 0;
     ix->pool_ub = 0;
+    ix->pool_ext = nullptr;
     ix->table_valid = true;
     ix->stats_valid = with_stats;
     return PK_OK;
@@ -764,6 +766,9 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         ix->launches += 1;
     } else {
         if (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap) {
+            if (ix->mode == PK_MODE_SCAN)
+                return pk_set_error(PK_ERR_STATE, "scan-only handle: k-mer buffer full (%zu entries, %d segments); "
+                                    "export and reset before feeding more", ix->pool_cap, ix->nseg);
             const int rc = indexer_flush(ix, st, false, nullptr);
             if (rc != PK_OK) return rc;
         }
@@ -813,7 +818,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
 
 // feeds are cut so that one partition pass never exceeds kMaxFeed bases
 static int indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st) {
-    const size_t step = ix->mode == PK_MODE_PARTITION ? std::min(kMaxFeed, ix->pool_cap) : n;
+    const size_t step = ix->mode != PK_MODE_DIRECT ? std::min(kMaxFeed, ix->pool_cap) : n;
     size_t off = 0;
     while (off < n) {
         const size_t len = std::min(step, n - off);
@@ -835,8 +840,8 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     if (range_hi == 0) range_hi = T;
     PK_REQUIRE(range_lo < range_hi && range_hi <= T, "pk_indexer_create: bad range [%llu, %llu) for 4^K = %llu",
                (unsigned long long)range_lo, (unsigned long long)range_hi, (unsigned long long)T);
-    PK_REQUIRE(mode == PK_MODE_AUTO || mode == PK_MODE_DIRECT || mode == PK_MODE_PARTITION,
-               "pk_indexer_create: unknown mode %d", mode);
+    PK_REQUIRE(mode == PK_MODE_AUTO || mode == PK_MODE_DIRECT || mode == PK_MODE_PARTITION ||
+               mode == PK_MODE_SCAN, "pk_indexer_create: unknown mode %d", mode);
     int ndev = 0;
     PK_CUDA(cudaGetDeviceCount(&ndev));
     PK_REQUIRE(device >= 0 && device < ndev, "pk_indexer_create: device %d of %d", device, ndev);
@@ -860,7 +865,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     if (mode == PK_MODE_AUTO)
         mode = (ix->table_bytes > (1ull << 26) && nb <= (uint64_t)kMaxBuckets) ? PK_MODE_PARTITION
                                                                               : PK_MODE_DIRECT;
-    if (mode == PK_MODE_PARTITION && nb > (uint64_t)kMaxBuckets) {
+    if ((mode == PK_MODE_PARTITION || mode == PK_MODE_SCAN) && nb > (uint64_t)kMaxBuckets) {
         delete ix;
         return pk_set_error(PK_ERR_ARG, "pk_indexer_create: range needs %llu windows, at most %d "
                             "are supported in PARTITION mode", (unsigned long long)nb, kMaxBuckets);
@@ -872,7 +877,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     const size_t alloc = (ix->table_bytes + 255) & ~(size_t)255;
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    step(cudaMalloc(&ix->table, alloc));
+    if (mode != PK_MODE_SCAN) step(cudaMalloc(&ix->table, alloc));     // a scanner owns no table
     step(cudaMalloc(&ix->carry, 64));
     step(cudaMalloc(&ix->counters, 257 * sizeof(unsigned long long)));
     step(cudaHostAlloc(&ix->h_counters, 257 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -884,7 +889,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     }
     step(cudaEventCreateWithFlags(&ix->joined, cudaEventDisableTiming));
     ix->last_stream = ix->work_stream;
-    if (mode == PK_MODE_PARTITION && e == cudaSuccess) {
+    if ((mode == PK_MODE_PARTITION || mode == PK_MODE_SCAN) && e == cudaSuccess) {
         size_t free_b = 0, total_b = 0;
         step(cudaMemGetInfo(&free_b, &total_b));
         size_t cap = (size_t)1 << 30;                      // 2^30 entries = 4 GiB
@@ -898,13 +903,15 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->pool, cap * sizeof(uint32_t)));
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
-        step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
-        step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
+        if (mode == PK_MODE_PARTITION) {
+            step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+            step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
+        }
         for (int i = 0; i < 2; i++)
             step(cudaEventCreateWithFlags(&ix->committed[i], cudaEventDisableTiming));
         // persisting-L2 carve-out for the counters (PYKMER_B200_L2_PERSIST=0 disables it)
         const char *pe = getenv("PYKMER_B200_L2_PERSIST");
-        if (e == cudaSuccess && !(pe && atoi(pe) == 0)) {
+        if (e == cudaSuccess && mode == PK_MODE_PARTITION && !(pe && atoi(pe) == 0)) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
@@ -922,7 +929,8 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         if (e == cudaSuccess) {
             step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
             step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));
-            step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
+            if (ix->scratch)
+                step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
         }
     }
     if (e == cudaSuccess) {
@@ -987,6 +995,7 @@ PK_API int pk_indexer_reset(pk_indexer *ix, pk_stream stream) {
         PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
         ix->nseg = 0;
         ix->pool_ub = 0;
+        ix->pool_ext = nullptr;
         ix->table_valid = false;
         ix->stats_valid = false;
     }
@@ -1095,6 +1104,9 @@ static int indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t sta
                             uint8_t *table_host) {
     PK_REQUIRE(ix != nullptr, "pk_indexer_finalize: NULL handle");
     PK_REQUIRE(hist_host != nullptr && stats_host != nullptr, "pk_indexer_finalize: NULL output");
+    if (ix->mode == PK_MODE_SCAN)
+        return pk_set_error(PK_ERR_STATE, "pk_indexer_finalize: a scan-only handle has no table; export its "
+                            "segments to the handles that own the windows");
     pk_device_guard guard(ix->device);
     bool copied = false;
     {
@@ -1164,6 +1176,8 @@ PK_API int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t of
     PK_REQUIRE(offset <= ix->table_bytes && bytes <= ix->table_bytes - offset,
                "pk_indexer_table_to_host: [%zu, +%zu) outside %zu table bytes", offset, bytes,
                ix->table_bytes);
+    if (ix->mode == PK_MODE_SCAN)
+        return pk_set_error(PK_ERR_STATE, "pk_indexer_table_to_host: a scan-only handle has no table");
     if (ix->mode == PK_MODE_PARTITION && (ix->nseg || !ix->table_valid))
         return pk_set_error(PK_ERR_STATE, "pk_indexer_table_to_host: call pk_indexer_finalize first "
                             "(k-mers are still buffered)");
@@ -1180,6 +1194,90 @@ PK_API int pk_indexer_table_to_host(pk_indexer *ix, uint8_t *dst_host, size_t of
 PK_API int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches) {
     PK_REQUIRE(ix != nullptr && launches != nullptr, "pk_indexer_launch_count: NULL argument");
     *launches = ix->launches;
+    return PK_OK;
+}
+
+// ---- sequence-sharded multi-GPU: scan anywhere, count where the window lives ----------------
+PK_API int pk_indexer_prime(pk_indexer *ix, const uint8_t *halo_dev, size_t n, uint64_t stream_off,
+                            pk_stream stream) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_prime: NULL handle");
+    PK_REQUIRE(n <= (size_t)kCarry && (n == 0 || halo_dev != nullptr), "pk_indexer_prime: at most %d halo bytes", kCarry);
+    pk_device_guard guard(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != ix->last_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
+    }
+    PK_CUDA(cudaMemsetAsync(ix->carry, 0, 64, st));
+    if (n) {
+        k_update_carry<<<1, 32, 0, st>>>(ix->carry, halo_dev, n);
+        PK_CUDA(cudaGetLastError());
+        ix->launches += 1;
+    }
+    ix->stream_off = stream_off;
+    ix->last_stream = st;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_scan_result(pk_indexer *ix, uint64_t *num_kmers) {
+    PK_REQUIRE(ix != nullptr && num_kmers != nullptr, "pk_indexer_scan_result: NULL argument");
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    PK_CUDA(cudaMemcpyAsync(ix->h_counters, ix->counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            ix->work_stream));
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));
+    *num_kmers = ix->h_counters[0];
+    return PK_OK;
+}
+
+PK_API int pk_indexer_export_segments(pk_indexer *ix, const uint32_t **entries_dev, uint32_t *nseg,
+                                      uint32_t *nwindows, uint32_t *seg_off_host, uint32_t *seg_cnt_host,
+                                      size_t capacity) {
+    PK_REQUIRE(ix != nullptr && entries_dev && nseg && nwindows, "pk_indexer_export_segments: NULL argument");
+    PK_REQUIRE(ix->mode != PK_MODE_DIRECT, "pk_indexer_export_segments: DIRECT mode buffers no k-mers");
+    const size_t need = (size_t)ix->nseg * ix->nbuckets;
+    *entries_dev = ix->pool;
+    *nseg = (uint32_t)ix->nseg;
+    *nwindows = ix->nbuckets;
+    if (!seg_off_host || !seg_cnt_host) return PK_OK;      // size query
+    PK_REQUIRE(capacity >= need, "pk_indexer_export_segments: need room for %zu values, got %zu", need, capacity);
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    if (need) {
+        PK_CUDA(cudaMemcpyAsync(seg_cnt_host, seg_cnt(ix, 0), need * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->work_stream));
+        PK_CUDA(cudaMemcpyAsync(seg_off_host, seg_off(ix, 0), need * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->work_stream));
+    }
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));
+    return PK_OK;
+}
+
+PK_API int pk_indexer_import_segments(pk_indexer *ix, const uint32_t *entries_dev, uint32_t nseg,
+                                      const uint32_t *seg_off_host, const uint32_t *seg_cnt_host) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_import_segments: NULL handle");
+    PK_REQUIRE(ix->mode == PK_MODE_PARTITION, "pk_indexer_import_segments: the handle must count in PARTITION mode");
+    PK_REQUIRE(ix->nseg == 0, "pk_indexer_import_segments: the handle already buffers k-mers of its own");
+    PK_REQUIRE(nseg <= (uint32_t)kMaxSegments, "pk_indexer_import_segments: at most %d segments", kMaxSegments);
+    PK_REQUIRE(nseg == 0 || (entries_dev && seg_off_host && seg_cnt_host), "pk_indexer_import_segments: NULL argument");
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    const size_t n = (size_t)nseg * ix->nbuckets;
+    if (n) {
+        PK_CUDA(cudaMemcpyAsync(seg_cnt(ix, 0), seg_cnt_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->work_stream));
+        PK_CUDA(cudaMemcpyAsync(seg_off(ix, 0), seg_off_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->work_stream));
+        PK_CUDA(cudaStreamSynchronize(ix->work_stream));   // the host tables may go away
+    }
+    ix->pool_ext = entries_dev;
+    ix->nseg = (int)nseg;
+    ix->stats_valid = false;
     return PK_OK;
 }
 
@@ -1218,7 +1316,7 @@ PK_API int pk_indexer_profile(pk_indexer *ix, double ms_host[8], uint32_t launch
 PK_API int pk_indexer_mode(pk_indexer *ix, int *mode, int *windows) {
     PK_REQUIRE(ix != nullptr, "pk_indexer_mode: NULL handle");
     if (mode) *mode = ix->mode;
-    if (windows) *windows = ix->mode == PK_MODE_PARTITION ? (int)ix->nbuckets : 0;
+    if (windows) *windows = ix->mode != PK_MODE_DIRECT ? (int)ix->nbuckets : 0;
     return PK_OK;
 }
 

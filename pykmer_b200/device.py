@@ -35,6 +35,21 @@ def to_device_u8(arr, device: Optional[int] = None) -> torch.Tensor:
     return t.to(dev, non_blocking=False).contiguous()
 
 
+class _DeviceAlias:
+    """Minimal __cuda_array_interface__ carrier: lets torch view library-owned device memory."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def _alias_device_memory(ptr: int, n_int32: int, device: int) -> torch.Tensor:
+    if n_int32 == 0 or ptr == 0:
+        return torch.empty(0, dtype=torch.int32, device=torch.device("cuda", device))
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DeviceAlias(ptr, n_int32), device=torch.device("cuda", device))
+
+
 class Indexer:
     """One pk_indexer handle (one GPU, one k-mer range)."""
 
@@ -140,6 +155,43 @@ class Indexer:
         m, w = ctypes.c_int(0), ctypes.c_int(0)
         nat.check(lib.pk_indexer_mode(self._h, ctypes.byref(m), ctypes.byref(w)))
         return m.value, w.value
+
+    # ---- sequence-sharded multi-GPU (see include/pykmer_b200.h) ------------------------------
+    def prime(self, halo: Optional[torch.Tensor], stream_off: int, stream=None) -> None:
+        """Begin a slice in mid-stream: `halo` = the <= 32 bytes preceding it (CUDA uint8)."""
+        n = 0 if halo is None else halo.numel()
+        p = 0 if halo is None else halo.data_ptr()
+        nat.check(lib.pk_indexer_prime(self._h, p, n, stream_off, _stream_ptr(stream)))
+
+    def scan_result(self) -> int:
+        n = ctypes.c_uint64(0)
+        nat.check(lib.pk_indexer_scan_result(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def export_segments(self):
+        """-> (entries: int32 CUDA tensor aliasing the handle's k-mer buffer,
+                seg_off, seg_cnt: uint32 numpy arrays of shape (nseg, nwindows))."""
+        p, ns, nw = ctypes.c_void_p(), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        nat.check(lib.pk_indexer_export_segments(self._h, ctypes.byref(p), ctypes.byref(ns),
+                                                 ctypes.byref(nw), None, None, 0))
+        off = np.zeros((ns.value, nw.value), dtype=np.uint32)
+        cnt = np.zeros((ns.value, nw.value), dtype=np.uint32)
+        if off.size:
+            nat.check(lib.pk_indexer_export_segments(self._h, ctypes.byref(p), ctypes.byref(ns),
+                                                     ctypes.byref(nw), off.ctypes.data, cnt.ctypes.data,
+                                                     off.size))
+        used = int((off.astype(np.int64) + cnt).max()) if off.size else 0
+        entries = _alias_device_memory(int(p.value or 0), used, self.device)
+        return entries, off, cnt
+
+    def import_segments(self, entries: torch.Tensor, seg_off: np.ndarray, seg_cnt: np.ndarray) -> None:
+        """Count k-mer entries gathered from other ranks; `entries` must outlive finalize()."""
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint32)
+        seg_cnt = np.ascontiguousarray(seg_cnt, dtype=np.uint32)
+        assert seg_off.shape == seg_cnt.shape and seg_off.ndim == 2
+        self._keep.append(entries)
+        nat.check(lib.pk_indexer_import_segments(self._h, entries.data_ptr() if entries.numel() else 0,
+                                                 seg_off.shape[0], seg_off.ctypes.data, seg_cnt.ctypes.data))
 
     PROFILE_CLASSES = ("scan_count_direct", "scan_bucket_count", "bucket_offsets", "scan_scatter",
                        "window_count", "window_commit", "table_stats", "update_carry")

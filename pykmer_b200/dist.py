@@ -18,6 +18,7 @@ import torch
 import torch.distributed as dist
 
 ALIGN = 4096          # shard boundaries are multiples of this many table entries
+WINDOW = 1 << 24      # table window of the PARTITION counting scheme (include/pykmer_b200.h)
 
 
 def world() -> Tuple[int, int]:
@@ -84,3 +85,121 @@ def broadcast_stream(chunk: Optional[torch.Tensor], nbytes: int, src: int = 0, g
         chunk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     dist.broadcast(chunk, src=src, group=group)
     return chunk
+
+
+# ---------------------------------------------------------------------------------------------
+# Sequence-sharded indexing: every rank scans 1/N of the stream (PK_MODE_SCAN handle over the
+# full k-mer range), the bucketed entries travel to the rank that owns their table window with
+# ONE all-to-all over NVLink, and each rank counts its own windows (PK_MODE_PARTITION handle).
+
+def window_owner_ranges(nwindows: int, nranks: int) -> List[Tuple[int, int]]:
+    """Contiguous window ranges [w0, w1) per rank; they tile [0, nwindows)."""
+    return [(nwindows * r // nranks, nwindows * (r + 1) // nranks) for r in range(nranks)]
+
+
+def balanced_window_owners(per_window: np.ndarray, nranks: int, overhead: int = 3_000_000) -> List[Tuple[int, int]]:
+    """Contiguous window ranges with about equal cost, cost(window) = its k-mer entries + a
+    fixed per-window overhead (the commit pass).  Canonical k-mers crowd the low windows
+    (first-base shares 7/16, 5/16, 3/16, 1/16), so equal window counts would leave rank 0 with
+    ~1.9x the mean."""
+    cost = per_window.astype(np.int64) + overhead
+    nwin = len(cost)
+    cum = np.concatenate(([0], np.cumsum(cost)))
+    cuts = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        w = int(np.searchsorted(cum, target))
+        w = min(max(w, cuts[-1] + 1), nwin - (nranks - r))      # every rank owns >= 1 window
+        cuts.append(w)
+    cuts.append(nwin)
+    return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
+
+
+def slice_bounds(nbytes: int, rank: int, nranks: int, align: int = 16) -> Tuple[int, int]:
+    """Byte slice [a, b) of the stream scanned by `rank` (16-byte aligned starts)."""
+    def cut(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= nranks:
+            return nbytes
+        return (nbytes * r // nranks) // align * align
+    return cut(rank), cut(rank + 1)
+
+
+def plan_exchange(all_cnt: np.ndarray, owners: List[Tuple[int, int]], rank: int):
+    """all_cnt[s, f, w] = entries of source rank s, segment f, window w (uint32/int64).
+    -> (send_counts[f][d], recv_counts[f][s], imp_off, imp_cnt) where imp_* are the segment
+    tables (nranks * nseg, local windows) of the receive buffer laid out segment by segment,
+    source by source, window by window."""
+    nranks, nseg, _ = all_cnt.shape
+    w0, w1 = owners[rank]
+    send = np.zeros((nseg, nranks), dtype=np.int64)
+    recv = np.zeros((nseg, nranks), dtype=np.int64)
+    for f in range(nseg):
+        for d, (a, b) in enumerate(owners):
+            send[f, d] = int(all_cnt[rank, f, a:b].sum())
+        for s in range(nranks):
+            recv[f, s] = int(all_cnt[s, f, w0:w1].sum())
+    imp_cnt = np.zeros((nseg * nranks, w1 - w0), dtype=np.uint32)
+    imp_off = np.zeros((nseg * nranks, w1 - w0), dtype=np.uint32)
+    base = 0
+    for f in range(nseg):
+        for s in range(nranks):
+            c = all_cnt[s, f, w0:w1].astype(np.int64)
+            imp_cnt[f * nranks + s] = c
+            imp_off[f * nranks + s] = base + np.concatenate(([0], np.cumsum(c)[:-1]))
+            base += int(c.sum())
+    return send, recv, imp_off, imp_cnt, base
+
+
+def gather_window_counts(scanner, group=None) -> np.ndarray:
+    """all_cnt[s, f, w]: entries of rank s, segment f, window w (a few KB, all-gathered)."""
+    rank, nranks = world()
+    entries, off, cnt = scanner.export_segments()
+    nwin = cnt.shape[1] if cnt.ndim == 2 and cnt.shape[0] else scanner.mode()[1]
+    dev = entries.device
+    nseg_t = torch.tensor([cnt.shape[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(nseg_t, op=dist.ReduceOp.MAX, group=group)
+    nseg = int(nseg_t.item())
+    mine = np.zeros((nseg, nwin), dtype=np.int64)
+    mine[:cnt.shape[0]] = cnt
+    gathered = torch.empty((nranks, nseg, nwin), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(mine).to(dev).view(-1), group=group)
+    return gathered.cpu().numpy()
+
+
+def exchange_entries(scanner, counter, owners: Optional[List[Tuple[int, int]]] = None, group=None):
+    """All-to-all of the scanner's bucketed k-mer entries to the window owners; the counter of
+    this rank is left holding (importing) everything that falls into its windows.
+    owners: window range per rank (default: equal window counts).
+    Returns the receive buffer (keep it alive until counter.finalize())."""
+    rank, nranks = world()
+    entries, off, cnt = scanner.export_segments()
+    nwin = cnt.shape[1] if cnt.ndim == 2 and cnt.shape[0] else scanner.mode()[1]
+    dev = entries.device
+    # every rank needs everybody's per-window counts (a few KB): pad to the largest segment count
+    nseg_t = torch.tensor([cnt.shape[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(nseg_t, op=dist.ReduceOp.MAX, group=group)
+    nseg = int(nseg_t.item())
+    mine = np.zeros((nseg, nwin), dtype=np.int64)
+    mine[:cnt.shape[0]] = cnt
+    gathered = torch.empty((nranks, nseg, nwin), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(mine).to(dev).view(-1), group=group)
+    all_cnt = gathered.cpu().numpy()
+    if owners is None:
+        owners = window_owner_ranges(nwin, nranks)
+    send, recv, imp_off, imp_cnt, total = plan_exchange(all_cnt, owners, rank)
+    recv_buf = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    pos = 0
+    for f in range(nseg):
+        if f < cnt.shape[0]:
+            a = int(off[f, 0])
+            src = entries[a:a + int(send[f].sum())]          # windows of one segment are contiguous
+        else:
+            src = entries[:0]
+        n_in = int(recv[f].sum())
+        dist.all_to_all_single(recv_buf[pos:pos + n_in], src, output_split_sizes=recv[f].tolist(),
+                               input_split_sizes=send[f].tolist(), group=group)
+        pos += n_in
+    counter.import_segments(recv_buf, imp_off, imp_cnt)
+    return recv_buf

@@ -98,3 +98,44 @@ def test_two_rank_reductions_equal_the_whole_job(tmp_path):
                            "vals_min": st["vals_min"], "vals_max": st["vals_max"]}
         assert r["flags"] == flags.tolist()
         assert np.array_equal(np.array(r["G"]), G)
+
+
+def test_exchange_plan_routes_every_entry_to_its_window_owner():
+    """plan_exchange (pure host logic of the sequence-sharded indexer): emulate the all-to-all
+    in NumPy and check that every rank ends up with exactly the entries of its windows, and
+    that the imported segment tables index them."""
+    from pykmer_b200 import dist as pdist
+    rng = np.random.default_rng(3)
+    nranks, nseg, nwin = 4, 2, 11
+    all_cnt = rng.integers(0, 50, size=(nranks, nseg, nwin)).astype(np.int64)
+    all_cnt[2, 1] = 0                                           # a rank with an empty segment
+    per_window = all_cnt.sum(axis=(0, 1))
+    for owners in (pdist.window_owner_ranges(nwin, nranks),
+                   pdist.balanced_window_owners(per_window, nranks, overhead=5)):
+        assert owners[0][0] == 0 and owners[-1][1] == nwin
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(owners[:-1], owners[1:]))
+        # each rank's pool: per segment, windows in order; an entry is tagged (src, seg, window, i)
+        pools = {}
+        for s in range(nranks):
+            for f in range(nseg):
+                pools[s, f] = [(s, f, w, i) for w in range(nwin) for i in range(all_cnt[s, f, w])]
+        plans = [pdist.plan_exchange(all_cnt, owners, r) for r in range(nranks)]
+        for d in range(nranks):
+            send_d, recv_d, imp_off, imp_cnt, total = plans[d]
+            buf = []
+            for f in range(nseg):
+                for s in range(nranks):
+                    send_s = plans[s][0]
+                    start = int(send_s[f, :d].sum())
+                    chunk = pools[s, f][start:start + int(send_s[f, d])]
+                    assert len(chunk) == recv_d[f, s]
+                    buf += chunk
+            assert len(buf) == total
+            w0, w1 = owners[d]
+            for seg in range(nseg * nranks):
+                f, s = divmod(seg, nranks)
+                for wl in range(w1 - w0):
+                    got = buf[int(imp_off[seg, wl]):int(imp_off[seg, wl]) + int(imp_cnt[seg, wl])]
+                    assert got == [(s, f, w0 + wl, i) for i in range(all_cnt[s, f, w0 + wl])]
+    bal = pdist.balanced_window_owners(np.array([100, 1, 1, 1, 1, 1, 1, 1]), 2, overhead=0)
+    assert bal == [(0, 1), (1, 8)]

@@ -581,3 +581,74 @@ def test_finalize_to_host_streams_the_table(env, mode, wlog):
             assert hist == env["oracle"].table_stats(want)[0]
         hist2, st2 = ix.finalize(table_out=out)              # nothing pending: plain copy
         assert (hist2, st2) == (hist, st) and np.array_equal(out.numpy(), want)
+
+
+@pytest.mark.parametrize("K,wlog,nranks", [(9, 10, 3), (11, 12, 2), (17, 12, 4)])
+def test_sequence_sharded_scan_exchange_count(env, K, wlog, nranks):
+    """The multi-GPU indexer path emulated rank after rank on one GPU: every 'rank' scans its
+    slice of the stream (primed with the preceding bytes), the bucketed entries are routed to
+    the owners of their windows exactly as dist.exchange_entries does (the all-to-all is
+    emulated with tensor copies), each owner counts its windows; concatenated shards, num_kmers
+    and record flags equal the oracle's single pass."""
+    import torch
+    from pykmer_b200 import dist as pdist, _native as nat
+    dev, oracle = env["dev"], env["oracle"]
+    rng = np.random.default_rng(K * 7 + nranks)
+    s = _random_stream(rng, 120_000)
+    if K > 13:                                                  # make a narrow k-mer range busy
+        s[::7] = ord("A"); s[1::7] = ord("A"); s[2::7] = ord("A")
+    starts = np.array([0, 30_000, 30_001, 90_000], dtype=np.uint64)
+    hi_all = min(4 ** K, 1 << 22)
+    want, num, oflags = oracle.index_stream(s, K, range_hi=hi_all, rec_starts=starts)
+    os.environ["PYKMER_B200_WINDOW_LOG2"] = str(wlog)
+    try:
+        scanners, exports = [], []
+        for r in range(nranks):
+            a, b = pdist.slice_bounds(len(s), r, nranks)
+            sc = dev.Indexer(K, range_hi=hi_all, mode=nat.PK_MODE_SCAN)
+            sc.set_records(starts)
+            halo = torch.from_numpy(s[max(0, a - 32):a].copy()).cuda() if a > 0 else None
+            sc.prime(halo, a)
+            piece = torch.from_numpy(s[a:b].copy()).cuda()
+            sc.feed_device(piece[:len(piece) // 2 // 16 * 16])     # two feeds -> two segments
+            sc.feed_device(piece[len(piece) // 2 // 16 * 16:])
+            scanners.append(sc)
+            exports.append(sc.export_segments())
+            with pytest.raises(RuntimeError):
+                sc.finalize()                                    # a scanner has no table
+        nwin = scanners[0].mode()[1]
+        nseg = max(e[2].shape[0] for e in exports)
+        all_cnt = np.zeros((nranks, nseg, nwin), dtype=np.int64)
+        for r, (_, off, cnt) in enumerate(exports):
+            all_cnt[r, :cnt.shape[0]] = cnt
+        owners = pdist.balanced_window_owners(all_cnt.sum(axis=(0, 1)), nranks, overhead=10)
+        tables, total, flags = [], 0, np.zeros(len(starts), dtype=np.uint8)
+        for d in range(nranks):
+            send_d, recv_d, imp_off, imp_cnt, tot = pdist.plan_exchange(all_cnt, owners, d)
+            buf = torch.empty(max(tot, 1), dtype=torch.int32, device="cuda")
+            pos = 0
+            for f in range(nseg):
+                for src in range(nranks):
+                    entries, off, cnt = exports[src]
+                    send_s = pdist.plan_exchange(all_cnt, owners, src)[0]
+                    if f >= cnt.shape[0]:
+                        continue
+                    start = int(off[f, 0]) + int(send_s[f, :d].sum())
+                    n = int(send_s[f, d])
+                    buf[pos:pos + n] = entries[start:start + n]
+                    pos += n
+            w0, w1 = owners[d]
+            lo, hi = w0 << wlog, min(hi_all, w1 << wlog)
+            ct = dev.Indexer(K, range_lo=lo, range_hi=hi, mode=nat.PK_MODE_PARTITION)
+            ct.import_segments(buf, imp_off, imp_cnt)
+            hist, st = ct.finalize()
+            tables.append(ct.table_to_host().numpy().copy())
+            ct.close()
+        for sc in scanners:
+            total += sc.scan_result()
+            flags |= sc.record_flags()
+            sc.close()
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+    assert total == num and np.array_equal(flags, oflags)
+    assert np.array_equal(np.concatenate(tables), want)
