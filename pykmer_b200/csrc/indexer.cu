@@ -45,7 +45,7 @@ constexpr size_t kStageBytes = 32u << 20;   // pinned-copy chunk of feed_host
 constexpr int kCarry = 32;                  // bytes of stream tail kept between feeds
 constexpr int kMaxBuckets = 16384;          // windows per handle in PARTITION / SCAN mode
 constexpr int kMaxSegments = 128;           // feeds buffered between two flushes
-constexpr size_t kMaxFeed = 256u << 20;     // bases per partition pass
+constexpr size_t kMaxFeed = 1u << 30;       // bases per partition pass (one segment each)
 constexpr int kTileEntries = kScanWarps * 31 * 16;   // most entries one block tile can emit
 
 struct ScanParams {

@@ -173,23 +173,33 @@ def exchange_entries(scanner, counter, owners: Optional[List[Tuple[int, int]]] =
     this rank is left holding (importing) everything that falls into its windows.
     owners: window range per rank (default: equal window counts).
     Returns the receive buffer (keep it alive until counter.finalize())."""
+    import os
+    import time
+    verbose = os.environ.get("PYKMER_B200_VERBOSE")
+    t = [time.perf_counter()]
     rank, nranks = world()
     entries, off, cnt = scanner.export_segments()
+    t.append(time.perf_counter())
     nwin = cnt.shape[1] if cnt.ndim == 2 and cnt.shape[0] else scanner.mode()[1]
     dev = entries.device
-    # every rank needs everybody's per-window counts (a few KB): pad to the largest segment count
-    nseg_t = torch.tensor([cnt.shape[0]], dtype=torch.int64, device=dev)
-    dist.all_reduce(nseg_t, op=dist.ReduceOp.MAX, group=group)
-    nseg = int(nseg_t.item())
-    mine = np.zeros((nseg, nwin), dtype=np.int64)
-    mine[:cnt.shape[0]] = cnt
-    gathered = torch.empty((nranks, nseg, nwin), dtype=torch.int64, device=dev)
+    # every rank needs everybody's per-window counts (a few KB); row 0 of the payload carries
+    # the segment count so that one all-gather is enough
+    cap = 8
+    assert cnt.shape[0] <= cap, "more than 8 feed segments per exchange"
+    mine = np.zeros((cap + 1, nwin), dtype=np.int64)
+    mine[0, 0] = cnt.shape[0]
+    mine[1:1 + cnt.shape[0]] = cnt
+    gathered = torch.empty((nranks, cap + 1, nwin), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(mine).to(dev).view(-1), group=group)
-    all_cnt = gathered.cpu().numpy()
+    g = gathered.cpu().numpy()
+    nseg = int(g[:, 0, 0].max())
+    all_cnt = g[:, 1:1 + nseg, :]
+    t.append(time.perf_counter())
     if owners is None:
         owners = window_owner_ranges(nwin, nranks)
     send, recv, imp_off, imp_cnt, total = plan_exchange(all_cnt, owners, rank)
     recv_buf = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    t.append(time.perf_counter())
     pos = 0
     for f in range(nseg):
         if f < cnt.shape[0]:
@@ -201,5 +211,13 @@ def exchange_entries(scanner, counter, owners: Optional[List[Tuple[int, int]]] =
         dist.all_to_all_single(recv_buf[pos:pos + n_in], src, output_split_sizes=recv[f].tolist(),
                                input_split_sizes=send[f].tolist(), group=group)
         pos += n_in
+    if verbose:
+        torch.cuda.synchronize()
+    t.append(time.perf_counter())
     counter.import_segments(recv_buf, imp_off, imp_cnt)
+    t.append(time.perf_counter())
+    if verbose and rank == 0:
+        names = ("export", "gather", "plan", "all_to_all", "import")
+        print("[pykmer_b200] exchange ms: " + ", ".join(f"{n} {1e3 * (b - a):.3f}" for n, a, b in zip(names, t[:-1], t[1:]))
+              + f"; sent {4 * int(send.sum() - send[:, rank].sum())} B", flush=True)
     return recv_buf
