@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=50, help="merger: number of samples")
     ap.add_argument("--max-count", type=int, default=50, help="merger: --max-count")
     ap.add_argument("--mode", type=int, default=0, help="indexer counting mode (0 auto)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="sequence sharding: 'fused' = pass 2 stores into the owners' buffers over NVLink "
+                         "(CUDA IPC peer mappings), 'nccl' = bucket locally, then torch all_to_all_single")
     ap.add_argument("--shard", default="sequence", choices=["sequence", "kmer"],
                     help="N > 1 indexer: 'sequence' = each rank scans 1/N of the stream and the k-mer entries "
                          "are exchanged all-to-all; 'kmer' = every rank scans everything, keeps its k-mer range")
@@ -280,12 +283,27 @@ def run_indexer_seqshard(args, rank, local_rank, world):
     w0, w1 = owners[rank]
     lo, hi = w0 << 24, min(T, w1 << 24)
     counter = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=nat.PK_MODE_PARTITION)
+    fused = args.exchange == "fused"
+    if fused:
+        pdist.connect_peer_pools(scanner, counter)
+    stage = torch.empty(b - a, dtype=torch.uint8, device="cuda") if fused else None
     last = {}
 
     def step_device(src_host=None, table_out=None):
-        scan(src_host)
-        counter.reset()
-        buf = pdist.exchange_entries(scanner, counter, owners)
+        if fused:
+            # scan, count per window, all-gather the counts, store entries into the owners over NVLink
+            scanner.reset()
+            scanner.prime(halo, a)
+            counter.reset()
+            src = d_slice
+            if src_host is not None:
+                stage.copy_(src_host, non_blocking=True)
+                src = stage
+            buf = pdist.exchange_fused(scanner, counter, src, owners)
+        else:
+            scan(src_host)
+            counter.reset()
+            buf = pdist.exchange_entries(scanner, counter, owners)
         hist, st = counter.finalize(table_out=table_out)
         st["num_kmers"] = scanner.scan_result()
         hist, st = pdist.reduce_index_stats(hist, st)
@@ -303,9 +321,14 @@ def run_indexer_seqshard(args, rank, local_rank, world):
 
     scanner.set_profiling(True); counter.set_profiling(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    ev[0].record(); scan(); ev[1].record()
-    counter.reset()
-    ev[2].record(); buf = pdist.exchange_entries(scanner, counter, owners); ev[3].record()
+    if fused:
+        scanner.reset(); scanner.prime(halo, a); counter.reset()
+        ev[0].record(); ev[1].record()
+        ev[2].record(); buf = pdist.exchange_fused(scanner, counter, d_slice, owners); ev[3].record()
+    else:
+        ev[0].record(); scan(); ev[1].record()
+        counter.reset()
+        ev[2].record(); buf = pdist.exchange_entries(scanner, counter, owners); ev[3].record()
     counter.finalize()
     torch.cuda.synchronize()
     prof = dict(scanner.profile()); prof.update(counter.profile())
@@ -346,7 +369,9 @@ def run_indexer_seqshard(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": f"indexer K={K}, synthetic tomato-sized multi-FASTA stream "
                                    f"({L} bp, 13 records), 4^{K}-byte table",
-                       "parallelism": f"sequence x{world} scan, all-to-all of k-mer entries, kmer-window x{world} count",
+                       "parallelism": f"sequence x{world} scan, k-mer entries to window owners "
+                                      f"({'stores over NVLink fused into pass 2' if fused else 'NCCL all-to-all'}), "
+                                      f"kmer-window x{world} count",
                        "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
                        "vals_count": st["vals_count"], "vals_max": st["vals_max"],
                        "records_with_kmers": int(flags.sum())},

@@ -143,6 +143,23 @@ int pk_indexer_export_segments(pk_indexer *ix, const uint32_t **entries_dev, uin
 int pk_indexer_import_segments(pk_indexer *ix, const uint32_t *entries_dev, uint32_t nseg,
                                const uint32_t *seg_off_host, const uint32_t *seg_cnt_host);
 
+/* Fused exchange (no separate all-to-all): pass 2 of the scanner stores every entry straight
+ * into the k-mer buffer of the handle that owns its window, through CUDA-IPC peer mappings
+ * over NVLink.  Per step: pk_indexer_scan_pass1 (count per window) -> pk_indexer_pass1_counts
+ * -> the ranks all-gather the counts and derive the routing -> pk_indexer_scan_pass2_remote
+ * (owner rank and destination offset per window; synchronises) -> barrier ->
+ * pk_indexer_import_segments(owner, NULL, ...) on every owner (NULL = its own buffer).
+ * pk_indexer_pool_ipc_handle exports a PARTITION handle's buffer (64-byte cudaIpcMemHandle_t),
+ * pk_indexer_open_peer_pool maps it into a scanner as destination `peer` (pass the local
+ * owner handle instead of an IPC handle for the rank's own windows). */
+int pk_indexer_pool_ipc_handle(pk_indexer *ix, void *handle64, size_t *capacity_entries);
+int pk_indexer_open_peer_pool(pk_indexer *scanner, int peer, const void *handle64,
+                              pk_indexer *local_owner);
+int pk_indexer_scan_pass1(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_stream stream);
+int pk_indexer_pass1_counts(pk_indexer *ix, uint32_t *counts_host, size_t nwindows);
+int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32_t *owner_host,
+                                 const uint32_t *dest_off_host, pk_stream stream);
+
 /* Per-kernel-class device time, measured with CUDA events on the launching stream
  * around every launch made through the handle while enabled.  Classes (index into
  * ms_host / launches_host): 0 scan_count_direct, 1 scan_bucket_count, 2 bucket_offsets,

@@ -24,7 +24,8 @@ SYMBOLS = (
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
     "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_set_profiling", "pk_indexer_profile",
     "pk_indexer_prime", "pk_indexer_scan_result", "pk_indexer_export_segments",
-    "pk_indexer_import_segments",
+    "pk_indexer_import_segments", "pk_indexer_pool_ipc_handle", "pk_indexer_open_peer_pool",
+    "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
     "pk_table_stats_device",
     "pk_threshold_pack_device", "pk_gram_device", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device",
@@ -78,6 +79,11 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_export_segments": [vp, c.POINTER(vp), c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                        vp, vp, sz],
         "pk_indexer_import_segments": [vp, vp, c.c_uint32, vp, vp],
+        "pk_indexer_pool_ipc_handle": [vp, vp, c.POINTER(sz)],
+        "pk_indexer_open_peer_pool": [vp, i32, vp, vp],
+        "pk_indexer_scan_pass1": [vp, vp, sz, vp],
+        "pk_indexer_pass1_counts": [vp, vp, sz],
+        "pk_indexer_scan_pass2_remote": [vp, i32, vp, vp, vp],
         "pk_table_stats_device": [vp, sz, vp, vp, vp],
         "pk_threshold_pack_device": [vp, sz, i32, i32, vp, vp],
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],

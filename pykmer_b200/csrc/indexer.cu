@@ -66,6 +66,11 @@ struct ScanParams {
     const uint32_t *seg_off;  // [nbuckets] pool index of each segment      (pass 2 in)
     uint32_t *seg_fill;       // [nbuckets] fill cursors                    (pass 2)
     uint32_t *pool;
+    // pass 2 with remote destinations (sequence-sharded multi-GPU): window b's entries go to
+    // peer[win_owner[b]] + dest_off[b] -- peer-mapped pools of the window owners (NVLink stores)
+    const uint32_t *win_owner;
+    const uint32_t *dest_off;
+    uint32_t *peer[16];
 };
 
 __device__ __forceinline__ void load_group(const ScanParams &p, long long g, long long ngroups,
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams 
                 const uint32_t c = s_cnt[b];
                 s_toff[b] = run;
                 run += c;
-                if (c) s_gbase[b] = p.seg_off[b] + atomicAdd(&p.seg_fill[b], c);
+                if (c) s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + atomicAdd(&p.seg_fill[b], c);
             }
         }
         __syncthreads();
@@ -329,7 +334,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams 
         const uint32_t total = s_total;
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             const uint32_t b = s_bid[i];
-            p.pool[s_gbase[b] + (i - s_toff[b])] = s_ent[i];
+            uint32_t *dst = p.win_owner ? p.peer[p.win_owner[b]] : p.pool;
+            dst[s_gbase[b] + (i - s_toff[b])] = s_ent[i];
         }
         // the next iteration only touches s_cnt before its first barrier
     }
@@ -587,6 +593,12 @@ struct pk_indexer {
     uint32_t win_log2 = 24, nbuckets = 0;
     uint32_t *pool = nullptr;                  // buffered entries
     const uint32_t *pool_ext = nullptr;        // entries imported from other ranks (pk_indexer_import_segments)
+    // fused exchange: peer-mapped pools of the window owners and the per-window routing
+    uint32_t *peer_pool[16] = {nullptr};
+    void *peer_ipc[16] = {nullptr};            // cudaIpcOpenMemHandle bases to close
+    uint32_t *route = nullptr;                 // device: [2][nbuckets] owner, destination offset
+    const uint8_t *p1_seq = nullptr;           // sequence of the pending pass 1
+    size_t p1_n = 0;
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
     uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
     uint32_t *cursor = nullptr;                // device pool cursor
@@ -735,7 +747,10 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
     return PK_OK;
 }
 
-static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st) {
+enum { SCAN_BOTH = 0, SCAN_PASS1 = 1, SCAN_PASS2_REMOTE = 2 };
+
+static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st,
+                               int phase = SCAN_BOTH) {
     if (n == 0) return PK_OK;
     ScanParams p;
     memset(&p, 0, sizeof p);
@@ -752,6 +767,13 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         else      { if (full) KERNEL<false, true><<<GRID, kScanThreads, SMEM, st>>>(p);        \
                     else      KERNEL<false, false><<<GRID, kScanThreads, SMEM, st>>>(p); }     \
     } while (0)
+#define PK_SMEM_OPT_IN(KERNEL, BYTES)                                                          \
+    do {                                                                                       \
+        PK_CUDA(cudaFuncSetAttribute(KERNEL<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));   \
+        PK_CUDA(cudaFuncSetAttribute(KERNEL<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));  \
+        PK_CUDA(cudaFuncSetAttribute(KERNEL<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));  \
+        PK_CUDA(cudaFuncSetAttribute(KERNEL<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))); \
+    } while (0)
     const long long gpw = wide ? 30 : 31;
     const long long ngroups = (long long)((n + 15) / 16);
     const long long ntiles = (ngroups + gpw - 1) / gpw;
@@ -765,7 +787,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
     } else {
-        if (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap) {
+        if (phase != SCAN_PASS2_REMOTE && (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap)) {
             if (ix->mode == PK_MODE_SCAN)
                 return pk_set_error(PK_ERR_STATE, "scan-only handle: k-mer buffer full (%zu entries, %d segments); "
                                     "export and reset before feeding more", ix->pool_cap, ix->nseg);
@@ -778,19 +800,33 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         const size_t smem1 = (size_t)ix->nbuckets * sizeof(uint32_t);
         const size_t smem2 = scatter_smem_bytes(ix->nbuckets);
         if (!ix->scatter_smem_set) {
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            PK_CUDA(cudaFuncSetAttribute(k_scan_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PK_SMEM_OPT_IN(k_scan_scatter, smem2);
+            if (smem1 > 48 * 1024) PK_SMEM_OPT_IN(k_scan_bucket_count, smem1);
             ix->scatter_smem_set = true;
         }
-        {
-            prof_scope ps(ix, st, PROF_BUCKET_COUNT);
-            PK_LAUNCH_SCAN(k_scan_bucket_count, grid, smem1);
+        if (phase != SCAN_PASS2_REMOTE) {
+            {
+                prof_scope ps(ix, st, PROF_BUCKET_COUNT);
+                PK_LAUNCH_SCAN(k_scan_bucket_count, grid, smem1);
+            }
+            ix->launches += 1;
         }
-        {
+        if (phase == SCAN_BOTH) {
             prof_scope ps(ix, st, PROF_OFFSETS);
             k_bucket_offsets<<<1, 256, 0, st>>>(p.seg_cnt, seg_off(ix, f), ix->nbuckets, ix->cursor);
+            ix->launches += 1;
+        }
+        if (phase == SCAN_PASS1) {
+            PK_CUDA(cudaGetLastError());
+            ix->p1_seq = seq_dev;
+            ix->p1_n = n;
+            ix->last_stream = st;
+            return PK_OK;                              // pass 2 follows once the routing is known
+        }
+        if (phase == SCAN_PASS2_REMOTE) {
+            p.win_owner = ix->route;
+            p.dest_off = ix->route + ix->nbuckets;
+            for (int i = 0; i < 16; i++) p.peer[i] = ix->peer_pool[i];
         }
         const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 4));
         {
@@ -798,9 +834,11 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             PK_LAUNCH_SCAN(k_scan_scatter, grid2, smem2);
         }
         PK_CUDA(cudaGetLastError());
-        ix->launches += 3;
-        ix->nseg++;
-        ix->pool_ub += n;
+        ix->launches += 1;
+        if (phase == SCAN_BOTH) {
+            ix->nseg++;
+            ix->pool_ub += n;
+        }
         ix->stats_valid = false;
     }
     {
@@ -814,6 +852,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     ix->last_stream = st;
     return PK_OK;
 #undef PK_LAUNCH_SCAN
+#undef PK_SMEM_OPT_IN
 }
 
 // feeds are cut so that one partition pass never exceeds kMaxFeed bases
@@ -960,7 +999,9 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
-    cudaFree(ix->bins_part);
+    cudaFree(ix->bins_part); cudaFree(ix->route);
+    for (int i = 0; i < 16; i++)
+        if (ix->peer_ipc[i]) cudaIpcCloseMemHandle(ix->peer_ipc[i]);
     for (int i = 0; i < 2; i++)
         if (ix->committed[i]) cudaEventDestroy(ix->committed[i]);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
@@ -996,6 +1037,8 @@ PK_API int pk_indexer_reset(pk_indexer *ix, pk_stream stream) {
         ix->nseg = 0;
         ix->pool_ub = 0;
         ix->pool_ext = nullptr;
+        ix->p1_seq = nullptr;
+        ix->p1_n = 0;
         ix->table_valid = false;
         ix->stats_valid = false;
     }
@@ -1263,7 +1306,8 @@ PK_API int pk_indexer_import_segments(pk_indexer *ix, const uint32_t *entries_de
     PK_REQUIRE(ix->mode == PK_MODE_PARTITION, "pk_indexer_import_segments: the handle must count in PARTITION mode");
     PK_REQUIRE(ix->nseg == 0, "pk_indexer_import_segments: the handle already buffers k-mers of its own");
     PK_REQUIRE(nseg <= (uint32_t)kMaxSegments, "pk_indexer_import_segments: at most %d segments", kMaxSegments);
-    PK_REQUIRE(nseg == 0 || (entries_dev && seg_off_host && seg_cnt_host), "pk_indexer_import_segments: NULL argument");
+    PK_REQUIRE(nseg == 0 || (seg_off_host && seg_cnt_host), "pk_indexer_import_segments: NULL argument");
+    if (!entries_dev) entries_dev = ix->pool;             // peers stored the entries into this handle's pool
     pk_device_guard guard(ix->device);
     {
         const int rc = indexer_join(ix);
@@ -1278,6 +1322,99 @@ PK_API int pk_indexer_import_segments(pk_indexer *ix, const uint32_t *entries_de
     ix->pool_ext = entries_dev;
     ix->nseg = (int)nseg;
     ix->stats_valid = false;
+    return PK_OK;
+}
+
+// ---- fused exchange: pass 2 stores straight into the window owners' pools over NVLink --------
+PK_API int pk_indexer_pool_ipc_handle(pk_indexer *ix, void *handle64, size_t *capacity_entries) {
+    PK_REQUIRE(ix != nullptr && handle64 != nullptr, "pk_indexer_pool_ipc_handle: NULL argument");
+    PK_REQUIRE(ix->pool != nullptr, "pk_indexer_pool_ipc_handle: the handle has no k-mer buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    pk_device_guard guard(ix->device);
+    cudaIpcMemHandle_t h;
+    PK_CUDA(cudaIpcGetMemHandle(&h, ix->pool));
+    memcpy(handle64, &h, 64);
+    if (capacity_entries) *capacity_entries = ix->pool_cap;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_open_peer_pool(pk_indexer *scanner, int peer, const void *handle64,
+                                     pk_indexer *local_owner) {
+    PK_REQUIRE(scanner != nullptr && peer >= 0 && peer < 16, "pk_indexer_open_peer_pool: bad argument");
+    PK_REQUIRE((handle64 != nullptr) != (local_owner != nullptr),
+               "pk_indexer_open_peer_pool: give either an IPC handle or the local owner handle");
+    pk_device_guard guard(scanner->device);
+    if (scanner->peer_ipc[peer]) { cudaIpcCloseMemHandle(scanner->peer_ipc[peer]); scanner->peer_ipc[peer] = nullptr; }
+    if (local_owner) {
+        scanner->peer_pool[peer] = local_owner->pool;
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void *base = nullptr;
+        PK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        scanner->peer_ipc[peer] = base;
+        scanner->peer_pool[peer] = static_cast<uint32_t *>(base);
+    }
+    return PK_OK;
+}
+
+PK_API int pk_indexer_scan_pass1(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_stream stream) {
+    PK_REQUIRE(ix != nullptr && ix->mode == PK_MODE_SCAN, "pk_indexer_scan_pass1: needs a scan-only handle");
+    PK_REQUIRE(seq_dev != nullptr && n > 0 && n <= kMaxFeed && n <= ix->pool_cap,
+               "pk_indexer_scan_pass1: between 1 and 2^30 bases per pass");
+    PK_REQUIRE(((uintptr_t)seq_dev & 15u) == 0, "pk_indexer_scan_pass1: seq_dev must be 16-byte aligned");
+    PK_REQUIRE(ix->nseg == 0 && ix->p1_seq == nullptr, "pk_indexer_scan_pass1: a pass is already pending");
+    pk_device_guard guard(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != ix->last_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
+    }
+    return indexer_launch_scan(ix, seq_dev, n, st, SCAN_PASS1);
+}
+
+PK_API int pk_indexer_pass1_counts(pk_indexer *ix, uint32_t *counts_host, size_t nwindows) {
+    PK_REQUIRE(ix != nullptr && counts_host != nullptr, "pk_indexer_pass1_counts: NULL argument");
+    PK_REQUIRE(ix->p1_seq != nullptr, "pk_indexer_pass1_counts: no pass 1 pending");
+    PK_REQUIRE(nwindows == ix->nbuckets, "pk_indexer_pass1_counts: the handle has %u windows", ix->nbuckets);
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    PK_CUDA(cudaMemcpyAsync(counts_host, seg_cnt(ix, 0), nwindows * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            ix->work_stream));
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));
+    return PK_OK;
+}
+
+PK_API int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32_t *owner_host,
+                                        const uint32_t *dest_off_host, pk_stream stream) {
+    PK_REQUIRE(ix != nullptr && owner_host != nullptr && dest_off_host != nullptr,
+               "pk_indexer_scan_pass2_remote: NULL argument");
+    PK_REQUIRE(ix->p1_seq != nullptr, "pk_indexer_scan_pass2_remote: no pass 1 pending");
+    PK_REQUIRE(nranks >= 1 && nranks <= 16, "pk_indexer_scan_pass2_remote: 1..16 ranks");
+    for (uint32_t b = 0; b < ix->nbuckets; b++) {
+        PK_REQUIRE(owner_host[b] < (uint32_t)nranks && ix->peer_pool[owner_host[b]] != nullptr,
+                   "pk_indexer_scan_pass2_remote: window %u routed to rank %u whose pool is not open", b, owner_host[b]);
+    }
+    pk_device_guard guard(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != ix->last_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
+    }
+    if (!ix->route) PK_CUDA(cudaMalloc(&ix->route, (size_t)2 * kMaxBuckets * sizeof(uint32_t)));
+    PK_CUDA(cudaMemcpyAsync(ix->route, owner_host, ix->nbuckets * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(ix->route + ix->nbuckets, dest_off_host, ix->nbuckets * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, st));
+    const uint8_t *seq = ix->p1_seq;
+    const size_t n = ix->p1_n;
+    ix->p1_seq = nullptr;
+    ix->p1_n = 0;
+    const int rc = indexer_launch_scan(ix, seq, n, st, SCAN_PASS2_REMOTE);
+    if (rc != PK_OK) return rc;
+    PK_CUDA(cudaStreamSynchronize(st));        // the pageable routing tables may go away; stores have landed
     return PK_OK;
 }
 

@@ -193,6 +193,45 @@ class Indexer:
         nat.check(lib.pk_indexer_import_segments(self._h, entries.data_ptr() if entries.numel() else 0,
                                                  seg_off.shape[0], seg_off.ctypes.data, seg_cnt.ctypes.data))
 
+    # ---- fused exchange: pass 2 stores into the window owners' buffers over NVLink ------------
+    def pool_ipc_handle(self) -> Tuple[bytes, int]:
+        buf = ctypes.create_string_buffer(64)
+        cap = ctypes.c_size_t(0)
+        nat.check(lib.pk_indexer_pool_ipc_handle(self._h, buf, ctypes.byref(cap)))
+        return buf.raw, int(cap.value)
+
+    def open_peer_pool(self, peer: int, handle: Optional[bytes] = None, local_owner: "Indexer" = None) -> None:
+        if local_owner is not None:
+            nat.check(lib.pk_indexer_open_peer_pool(self._h, peer, None, local_owner._h))
+        else:
+            buf = ctypes.create_string_buffer(handle, 64)
+            nat.check(lib.pk_indexer_open_peer_pool(self._h, peer, buf, None))
+
+    def scan_pass1(self, seq: torch.Tensor, stream=None) -> None:
+        assert seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()
+        self._keep.append(seq)
+        nat.check(lib.pk_indexer_scan_pass1(self._h, seq.data_ptr(), seq.numel(), _stream_ptr(stream)))
+
+    def pass1_counts(self) -> np.ndarray:
+        nwin = self.mode()[1]
+        cnt = np.zeros(nwin, dtype=np.uint32)
+        nat.check(lib.pk_indexer_pass1_counts(self._h, cnt.ctypes.data, nwin))
+        return cnt
+
+    def scan_pass2_remote(self, nranks: int, owner: np.ndarray, dest_off: np.ndarray, stream=None) -> None:
+        owner = np.ascontiguousarray(owner, dtype=np.uint32)
+        dest_off = np.ascontiguousarray(dest_off, dtype=np.uint32)
+        nat.check(lib.pk_indexer_scan_pass2_remote(self._h, nranks, owner.ctypes.data, dest_off.ctypes.data,
+                                                   _stream_ptr(stream)))
+        self._keep.clear()
+
+    def import_own_pool(self, seg_off: np.ndarray, seg_cnt: np.ndarray) -> None:
+        """Count entries that peers stored into this handle's own k-mer buffer."""
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint32)
+        seg_cnt = np.ascontiguousarray(seg_cnt, dtype=np.uint32)
+        nat.check(lib.pk_indexer_import_segments(self._h, None, seg_off.shape[0], seg_off.ctypes.data,
+                                                 seg_cnt.ctypes.data))
+
     PROFILE_CLASSES = ("scan_count_direct", "scan_bucket_count", "bucket_offsets", "scan_scatter",
                        "window_count", "window_commit", "table_stats", "update_carry")
 

@@ -221,3 +221,69 @@ def exchange_entries(scanner, counter, owners: Optional[List[Tuple[int, int]]] =
         print("[pykmer_b200] exchange ms: " + ", ".join(f"{n} {1e3 * (b - a):.3f}" for n, a, b in zip(names, t[:-1], t[1:]))
               + f"; sent {4 * int(send.sum() - send[:, rank].sum())} B", flush=True)
     return recv_buf
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused exchange: no all-to-all at all.  Pass 2 of every scanner stores its entries directly
+# into the k-mer buffer of the rank that owns the window (CUDA-IPC peer mapping, NVLink), so the
+# transfer rides on the scatter kernel's own coalesced stores.
+
+def plan_fused(all_cnt: np.ndarray, owners: List[Tuple[int, int]], rank: int):
+    """all_cnt[s, w] = entries of source rank s in window w.  Destination buffers are laid out
+    source by source, window by window.  -> (owner_of[w], dest_off_mine[w], imp_off, imp_cnt,
+    landed) with imp_* the (nranks, local windows) tables of what lands in THIS rank's buffer."""
+    nranks, nwin = all_cnt.shape
+    owner_of = np.zeros(nwin, dtype=np.uint32)
+    dest_off = np.zeros(nwin, dtype=np.uint32)
+    for d, (a, b) in enumerate(owners):
+        owner_of[a:b] = d
+        base = 0
+        for s in range(nranks):
+            c = all_cnt[s, a:b].astype(np.int64)
+            offs = base + np.concatenate(([0], np.cumsum(c)[:-1])) if b > a else np.zeros(0, dtype=np.int64)
+            if s == rank:
+                dest_off[a:b] = offs
+            base += int(c.sum())
+    w0, w1 = owners[rank]
+    imp_cnt = all_cnt[:, w0:w1].astype(np.uint32)
+    imp_off = np.zeros_like(imp_cnt)
+    base = 0
+    for s in range(nranks):
+        c = all_cnt[s, w0:w1].astype(np.int64)
+        imp_off[s] = base + np.concatenate(([0], np.cumsum(c)[:-1])) if w1 > w0 else 0
+        base += int(c.sum())
+    return owner_of, dest_off, imp_off, imp_cnt, base
+
+
+def connect_peer_pools(scanner, counter, group=None) -> None:
+    """Once per job: every scanner maps every counter's k-mer buffer (IPC handles all-gathered)."""
+    rank, nranks = world()
+    handle, cap = counter.pool_ipc_handle()
+    dev = _device_for_backend()
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    allh = torch.empty((nranks, 64), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+    allh = allh.cpu().numpy()
+    for d in range(nranks):
+        if d == rank:
+            scanner.open_peer_pool(d, local_owner=counter)
+        else:
+            scanner.open_peer_pool(d, handle=allh[d].tobytes())
+
+
+def exchange_fused(scanner, counter, seq: torch.Tensor, owners: List[Tuple[int, int]], group=None) -> np.ndarray:
+    """One sequence-sharded scan step with the exchange fused into pass 2.  `seq` is this rank's
+    slice (the scanner must have been reset and primed).  Leaves the counter importing what
+    landed in its buffer; returns all_cnt."""
+    rank, nranks = world()
+    scanner.scan_pass1(seq)
+    cnt = scanner.pass1_counts()
+    dev = seq.device
+    gathered = torch.empty((nranks, cnt.size), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(cnt.astype(np.int64)).to(dev), group=group)
+    all_cnt = gathered.cpu().numpy()
+    owner_of, dest_off, imp_off, imp_cnt, landed = plan_fused(all_cnt, owners, rank)
+    scanner.scan_pass2_remote(nranks, owner_of, dest_off)          # synchronises: stores have landed
+    dist.barrier(group=group)                                       # ... on every rank
+    counter.import_own_pool(imp_off, imp_cnt)
+    return all_cnt

@@ -652,3 +652,61 @@ def test_sequence_sharded_scan_exchange_count(env, K, wlog, nranks):
         os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
     assert total == num and np.array_equal(flags, oflags)
     assert np.array_equal(np.concatenate(tables), want)
+
+
+@pytest.mark.parametrize("K,wlog,nranks", [(9, 10, 3), (11, 12, 2), (17, 12, 4)])
+def test_fused_exchange_routing_on_one_gpu(env, K, wlog, nranks):
+    """The fused multi-GPU path (pass 2 stores straight into the window owners' buffers) with all
+    'ranks' living on one GPU: the same kernels, routing tables and import tables as the
+    NVLink run, peers mapped locally instead of through CUDA IPC."""
+    import torch
+    from pykmer_b200 import dist as pdist, _native as nat
+    dev, oracle = env["dev"], env["oracle"]
+    rng = np.random.default_rng(K * 11 + nranks)
+    s = _random_stream(rng, 150_000)
+    if K > 13:
+        s[::7] = ord("A"); s[1::7] = ord("A"); s[2::7] = ord("A")
+    starts = np.array([0, 30_000, 30_001, 90_000], dtype=np.uint64)
+    hi_all = min(4 ** K, 1 << 22)
+    want, num, oflags = oracle.index_stream(s, K, range_hi=hi_all, rec_starts=starts)
+    os.environ["PYKMER_B200_WINDOW_LOG2"] = str(wlog)
+    try:
+        scanners, pieces = [], []
+        for r in range(nranks):
+            a, b = pdist.slice_bounds(len(s), r, nranks)
+            sc = dev.Indexer(K, range_hi=hi_all, mode=nat.PK_MODE_SCAN)
+            sc.set_records(starts)
+            sc.prime(torch.from_numpy(s[max(0, a - 32):a].copy()).cuda() if a > 0 else None, a)
+            piece = torch.from_numpy(s[a:b].copy()).cuda()
+            sc.scan_pass1(piece)
+            scanners.append(sc)
+            pieces.append(piece)
+        all_cnt = np.stack([sc.pass1_counts() for sc in scanners]).astype(np.int64)
+        owners = pdist.balanced_window_owners(all_cnt.sum(axis=0), nranks, overhead=10)
+        counters = []
+        for d in range(nranks):
+            w0, w1 = owners[d]
+            counters.append(dev.Indexer(K, range_lo=w0 << wlog, range_hi=min(hi_all, w1 << wlog),
+                                        mode=nat.PK_MODE_PARTITION))
+        for r, sc in enumerate(scanners):
+            for d in range(nranks):
+                sc.open_peer_pool(d, local_owner=counters[d])
+            owner_of, dest_off, _, _, _ = pdist.plan_fused(all_cnt, owners, r)
+            sc.scan_pass2_remote(nranks, owner_of, dest_off)
+        tables = []
+        for d, ct in enumerate(counters):
+            _, _, imp_off, imp_cnt, landed = pdist.plan_fused(all_cnt, owners, d)
+            assert landed == int(all_cnt[:, owners[d][0]:owners[d][1]].sum())
+            ct.import_own_pool(imp_off, imp_cnt)
+            ct.finalize()
+            tables.append(ct.table_to_host().numpy().copy())
+        total = sum(sc.scan_result() for sc in scanners)
+        flags = np.zeros(len(starts), dtype=np.uint8)
+        for sc in scanners:
+            flags |= sc.record_flags()
+        for h in scanners + counters:
+            h.close()
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+    assert total == num and np.array_equal(flags, oflags)
+    assert np.array_equal(np.concatenate(tables), want)
