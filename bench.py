@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="sequence sharding: 'fused' = pass 2 stores into the owners' buffers over NVLink "
                          "(CUDA IPC peer mappings), 'nccl' = bucket locally, then torch all_to_all_single")
-    ap.add_argument("--shard", default="sequence", choices=["sequence", "kmer"],
+    ap.add_argument("--shard", default="auto", choices=["auto", "sequence", "kmer"],
                     help="N > 1 indexer: 'sequence' = each rank scans 1/N of the stream and the k-mer entries "
                          "are exchanged all-to-all; 'kmer' = every rank scans everything, keeps its k-mer range")
     ap.add_argument("--cpu-sample-mbp", type=float, default=128.0)
@@ -645,6 +645,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if args.shard == "auto":
+            # very sparse tables (K >= 19: 16384 windows) are bound by per-window launches, where
+            # the replicated scan with k-mer ranges measured faster (profiles/)
+            args.shard = "sequence" if (4 ** args.kmer >> 24) <= 4096 else "kmer"
         if args.workload == "indexer" and world > 1 and args.shard == "sequence":
             run_indexer_seqshard(args, rank, local_rank, world)
         elif args.workload == "indexer":

@@ -50,15 +50,15 @@ def reduce_index_stats(hist: List[int], st: Dict[str, int], group=None) -> Tuple
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return list(hist), dict(st)
     dev = _device_for_backend()
-    sums = torch.tensor(list(hist) + [st["num_kmers"], st["vals_sum"], st["vals_count"]],
-                        dtype=torch.int64, device=dev)
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    mm = torch.tensor([-st["vals_min"], st["vals_max"]], dtype=torch.int64, device=dev)
-    dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
-    s = sums.cpu().tolist()
-    m = mm.cpu().tolist()
+    n = dist.get_world_size(group)
+    mine = torch.tensor(list(hist) + [st["num_kmers"], st["vals_sum"], st["vals_count"],
+                                      st["vals_min"], st["vals_max"]], dtype=torch.int64, device=dev)
+    every = torch.empty((n, mine.numel()), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every.view(-1), mine, group=group)      # one collective, one copy back
+    e = every.cpu().numpy()
+    s = e[:, :258].sum(axis=0).tolist()
     return s[:255], {"num_kmers": s[255], "vals_sum": s[256], "vals_count": s[257],
-                     "vals_min": -m[0], "vals_max": m[1]}
+                     "vals_min": int(e[:, 258].min()), "vals_max": int(e[:, 259].max())}
 
 
 def reduce_flags(flags: np.ndarray, group=None) -> np.ndarray:
