@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restri
 // window by window, and written out as contiguous runs into the segments pass 1 sized.
 // entry = (run length - 1) << 24 | offset inside the window.
 template <bool WIDE, bool FULL>
-__global__ void __launch_bounds__(kScanThreads) k_scan_scatter(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(const ScanParams p) {
     extern __shared__ uint32_t sm[];
     const uint32_t nb = p.nbuckets;
     uint32_t *s_cnt = sm;                                  // [nb] entries of this tile per window
@@ -767,6 +767,15 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         else      { if (full) KERNEL<false, true><<<GRID, kScanThreads, SMEM, st>>>(p);        \
                     else      KERNEL<false, false><<<GRID, kScanThreads, SMEM, st>>>(p); }     \
     } while (0)
+#define PK_OCCUPANCY(KERNEL, SMEM, OUT)                                                        \
+    do {                                                                                       \
+        cudaError_t oe__;                                                                      \
+        if (wide) oe__ = full ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&OUT, KERNEL<true, true>, kScanThreads, SMEM)    \
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&OUT, KERNEL<true, false>, kScanThreads, SMEM);  \
+        else      oe__ = full ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&OUT, KERNEL<false, true>, kScanThreads, SMEM)   \
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&OUT, KERNEL<false, false>, kScanThreads, SMEM); \
+        if (oe__ != cudaSuccess || OUT < 1) { cudaGetLastError(); OUT = 1; }                   \
+    } while (0)
 #define PK_SMEM_OPT_IN(KERNEL, BYTES)                                                          \
     do {                                                                                       \
         PK_CUDA(cudaFuncSetAttribute(KERNEL<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));   \
@@ -778,8 +787,11 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     const long long ngroups = (long long)((n + 15) / 16);
     const long long ntiles = (ngroups + gpw - 1) / gpw;
     const long long want = (ntiles + kScanWarps - 1) / kScanWarps;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 8));
+    // grid-stride kernels: exactly as many blocks as are resident at once (no partial second wave)
     if (ix->mode == PK_MODE_DIRECT) {
+        int per_sm = 0;
+        PK_OCCUPANCY(k_scan_count_direct, 0, per_sm);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm));
         {
             prof_scope ps(ix, st, PROF_SCAN_DIRECT);
             PK_LAUNCH_SCAN(k_scan_count_direct, grid, 0);
@@ -805,6 +817,9 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             ix->scatter_smem_set = true;
         }
         if (phase != SCAN_PASS2_REMOTE) {
+            int per_sm = 0;
+            PK_OCCUPANCY(k_scan_bucket_count, smem1, per_sm);
+            const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm));
             {
                 prof_scope ps(ix, st, PROF_BUCKET_COUNT);
                 PK_LAUNCH_SCAN(k_scan_bucket_count, grid, smem1);
@@ -828,7 +843,10 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             p.dest_off = ix->route + ix->nbuckets;
             for (int i = 0; i < 16; i++) p.peer[i] = ix->peer_pool[i];
         }
-        const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * 4));
+        // persistent kernel: exactly as many blocks as are resident at once (no second wave)
+        int per_sm = 0;
+        PK_OCCUPANCY(k_scan_scatter, smem2, per_sm);
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm));
         {
             prof_scope ps(ix, st, PROF_SCATTER);
             PK_LAUNCH_SCAN(k_scan_scatter, grid2, smem2);
@@ -853,6 +871,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     return PK_OK;
 #undef PK_LAUNCH_SCAN
 #undef PK_SMEM_OPT_IN
+#undef PK_OCCUPANCY
 }
 
 // feeds are cut so that one partition pass never exceeds kMaxFeed bases
