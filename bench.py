@@ -127,6 +127,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/), or None."""
+    try:
+        import glob
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+        return int(json.load(open(files[-1]))[kernel]) if files else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -444,9 +454,11 @@ def run_indexer(args, rank, local_rank, world):
     dom_ms, dom_launches = prof[dom]
     achieved = alg_by_class[dom] / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_" + dom) if K == 15 else None,
+                "peak_source": peak_src,
                 "kernel_ms_total": dom_ms, "kernel_launches": dom_launches,
                 "algorithmic_bytes": alg_by_class[dom],
+                "algorithmic_bytes_per_launch": alg_by_class[dom] / max(dom_launches, 1),
                 "counted_kmers_per_s": n_k_local / (dom_ms * 1e-3) if dom in ("window_count", "scan_count_direct") else None,
                 "step_algorithmic_bytes": step_alg,
                 "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
