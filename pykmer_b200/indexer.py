@@ -13,6 +13,7 @@ from __future__ import annotations
 import hashlib
 import os
 import sys
+import time
 from typing import List, Optional
 
 import numpy as np
@@ -51,6 +52,7 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
     print(f"project_name {header.project_name} sample_name {header.sample_name} "
           f"kmer_len {header.kmer_len:15,d} kmer_size {header.kmer_size:15,d}")
     header.init_index_tmp_file(overwrite=overwrite)
+    t_start = time.perf_counter()
 
     fs = FastaStream(input_file, chunk_bytes=chunk_bytes)
     with dev.Indexer(kmer_len, device=device) as ix:
@@ -83,9 +85,16 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
     print(f"project_name {header.project_name} kmer_len {header.kmer_len:15,d} "
           f"num_kmers {header.num_kmers:15,d} kmer_size {header.kmer_size:15,d}")
 
+    t_gpu = time.perf_counter()
     checksum = _write_table(header.index_tmp_file, table)
+    t_write = time.perf_counter()
     header.write_metadata_index_tmp_file(output_checksum=checksum)
     os.rename(header.index_tmp_file, header.index_file)          # indexer.py:412
+    t_end = time.perf_counter()
+    header.wall_seconds = {"ingest_and_gpu": t_gpu - t_start, "write_and_sha256_table": t_write - t_gpu,
+                           "metadata_and_input_sha256": t_end - t_write, "total": t_end - t_start}
+    print("  wall: ingest+GPU {ingest_and_gpu:.2f} s, table write+sha256 {write_and_sha256_table:.2f} s, "
+          "metadata {metadata_and_input_sha256:.2f} s, total {total:.2f} s".format(**header.wall_seconds))
     return header
 
 
