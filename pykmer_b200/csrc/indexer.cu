@@ -1019,6 +1019,7 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part); cudaFree(ix->route);
+    if (ix->l2_persist_bytes) cudaCtxResetPersistingL2Cache();   // give the carve-out's lines back
     for (int i = 0; i < 16; i++)
         if (ix->peer_ipc[i]) cudaIpcCloseMemHandle(ix->peer_ipc[i]);
     for (int i = 0; i < 2; i++)

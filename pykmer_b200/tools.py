@@ -254,8 +254,12 @@ class Header(HeaderVars):
         """The uint8[4^K] table of a .kin / .kin.bgz file."""
         path = index_file or self.index_file
         if path.endswith("." + self.COMP_EXT):
-            with gzip.open(path, "rb") as fz:
-                arr = np.frombuffer(fz.read(), dtype=np.uint8)
+            from .fasta import bgzf_chunks, is_bgzf
+            if is_bgzf(path):                       # independent blocks: inflate on all host cores
+                arr = np.frombuffer(b"".join(bgzf_chunks(path)), dtype=np.uint8)
+            else:                                   # plain gzip stream, as the reference reads it
+                with gzip.open(path, "rb") as fz:
+                    arr = np.frombuffer(fz.read(), dtype=np.uint8)
         else:
             arr = np.fromfile(path, dtype=np.uint8)
         assert arr.size == self.data_size, f"{path}: {arr.size} bytes, expected {self.data_size}"

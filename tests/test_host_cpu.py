@@ -169,3 +169,26 @@ def test_merger_argument_validation(tmp_path):
         merger.main([str(tmp_path / "p"), str(tmp_path / "a.kin")])
     args = merger.build_parser().parse_args(["proj", "a.kin", "b.kin", "--max-count=50"])
     assert args.max_count == 50 and args.min_count == 1 and args.threads == 4
+
+
+def test_bgzf_module_roundtrip_and_kin_bgz_reader(tmp_path):
+    """.kin.bgz written by the parallel BGZF writer: gzip reads it (what the reference's merger does,
+    tools.py:296-302), the parallel reader reads it, Header.read_table takes either flavour."""
+    from pykmer_b200 import bgzf
+    K = 7
+    table = synth.synth_table(2, K)
+    base = str(tmp_path / "s.fa")
+    kin = base + ".07.kin"
+    table.tofile(kin)
+    out = bgzf.compress_file(kin, level=9, threads=3, batch=2)
+    assert out == kin + ".bgz" and fasta.is_bgzf(out)
+    assert gzip.open(out, "rb").read() == table.tobytes() == bgzf.read_all(out)
+    h = Header("p", input_file=base, kmer_len=K)
+    assert h.index_file == out                                   # .bgz preferred (tools.py:185-190)
+    assert np.array_equal(h.read_table(), table)
+    os.remove(out)
+    with gzip.open(out, "wb") as fz:                             # plain gzip under the .bgz name
+        fz.write(table.tobytes())
+    assert not fasta.is_bgzf(out) and np.array_equal(h.read_table(), table)
+    assert bgzf.decompress_file(bgzf.compress_file(kin, dst=str(tmp_path / "x.bgz")), str(tmp_path / "x.kin"))
+    assert open(tmp_path / "x.kin", "rb").read() == table.tobytes()
