@@ -1,11 +1,11 @@
 """merger: N .kin tables -> (N, N, 3) matrix of (Total #1, Total #2, Shared) (.kma + .kma.json).
 
 Host-side mirror of the reference's merger.py (argparse merger.py:51-59,
-calculate_distance :62-78, merge :80-210, main :213-239): same arguments,
-validation, output names and file contents.  The reference scans every pair of
-files (N(N-1)/2 tasks in a multiprocessing.Pool); here every table is read
-once, thresholded and bit-packed on the GPU, and the whole matrix is one Gram
-contraction G = B * B^T (pykmer_b200/csrc/merger.cu):
+calculate_distance :62-78, merge :80-210, main :213-239): same command line,
+validation, output names and file contents.  Where the reference scans every
+pair of files (N(N-1)/2 tasks in a multiprocessing.Pool), this module reads each
+table once, thresholds and bit-packs it on the GPU, and obtains the whole matrix
+from one Gram contraction G = B * B^T (pykmer_b200/csrc/merger.cu, gram_i8.cu):
 matrix[k, l] = (G[k,k], G[l,l], G[k,l]).
 
 The reference leaves the diagonal of the matrix uninitialised (merger.py:136);
@@ -15,17 +15,16 @@ from __future__ import annotations
 
 import argparse
 import json
-import os
 import sys
 from pathlib import Path
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from .tools import Header
 
-EXTS = ("." + Header.IND_EXT, "." + Header.IND_EXT + "." + Header.COMP_EXT,
-        ".kma", ".kma." + Header.COMP_EXT)
+KIN, PACKED = "." + Header.IND_EXT, "." + Header.COMP_EXT
+EXTS = (KIN, KIN + PACKED, ".kma", ".kma" + PACKED)                 # merger.py:38-43
 
 DEFAULT_MIN_COUNT = Header.DEFAULT_MIN_COUNT
 DEFAULT_MAX_COUNT = Header.DEFAULT_MAX_COUNT
@@ -33,41 +32,85 @@ DEFAULT_BUFFER_SIZE = Header.DEFAULT_BUFFER_SIZE
 DEFAULT_BLOCK_SIZE = Header.DEFAULT_BLOCK_SIZE
 DEFAULT_THREADS = 4
 
+# option, default, help text (the reference's CLI, merger.py:51-59)
+_OPTIONS = (
+    ("--min-count", DEFAULT_MIN_COUNT, "Minimum Kmer Count"),
+    ("--max-count", DEFAULT_MAX_COUNT, "Maximum Kmer Count"),
+    ("--buffer-size", DEFAULT_BUFFER_SIZE, "Buffer size"),
+    ("--block-size", DEFAULT_BLOCK_SIZE, "Block size"),
+    ("--threads", DEFAULT_THREADS, "Threads (kept for compatibility: the GPU path reads every table once)"),
+)
+
 
 def build_parser() -> argparse.ArgumentParser:
-    p = argparse.ArgumentParser(description="Merge kmer databases.")
-    p.add_argument("Project_Name", metavar="P", type=str, help="Project name")
-    p.add_argument("Kmer_1", metavar="K", type=Path, nargs=1, help="List of kin files")
-    p.add_argument("Kmer_N", metavar="K", type=Path, nargs="+", help="List of kin files")
-    p.add_argument("--min-count", type=int, default=DEFAULT_MIN_COUNT, nargs="?",
-                   help=f"Minimum Kmer Count [{DEFAULT_MIN_COUNT}]")
-    p.add_argument("--max-count", type=int, default=DEFAULT_MAX_COUNT, nargs="?",
-                   help=f"Maximum Kmer Count [{DEFAULT_MAX_COUNT}]")
-    p.add_argument("--buffer-size", type=int, default=DEFAULT_BUFFER_SIZE, nargs="?",
-                   help=f"Buffer size [{DEFAULT_BUFFER_SIZE}]")
-    p.add_argument("--block-size", type=int, default=DEFAULT_BLOCK_SIZE, nargs="?",
-                   help=f"Block size [{DEFAULT_BLOCK_SIZE}]")
-    p.add_argument("--threads", type=int, default=DEFAULT_THREADS, nargs="?",
-                   help=f"Threads [{DEFAULT_THREADS}] (accepted for compatibility; the GPU path "
-                        "reads each table once)")
-    return p
+    parser = argparse.ArgumentParser(description="Merge kmer databases.")
+    parser.add_argument("Project_Name", metavar="P", type=str, help="Project name")
+    for dest, nargs in (("Kmer_1", 1), ("Kmer_N", "+")):
+        parser.add_argument(dest, metavar="K", type=Path, nargs=nargs, help="List of kin files")
+    for flag, default, text in _OPTIONS:
+        parser.add_argument(flag, type=int, default=default, nargs="?", help=f"{text} [{default}]")
+    return parser
 
 
 def calculate_distance(k_index_file, l_index_file, min_count: int = DEFAULT_MIN_COUNT,
                        max_count: int = DEFAULT_MAX_COUNT, buffer_size: int = DEFAULT_BUFFER_SIZE,
                        block_size: int = DEFAULT_BLOCK_SIZE) -> Tuple[int, int, int]:
-    """One pair (merger.py:62-78) -> (Total k, Total l, Shared)."""
-    k_header = Header(str(k_index_file), index_file=str(k_index_file), buffer_size=buffer_size)
-    l_header = Header(str(l_index_file), index_file=str(l_index_file), buffer_size=buffer_size)
-    return k_header.calculate_distance(l_header, min_count=min_count, max_count=max_count,
-                                       block_size=block_size, threading=True)
+    """One pair of index files -> (Total k, Total l, Shared), as the Pool worker of the
+    reference returns it (merger.py:62-78)."""
+    pair = [Header(str(f), index_file=str(f), buffer_size=buffer_size) for f in (k_index_file, l_index_file)]
+    return pair[0].calculate_distance(pair[1], min_count=min_count, max_count=max_count,
+                                      block_size=block_size, threading=True)
+
+
+def _description_file(kin: Path) -> Path:
+    """<x>.kin[.bgz] -> <x>.kin.json (merger.py:112-113)."""
+    name = str(kin)
+    if name.endswith(PACKED):
+        name = name[:-len(PACKED)]
+    return Path(f"{name}.{Header.DESC_EXT}")
+
+
+def _check_inputs(indexes: Sequence[Path], buffer_size: int) -> List[Dict]:
+    """The reference's per-input checks (merger.py:104-129): extension, sibling JSON, equal K."""
+    entries: List[Dict] = []
+    for pos, kin in enumerate(indexes):
+        print(f"verifying {kin}")
+        assert str(kin).endswith(EXTS), f"all files must be .{Header.IND_EXT}[.bgz]: {kin}"
+        desc = _description_file(kin)
+        assert desc.exists(), (f"all .{Header.IND_EXT}[.{Header.COMP_EXT}] files must have a associated "
+                               f".{Header.IND_EXT}.{Header.DESC_EXT}: {desc}")
+        header = Header(str(kin), index_file=str(kin), buffer_size=buffer_size)
+        if entries:
+            want = entries[0]["header"].kmer_len
+            assert header.kmer_len == want, f"kmer_length differs. expected {want}, got {header.kmer_len}"
+        entries.append({"pos": pos, "index_file": str(kin), "description_file": str(desc), "header": header})
+    return entries
+
+
+def _save(outfile: Path, project_name: str, min_count: int, max_count: int, entries: List[Dict],
+          matrix: np.ndarray) -> None:
+    """.kma.json then .kma, each through a .tmp + rename (merger.py:190-208)."""
+    for e in entries:
+        e["header"] = e["header"].to_dict(lean=True)
+    doc = {"project_name": project_name, "min_count": min_count, "max_count": max_count, "data": entries}
+    json_path = Path(f"{outfile}.json")
+    print(f"saving {json_path}")
+    tmp = Path(f"{json_path}.tmp")
+    with tmp.open(mode="wt") as fh:
+        json.dump(doc, fh, sort_keys=True, indent=1)
+    tmp.rename(json_path)
+    print(f"saving {outfile}")
+    tmp = Path(f"{outfile}.tmp")
+    with tmp.open(mode="wb") as fh:
+        np.savez_compressed(fh, matrix=matrix)
+    tmp.rename(outfile)
 
 
 def merge(project_name: str, indexes: List[Path], min_count: int = DEFAULT_MIN_COUNT,
           max_count: int = DEFAULT_MAX_COUNT, buffer_size: int = DEFAULT_BUFFER_SIZE,
           block_size: int = DEFAULT_BLOCK_SIZE, threads: int = DEFAULT_THREADS,
           device: int = 0):
-    """merge (merger.py:80-210): validate, compute the matrix, write .kma.json and .kma."""
+    """merge (merger.py:80-210): validate, compute the matrix on the GPU, write the two files."""
     assert min_count >= 1                                     # merger.py:90-94
     assert max_count <= 255
     assert buffer_size > 0
@@ -81,49 +124,16 @@ def merge(project_name: str, indexes: List[Path], min_count: int = DEFAULT_MIN_C
 
     indexes = [Path(p) for p in indexes]
     assert all(i.exists() for i in indexes)
+    entries = _check_inputs(indexes, buffer_size)
 
-    data = []
-    kmer_len = None
-    for k, kin in enumerate(indexes):
-        print(f"verifying {kin}")
-        kins = str(kin)
-        assert kins.endswith(EXTS), f"all files must be .{Header.IND_EXT}[.bgz]: {kin}"
-        packed = "." + Header.COMP_EXT
-        desc = Path(f"{kins[:-len(packed)] if kins.endswith(packed) else kins}.{Header.DESC_EXT}")
-        assert desc.exists(), (f"all .{Header.IND_EXT}[.{Header.COMP_EXT}] files must have a "
-                               f"associated .{Header.IND_EXT}.{Header.DESC_EXT}: {desc}")
-        header = Header(kins, index_file=kins, buffer_size=buffer_size)
-        if kmer_len is None:
-            kmer_len = header.kmer_len
-        assert header.kmer_len == kmer_len, \
-            f"kmer_length differs. expected {kmer_len}, got {header.kmer_len}"
-        data.append({"pos": k, "index_file": kins, "description_file": str(desc), "header": header})
+    matrix = merge_tables([e["header"] for e in entries], min_count, max_count, device=device)
+    n = len(entries)
+    for k, l in ((k, l) for k in range(n - 1) for l in range(k + 1, n)):
+        t_k, t_l, shared = (int(v) for v in matrix[k, l])
+        print(f"   matrix Total #{k:3d} {t_k:15,d} Total #{l:3d} {t_l:15,d} Shared {shared:15,d}")
 
-    matrix = merge_tables([d["header"] for d in data], min_count, max_count, device=device)
-
-    for k in range(len(data) - 1):
-        for l in range(k + 1, len(data)):
-            print(f"   matrix Total #{k:3d} {int(matrix[k, l, 0]):15,d} Total #{l:3d} "
-                  f"{int(matrix[k, l, 1]):15,d} Shared {int(matrix[k, l, 2]):15,d}")
-
-    for v in data:
-        v["header"] = v["header"].to_dict(lean=True)
-    output = {"project_name": project_name, "min_count": min_count, "max_count": max_count,
-              "data": data}
-
-    outfile_json = Path(f"{outfile}.json")
-    outfile_json_tmp = Path(f"{outfile_json}.tmp")
-    print(f"saving {outfile_json}")
-    with outfile_json_tmp.open(mode="wt") as fh:
-        json.dump(output, fh, sort_keys=True, indent=1)
-    outfile_json_tmp.rename(outfile_json)
-
-    print(f"saving {outfile}")
-    outfile_tmp = Path(f"{outfile}.tmp")
-    with outfile_tmp.open(mode="wb") as fh:
-        np.savez_compressed(fh, matrix=matrix)
-    outfile_tmp.rename(outfile)
-    return data, matrix
+    _save(outfile, project_name, min_count, max_count, entries, matrix)
+    return entries, matrix
 
 
 def merge_tables(headers: List[Header], min_count: int, max_count: int, device: int = 0,
@@ -157,11 +167,10 @@ def merge_tables(headers: List[Header], min_count: int, max_count: int, device: 
 
 def main(argv: Optional[List[str]] = None) -> None:
     args = build_parser().parse_args(argv)
-    indexes: List[Path] = args.Kmer_1 + args.Kmer_N
+    indexes: List[Path] = sorted(args.Kmer_1 + args.Kmer_N)   # merger.py:228
     if len(indexes) <= 1:
         print("needs at least 2 files")
         sys.exit(1)
-    indexes.sort()                                             # merger.py:228
     merge(args.Project_Name, indexes, min_count=args.min_count, max_count=args.max_count,
           buffer_size=args.buffer_size, block_size=args.block_size, threads=args.threads)
 
