@@ -18,8 +18,8 @@
 //   warps 0-3  epilogue: tcgen05.ld the accumulator rows, add them into the global
 //              int64 Gram matrix.
 // NP (samples padded) is 64, 128 or 256; 256 uses two M=128 accumulators (all 512 TMEM
-// columns).  M=64 would not be faster than M=128 (half-rate), so for NP=64 the A
-// descriptor simply runs on into the next tile and rows 64..127 of D are ignored.
+// columns); 64 uses M=64 MMAs (half the A-operand traffic from shared memory, which is what
+// bounds that small tile).
 #include <algorithm>
 
 #include "common.h"
@@ -61,9 +61,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return d;                                             // layout_type 0 = no swizzle
 }
 
-// instruction descriptor, kind::i8: D = S32, A = B = unsigned 8 bit, both K-major, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor, kind::i8: D = S32, A = B = unsigned 8 bit, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -109,6 +109,10 @@ struct GramCfg {
     static constexpr int kTileBytes = NP * 32;            // one K=32 step of all NP rows
     static constexpr int kStageBytes = kKB * kTileBytes;
     static constexpr int kMTiles = NP == 256 ? 2 : 1;
+    // NP = 64 runs M = 64 MMAs: same 32 cycles as M = 128, but only half the A operand is read
+    // from shared memory, which is what bounds this small tile (4 KB instead of 6 KB per MMA).
+    // D then sits in "half sub-partition" layout: row r in TMEM lane (r % 16) + 32 * (r / 16).
+    static constexpr int kM = NP == 64 ? 64 : 128;
     static constexpr int kTmemCols = NP == 256 ? 512 : NP;
     static constexpr int kPad = 4096;                     // the M=128 descriptor of a 64-row tile overruns
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kPad + 256 + 1024;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc(NP);
+        const uint32_t idesc = make_idesc(C::kM, NP);
         for (size_t it = 0; it < nst; it++) {
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
@@ -256,8 +260,11 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int mt = 0; mt < C::kMTiles; mt++) {
-            const int row = mt * 128 + warp * 32 + lane;
-            if (mt * 128 + warp * 32 >= nsamples) continue;       // warp-uniform
+            // M = 128: lane l of warp w holds row 32 w + l; M = 64: lanes 0..15 hold rows 16 w + l
+            const int row_base = C::kM == 64 ? warp * 16 : mt * 128 + warp * 32;
+            const bool lane_has_row = C::kM == 64 ? lane < 16 : true;
+            const int row = row_base + lane;
+            if (row_base >= nsamples) continue;                   // warp-uniform
 #pragma unroll 1
             for (int c0 = 0; c0 < NP; c0 += 32) {
                 if (c0 >= nsamples) break;
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
                       "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < nsamples) {
+                if (lane_has_row && row < nsamples) {
 #pragma unroll
                     for (int c = 0; c < 32; c++)
                         if (c0 + c < nsamples && v[c])
