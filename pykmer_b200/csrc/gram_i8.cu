@@ -80,6 +80,17 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
                  : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 // 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
     return (nib * 0x00204081u) & 0x01010101u;
@@ -230,28 +241,34 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {
         // ------------------------------------------------------------ MMA issuer
+        // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors and
+        // barrier addresses in uniform registers); one elected lane issues the instructions.
         const uint32_t idesc = make_idesc(C::kM, NP);
+        const uint64_t desc0 = make_desc(smem_u32(smem), 128, 256);
         for (size_t it = 0; it < nst; it++) {
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&full_bar[s]), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t stage = smem_u32(smem + (size_t)s * C::kStageBytes);
+            if (elect_one()) {
+                // descriptor start address is in 16-byte units: stage and K-step are plain adds
+                const uint64_t dstage = desc0 + (uint64_t)((s * C::kStageBytes) >> 4);
 #pragma unroll
-            for (int kb = 0; kb < kKB; kb++) {
-                const uint32_t tile = stage + kb * C::kTileBytes;
-                const uint64_t bdesc = make_desc(tile, 128, 256);
+                for (int kb = 0; kb < kKB; kb++) {
+                    const uint64_t bdesc = dstage + (uint64_t)((kb * C::kTileBytes) >> 4);
 #pragma unroll
-                for (int mt = 0; mt < C::kMTiles; mt++) {
-                    const uint64_t adesc = make_desc(tile + mt * 128 * 32, 128, 256);
-                    mma_i8(tmem_base + mt * NP, adesc, bdesc, idesc, (it | kb) ? 1u : 0u);
+                    for (int mt = 0; mt < C::kMTiles; mt++)
+                        mma_i8(tmem_base + mt * NP, bdesc + (uint64_t)((mt * 128 * 32) >> 4), bdesc, idesc,
+                               (it | kb) ? 1u : 0u);
                 }
+                mma_commit(smem_u32(&empty_bar[s]));      // frees the stage when the MMAs retire
             }
-            mma_commit(smem_u32(&empty_bar[s]));          // frees the stage when the MMAs retire
+            __syncwarp();
         }
-        mma_commit(smem_u32(done_bar));
+        if (elect_one()) mma_commit(smem_u32(done_bar));
+        __syncwarp();
     }
 
     if (warp < 4 && nst) {
