@@ -487,6 +487,216 @@ __global__ void __launch_bounds__(256) k_reduce_bins(const unsigned long long *_
     bins[threadIdx.x] = s;
 }
 
+
+// ------------------------------------------------------------------------------ smem flush
+// Second level of the partition (dense tables): the entries of every 2^24 window are split
+// once more into 512 sub-buckets of 2^15 table entries, whose 32-bit counters fit in the
+// shared memory of one CTA (128 KB).  Counting then runs on shared-memory atomics (~1 T/s
+// measured) instead of L2 atomics (~0.16 T/s), and one CTA turns its counters straight into
+// 32 KB of table bytes + histogram: no counter array in L2, no separate commit pass.
+constexpr int kSubLog2 = 15;                    // table entries per sub-bucket
+constexpr int kSubs = 1 << (24 - kSubLog2);     // sub-buckets per 2^24 window (512)
+constexpr int kSubTile = 8192;                  // entries one CTA ranks per step in k_sub_scatter
+constexpr int kSubThreads = 512;
+
+// entries of window (w_first + blockIdx.y) -> per-sub-bucket counts
+__global__ void __launch_bounds__(256) k_sub_count(const uint32_t *__restrict__ pool,
+                                                   const uint32_t *__restrict__ seg_off,
+                                                   const uint32_t *__restrict__ seg_cnt, int nseg,
+                                                   uint32_t nb, uint32_t w_first, uint32_t win_log2,
+                                                   uint32_t *__restrict__ sub_cnt) {
+    __shared__ uint32_t s_cnt[kSubs];
+    for (int i = threadIdx.x; i < kSubs; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const uint32_t b = w_first + blockIdx.y;
+    const uint32_t wmask = (1u << win_log2) - 1u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int f = 0; f < nseg; f++) {
+        const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride)
+            atomicAdd(&s_cnt[(__ldg(pool + off + i) & wmask) >> kSubLog2], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSubs; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(&sub_cnt[(size_t)blockIdx.y * kSubs + i], s_cnt[i]);
+}
+
+// exclusive scan over nwin * 512 sub-bucket counts -> offsets in the second pool
+__global__ void __launch_bounds__(1024) k_sub_offsets(const uint32_t *__restrict__ cnt,
+                                                      uint32_t *__restrict__ off, uint32_t n) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(n, b0 + per);
+    uint32_t s = 0;
+    for (uint32_t b = b0; b < b1; b++) s += cnt[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v[32], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { v[i] = part[threadIdx.x * 32 + i]; sum += v[i]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)threadIdx.x >= o) incl += up;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { part[threadIdx.x * 32 + i] = run; run += v[i]; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t b = b0; b < b1; b++) { off[b] = run; run += cnt[b]; }
+}
+
+// entries of window (w_first + blockIdx.y) -> second pool, grouped by sub-bucket
+__global__ void __launch_bounds__(kSubThreads) k_sub_scatter(const uint32_t *__restrict__ pool,
+                                                             const uint32_t *__restrict__ seg_off,
+                                                             const uint32_t *__restrict__ seg_cnt, int nseg,
+                                                             uint32_t nb, uint32_t w_first, uint32_t win_log2,
+                                                             const uint32_t *__restrict__ sub_off,
+                                                             uint32_t *__restrict__ sub_fill,
+                                                             uint32_t *__restrict__ pool2) {
+    extern __shared__ uint32_t sm2[];
+    uint32_t *s_cnt = sm2;                         // [kSubs]
+    uint32_t *s_toff = sm2 + kSubs;                // [kSubs]
+    uint32_t *s_gbase = sm2 + 2 * kSubs;           // [kSubs]
+    uint32_t *s_ent = sm2 + 3 * kSubs;             // [kSubTile]
+    uint16_t *s_sid = reinterpret_cast<uint16_t *>(s_ent + kSubTile);   // [kSubTile]
+    __shared__ uint32_t s_total;
+    const uint32_t b = w_first + blockIdx.y;
+    const uint32_t wmask = (1u << win_log2) - 1u;
+    const size_t sbase = (size_t)blockIdx.y * kSubs;
+    constexpr int kPer = kSubTile / kSubThreads;   // 16 entries per thread
+    for (int f = 0; f < nseg; f++) {
+        const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
+        const uint32_t ntiles = (cnt + kSubTile - 1) / kSubTile;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            __syncthreads();                                  // previous tile fully written out
+            for (int i = threadIdx.x; i < kSubs; i += blockDim.x) s_cnt[i] = 0;
+            __syncthreads();
+            const uint32_t t0 = tile * kSubTile;
+            uint32_t ent[kPer], key[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                const uint32_t i = t0 + k * kSubThreads + threadIdx.x;      // coalesced
+                key[k] = 0xFFFFFFFFu;
+                if (i < cnt) {
+                    ent[k] = __ldcs(pool + off + i);
+                    const uint32_t sub = (ent[k] & wmask) >> kSubLog2;
+                    key[k] = (sub << 16) | atomicAdd(&s_cnt[sub], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {                           // scan the 512 counts with one warp
+                uint32_t v[kSubs / 32], sum = 0;
+#pragma unroll
+                for (int i = 0; i < kSubs / 32; i++) { v[i] = s_cnt[threadIdx.x * (kSubs / 32) + i]; sum += v[i]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if ((int)threadIdx.x >= o) incl += up;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int i = 0; i < kSubs / 32; i++) { s_toff[threadIdx.x * (kSubs / 32) + i] = run; run += v[i]; }
+                if (threadIdx.x == 31) s_total = incl;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < kSubs; i += blockDim.x) {
+                const uint32_t c = s_cnt[i];
+                if (c) s_gbase[i] = sub_off[sbase + i] + atomicAdd(&sub_fill[sbase + i], c);
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                if (key[k] != 0xFFFFFFFFu) {
+                    const uint32_t sub = key[k] >> 16, pos = s_toff[sub] + (key[k] & 0xFFFFu);
+                    s_ent[pos] = ent[k];
+                    s_sid[pos] = (uint16_t)sub;
+                }
+            }
+            __syncthreads();
+            const uint32_t total = s_total;
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                const uint32_t sub = s_sid[i];
+                pool2[s_gbase[sub] + (i - s_toff[sub])] = s_ent[i];
+            }
+        }
+    }
+}
+
+// one CTA per sub-bucket of window w: count in shared memory, write 32 KB of the table
+template <bool ACCUM>
+__global__ void __launch_bounds__(1024, 1) k_sub_tally(const uint32_t *__restrict__ pool2,
+                                                       const uint32_t *__restrict__ sub_off,
+                                                       const uint32_t *__restrict__ sub_cnt,
+                                                       uint32_t w_local, uint8_t *__restrict__ table_win,
+                                                       size_t n_win, unsigned long long *__restrict__ bins) {
+    extern __shared__ uint32_t sm3[];
+    uint32_t *cnt = sm3;                                     // [2^15]
+    uint32_t(*sh)[256] = reinterpret_cast<uint32_t(*)[256]>(sm3 + (1 << kSubLog2));   // [8][256]
+    const uint32_t sub = blockIdx.x;
+    const size_t first = (size_t)sub << kSubLog2;            // first table entry of this sub-bucket
+    if (first >= n_win) return;
+    const uint32_t n_here = (uint32_t)min((size_t)(1u << kSubLog2), n_win - first);
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(cnt);
+        for (int i = threadIdx.x; i < (1 << kSubLog2) / 4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        if (bins) for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    }
+    __syncthreads();
+    const size_t si = (size_t)w_local * kSubs + sub;
+    const uint32_t off = sub_off[si], m = sub_cnt[si];
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const uint32_t e = __ldcs(pool2 + off + i);
+        atomicAdd(&cnt[e & ((1u << kSubLog2) - 1u)], (e >> 24) + 1u);
+    }
+    __syncthreads();
+    const int warp = (threadIdx.x >> 5) & 7;
+    uint32_t c1 = 0, c2 = 0, c3 = 0;
+    uint32_t *tw = reinterpret_cast<uint32_t *>(table_win + first);
+    const uint32_t nq = n_here / 4;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const uint4 c = *reinterpret_cast<const uint4 *>(cnt + 4 * q);
+        const uint32_t x = commit_quad(c, ACCUM ? tw[q] : 0u, ACCUM);
+        __stcs(tw + q, x);
+        if (bins && x) {
+            c1 += __popc(__vcmpeq4(x, 0x01010101u)) >> 3;
+            c2 += __popc(__vcmpeq4(x, 0x02020202u)) >> 3;
+            c3 += __popc(__vcmpeq4(x, 0x03030303u)) >> 3;
+            if (x & 0xFCFCFCFCu) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t val = (x >> (8 * b)) & 0xFFu;
+                    if (val > 3u) atomicAdd(&sh[warp][val], 1u);
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {                                  // < 4 tail entries
+        for (uint32_t k = nq * 4; k < n_here; k++) {
+            uint32_t val = cnt[k];
+            if (ACCUM) val += table_win[first + k];
+            val = min(val, 255u);
+            table_win[first + k] = (uint8_t)val;
+            if (bins && val) atomicAdd(&sh[0][val], 1u);
+        }
+    }
+    if (!bins) return;
+    if (c1) atomicAdd(&sh[warp][1], c1);
+    if (c2) atomicAdd(&sh[warp][2], c2);
+    if (c3) atomicAdd(&sh[warp][3], c3);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += sh[k][threadIdx.x];
+        if (s && threadIdx.x) bins[(size_t)blockIdx.x * 256 + threadIdx.x] += s;
+    }
+}
+
 // new carry = last kCarry bytes of (old carry ++ seq[0..n))
 __global__ void k_update_carry(uint8_t *carry, const uint8_t *seq, size_t n) {
     const int i = threadIdx.x;                            // 32 threads
@@ -604,6 +814,10 @@ struct pk_indexer {
     uint32_t *cursor = nullptr;                // device pool cursor
     uint32_t *scratch = nullptr;               // one window of 32-bit counters
     unsigned long long *bins_part = nullptr;   // [4 * sm_count][256] partial histograms
+    uint32_t *pool2 = nullptr;                 // smem flush: entries regrouped by sub-bucket
+    uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
+    bool flush_smem = true;                    // second-level shared-memory flush (else L2 counters)
+    bool sub_smem_set = false;
     cudaEvent_t committed[2] = {nullptr, nullptr};
     int nseg = 0;
     size_t l2_persist_bytes = 0;               // persisting-L2 carve-out granted for `scratch`
@@ -674,7 +888,9 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
 // side on two streams was measured and is slower: both live off the same L2.
 // When table_host != NULL every committed window is copied out at once on the copy
 // stream, so the device-to-host transfer of the table overlaps the rest of the flush.
-static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
+static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host);
+
+static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
     const size_t win = (size_t)1 << ix->win_log2;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg;
@@ -713,6 +929,12 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
             PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
         }
     }
+    return indexer_flush_finish(ix, st, with_stats, table_host);
+}
+
+// common end of a flush: join the table copies, reduce the histogram, recycle the buffers
+static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
+    const int rows = ix->sm_count * 4;
     if (table_host) {
         PK_CUDA(cudaEventRecord(ix->committed[0], ix->copy_stream));
         PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
@@ -745,6 +967,64 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
     ix->table_valid = true;
     ix->stats_valid = with_stats;
     return PK_OK;
+}
+
+// PARTITION, dense tables: second-level split + shared-memory counting (k_sub_*).
+static int indexer_flush_smem(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
+    const size_t win = (size_t)1 << ix->win_log2;
+    const int rows = ix->sm_count * 4;                      // >= kSubs rows of partial bins
+    if (with_stats)
+        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
+    unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
+    const uint32_t *src = ix->pool_ext ? ix->pool_ext : ix->pool;
+    constexpr uint32_t kGroup = 64;                         // windows regrouped per pass over the pool
+    uint32_t *sub_cnt = ix->sub, *sub_off = ix->sub + kGroup * kSubs, *sub_fill = ix->sub + 2 * kGroup * kSubs;
+    const size_t smem_scatter = (size_t)3 * kSubs * sizeof(uint32_t) + (size_t)kSubTile * 6;
+    const size_t smem_tally = ((size_t)(1 << kSubLog2) + 8 * 256) * sizeof(uint32_t);
+    if (!ix->sub_smem_set) {
+        PK_CUDA(cudaFuncSetAttribute(k_sub_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        PK_CUDA(cudaFuncSetAttribute(k_sub_tally<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally));
+        PK_CUDA(cudaFuncSetAttribute(k_sub_tally<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally));
+        ix->sub_smem_set = true;
+    }
+    for (uint32_t w0 = 0; w0 < ix->nbuckets; w0 += kGroup) {
+        const uint32_t W = std::min(kGroup, ix->nbuckets - w0);
+        PK_CUDA(cudaMemsetAsync(ix->sub, 0, (size_t)3 * kGroup * kSubs * sizeof(uint32_t), st));
+        if (ix->nseg) {
+            {
+                prof_scope ps(ix, st, PROF_WINDOW_COUNT);
+                k_sub_count<<<dim3(32, W), 256, 0, st>>>(src, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg, ix->nbuckets,
+                                                        w0, ix->win_log2, sub_cnt);
+                k_sub_offsets<<<1, 1024, 0, st>>>(sub_cnt, sub_off, W * kSubs);
+                k_sub_scatter<<<dim3(16, W), kSubThreads, smem_scatter, st>>>(
+                    src, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg, ix->nbuckets, w0, ix->win_log2, sub_off, sub_fill,
+                    ix->pool2);
+            }
+            ix->launches += 3;
+        }
+        for (uint32_t b = 0; b < W; b++) {
+            const size_t n = std::min(win, ix->table_bytes - (size_t)(w0 + b) * win);
+            uint8_t *tw = ix->table + (size_t)(w0 + b) * win;
+            const unsigned nsub = (unsigned)((n + (1u << kSubLog2) - 1) >> kSubLog2);
+            {
+                prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
+                if (ix->table_valid) k_sub_tally<true><<<nsub, 1024, smem_tally, st>>>(ix->pool2, sub_off, sub_cnt, b, tw, n, bins);
+                else                 k_sub_tally<false><<<nsub, 1024, smem_tally, st>>>(ix->pool2, sub_off, sub_cnt, b, tw, n, bins);
+            }
+            ix->launches++;
+            if (table_host) {                               // ship this window while the next is counted
+                PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
+                PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
+                PK_CUDA(cudaMemcpyAsync(table_host + (size_t)(w0 + b) * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+            }
+        }
+    }
+    return indexer_flush_finish(ix, st, with_stats, table_host);
+}
+
+static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
+    return ix->flush_smem ? indexer_flush_smem(ix, st, with_stats, table_host)
+                          : indexer_flush_l2(ix, st, with_stats, table_host);
 }
 
 enum { SCAN_BOTH = 0, SCAN_PASS1 = 1, SCAN_PASS2_REMOTE = 2 };
@@ -962,14 +1242,23 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
         if (mode == PK_MODE_PARTITION) {
-            step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+            // how a window is counted: second-level split + shared-memory counters (default), or
+            // 32-bit counters kept in L2 (PYKMER_B200_FLUSH=l2; the first scheme of this repo)
+            const char *fe = getenv("PYKMER_B200_FLUSH");
+            ix->flush_smem = !(fe && strcmp(fe, "l2") == 0);
             step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
+            if (ix->flush_smem) {
+                step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
+                step(cudaMalloc(&ix->sub, (size_t)3 * 64 * kSubs * sizeof(uint32_t)));
+            } else {
+                step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+            }
         }
         for (int i = 0; i < 2; i++)
             step(cudaEventCreateWithFlags(&ix->committed[i], cudaEventDisableTiming));
         // persisting-L2 carve-out for the counters (PYKMER_B200_L2_PERSIST=0 disables it)
         const char *pe = getenv("PYKMER_B200_L2_PERSIST");
-        if (e == cudaSuccess && mode == PK_MODE_PARTITION && !(pe && atoi(pe) == 0)) {
+        if (e == cudaSuccess && mode == PK_MODE_PARTITION && !ix->flush_smem && !(pe && atoi(pe) == 0)) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
@@ -1018,7 +1307,7 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
-    cudaFree(ix->bins_part); cudaFree(ix->route);
+    cudaFree(ix->bins_part); cudaFree(ix->route); cudaFree(ix->pool2); cudaFree(ix->sub);
     if (ix->l2_persist_bytes) cudaCtxResetPersistingL2Cache();   // give the carve-out's lines back
     for (int i = 0; i < 16; i++)
         if (ix->peer_ipc[i]) cudaIpcCloseMemHandle(ix->peer_ipc[i]);

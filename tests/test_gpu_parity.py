@@ -27,11 +27,13 @@ def env():
 
 
 def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0,
-                  window_log2=None, pool_log2=None):
+                  window_log2=None, pool_log2=None, flush=None):
     import torch
     hi = 4 ** K if hi is None else hi
-    # test hooks of the library: small table windows / small k-mer buffer (read at create time)
-    for name, val in (("PYKMER_B200_WINDOW_LOG2", window_log2), ("PYKMER_B200_POOL_LOG2", pool_log2)):
+    # test hooks of the library: small table windows / small k-mer buffer / flush scheme
+    # (read at create time)
+    for name, val in (("PYKMER_B200_WINDOW_LOG2", window_log2), ("PYKMER_B200_POOL_LOG2", pool_log2),
+                      ("PYKMER_B200_FLUSH", flush)):
         if val is None:
             os.environ.pop(name, None)
         else:
@@ -41,6 +43,7 @@ def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=
     finally:
         os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
         os.environ.pop("PYKMER_B200_POOL_LOG2", None)
+        os.environ.pop("PYKMER_B200_FLUSH", None)
     with ix:
         if starts is not None:
             ix.set_records(starts)
@@ -422,7 +425,8 @@ PART = 2   # PK_MODE_PARTITION
 @pytest.mark.parametrize("K,wlog", [(5, 4), (5, 24), (9, 6), (9, 10), (11, 10), (11, 16), (13, 14), (13, 24)])
 @pytest.mark.parametrize("n", [0, 17, 4000, 100_003, 1_000_003])
 @pytest.mark.parametrize("plog", [12, 30])
-def test_partition_mode_random_streams_vs_oracle(env, K, wlog, n, plog):
+@pytest.mark.parametrize("flush", ["smem", "l2"])
+def test_partition_mode_random_streams_vs_oracle(env, K, wlog, n, plog, flush):
     """Window-partitioned counting (many windows, and a tiny k-mer buffer that forces
     repeated saturating flushes) gives the oracle's table, statistics and num_kmers."""
     if plog == 12 and n > 200_000:
@@ -430,7 +434,7 @@ def test_partition_mode_random_streams_vs_oracle(env, K, wlog, n, plog):
     rng = np.random.default_rng(31 * K + n + wlog)
     s = _random_stream(rng, n)
     want, num, _ = env["oracle"].index_stream(s, K)
-    table, hist, st, _ = _index_stream(env["dev"], s, K, mode=PART, window_log2=wlog, pool_log2=plog)
+    table, hist, st, _ = _index_stream(env["dev"], s, K, mode=PART, window_log2=wlog, pool_log2=plog, flush=flush)
     assert st["num_kmers"] == num
     assert np.array_equal(table, want)
     oh, ost = env["oracle"].table_stats(want)
@@ -446,10 +450,10 @@ def test_partition_mode_matches_reference_golden(env, case):
     gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
     stream, names, starts, lengths = fasta.read_fasta_stream(os.path.join(GOLD, "inputs", fname))
     wlog = 4 if K <= 7 else 12
-    for pieces in (None, [7, 100, 101, 5000]):
+    for pieces, flush in ((None, "smem"), ([7, 100, 101, 5000], "smem"), ([7, 100, 101, 5000], "l2")):
         pieces = [c for c in (pieces or []) if c < len(stream)] or None
         table, hist, st, flags = _index_stream(env["dev"], stream, K, starts=starts, mode=PART,
-                                               window_log2=wlog, pieces=pieces)
+                                               window_log2=wlog, pieces=pieces, flush=flush)
         assert st["num_kmers"] == gold["num_kmers"] and hist == gold["hist"]
         assert hashlib.sha256(table.tobytes()).hexdigest() == gold["output_file_cheksum"]
         chrom = [[names[i], lengths[i]] for i in range(len(names)) if flags[i]]
@@ -533,8 +537,14 @@ def test_full_size_config2_modes_agree(env):
     stream, starts, lengths = bench.load_stream(1.0, 0, 1)
     d = torch.from_numpy(stream).cuda()
     digests, stats = [], []
-    for mode in (1, 2):
-        with dev.Indexer(15, mode=mode) as ix:
+    for mode, flush in ((1, None), (2, "smem"), (2, "l2")):
+        if flush:
+            os.environ["PYKMER_B200_FLUSH"] = flush
+        try:
+            ix = dev.Indexer(15, mode=mode)
+        finally:
+            os.environ.pop("PYKMER_B200_FLUSH", None)
+        with ix:
             ix.set_records(starts)
             ix.feed_device(d)
             hist, st = ix.finalize()
@@ -554,7 +564,7 @@ def test_full_size_config2_modes_agree(env):
             for q in range(15):
                 rc |= (3 - ((idx >> (2 * q)) & 3)) << (2 * (14 - q))
             assert not host[idx[idx > rc]].any()
-    assert digests[0] == digests[1] and stats[0] == stats[1]
+    assert digests[0] == digests[1] == digests[2] and stats[0] == stats[1] == stats[2]
 
 
 @pytest.mark.parametrize("mode,wlog", [(1, None), (2, 10), (2, 24)])
