@@ -816,7 +816,7 @@ struct pk_indexer {
     unsigned long long *bins_part = nullptr;   // [4 * sm_count][256] partial histograms
     uint32_t *pool2 = nullptr;                 // smem flush: entries regrouped by sub-bucket
     uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
-    bool flush_smem = true;                    // second-level shared-memory flush (else L2 counters)
+    bool flush_smem = false;                   // second-level shared-memory flush (else L2 counters)
     bool sub_smem_set = false;
     cudaEvent_t committed[2] = {nullptr, nullptr};
     int nseg = 0;
@@ -1242,10 +1242,14 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
         if (mode == PK_MODE_PARTITION) {
-            // how a window is counted: second-level split + shared-memory counters (default), or
-            // 32-bit counters kept in L2 (PYKMER_B200_FLUSH=l2; the first scheme of this repo)
+            // how a window is counted: 32-bit counters kept in L2 (default), or a second-level
+            // split + shared-memory counters (PYKMER_B200_FLUSH=smem).  Measured on config 2
+            // (profiles/r01_ncu_sub_kernels.txt): L2 flush 6.5 ms, smem flush 13.8 ms -- its three
+            // extra passes over the 3.1 GB of entries are latency bound as written (scalar entry
+            // loads, one tile in flight per CTA); kept as the second, independent implementation
+            // the tests cross-check, and as the starting point for the next round.
             const char *fe = getenv("PYKMER_B200_FLUSH");
-            ix->flush_smem = !(fe && strcmp(fe, "l2") == 0);
+            ix->flush_smem = fe && strcmp(fe, "smem") == 0;
             step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
             if (ix->flush_smem) {
                 step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
