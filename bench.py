@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--shard", default="auto", choices=["auto", "sequence", "kmer"],
                     help="N > 1 indexer: 'sequence' = each rank scans 1/N of the stream and the k-mer entries "
                          "are exchanged all-to-all; 'kmer' = every rank scans everything, keeps its k-mer range")
+    ap.add_argument("--emulate-shard", default=None, metavar="R/N",
+                    help="development aid: on ONE GPU, run the k-mer-range shard that rank R of N would own "
+                         "(not a bench line: one rank's share of a multi-GPU job)")
     ap.add_argument("--cpu-sample-mbp", type=float, default=128.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -291,7 +294,8 @@ def run_indexer_seqshard(args, rank, local_rank, world):
     all_cnt = pdist.gather_window_counts(scanner)
     owners = pdist.balanced_window_owners(all_cnt.sum(axis=(0, 1)), world)
     w0, w1 = owners[rank]
-    lo, hi = w0 << 24, min(T, w1 << 24)
+    wl = scanner.window_log2()
+    lo, hi = w0 << wl, min(T, w1 << wl)
     counter = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=nat.PK_MODE_PARTITION)
     fused = args.exchange == "fused"
     if fused:
@@ -402,6 +406,9 @@ def run_indexer(args, rank, local_rank, world):
     L = int(sum(lengths))
     from pykmer_b200 import dist as pdist
     lo, hi = pdist.shard_range(T, rank, world)               # k-mer-axis shard of this rank
+    if args.emulate_shard:
+        er, en = (int(x) for x in args.emulate_shard.split("/"))
+        lo, hi = pdist.shard_range(T, er, en)
 
     d_stream = torch.from_numpy(stream).cuda()
     ix = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=args.mode)
@@ -498,7 +505,9 @@ def run_indexer(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": f"indexer K={K}, synthetic tomato-sized multi-FASTA stream "
                                    f"({L} bp, 13 records), 4^{K}-byte table",
-                       "parallelism": f"kmer-range x{world}" if world > 1 else "single GPU",
+                       "parallelism": f"kmer-range x{world}" if world > 1 else
+                                      (f"ONE shard ({args.emulate_shard}) of a k-mer-range job, development run"
+                                       if args.emulate_shard else "single GPU"),
                        "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
                        "vals_count": st["vals_count"], "vals_max": st["vals_max"]},
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "gpu_launches": launches,

@@ -66,10 +66,14 @@ int         pk_host_free(void *ptr);
  */
 #define PK_MODE_AUTO      0   /* PARTITION for tables beyond 64 Mi entries, else DIRECT */
 #define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
-#define PK_MODE_PARTITION 2   /* bucket k-mers by 2^24-entry table window, count each window
-                                 with L2-resident 32-bit counters, clamp and write it once.
-                                 (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 shrink the
-                                 window and the k-mer buffer; they exist for the tests.) */
+#define PK_MODE_PARTITION 2   /* bucket k-mers by table window, count each window in L2 and write
+                                 it once: 2^24-entry windows with 32-bit counters for K <= 15,
+                                 2^26-entry windows holding the table's own 8-bit lanes (carries
+                                 settled exactly) for K >= 17; pk_indexer_window_log2 tells.
+                                 (PYKMER_B200_WINDOW_LOG2 / PYKMER_B200_POOL_LOG2 /
+                                 PYKMER_B200_OVF_LOG2 shrink the window, the k-mer buffer and the
+                                 carry table, PYKMER_B200_FLUSH = l2 | byte | smem forces the
+                                 scheme; they exist for the tests.) */
 
 #define PK_MODE_SCAN      3   /* scan + bucket only (no table): the scanning half of the
                                  sequence-sharded multi-GPU path, see pk_indexer_export_segments */
@@ -169,6 +173,8 @@ int pk_indexer_set_profiling(pk_indexer *ix, int enable);
 int pk_indexer_profile(pk_indexer *ix, double ms_host[8], uint32_t launches_host[8]);
 /* the counting scheme PK_MODE_AUTO resolved to, and its number of table windows */
 int pk_indexer_mode(pk_indexer *ix, int *mode, int *windows);
+/* log2 of the table entries per window (0 in DIRECT mode); every handle of one K agrees on it */
+int pk_indexer_window_log2(pk_indexer *ix, int *window_log2);
 
 /* Header.update_stats (tools.py:246-263) over any device table.
  * stats_host = {vals_sum, vals_count, vals_min, vals_max}.  Synchronises `stream`. */

@@ -22,7 +22,7 @@ SYMBOLS = (
     "pk_indexer_feed_device", "pk_indexer_feed_host", "pk_indexer_sync", "pk_indexer_finalize",
     "pk_indexer_finalize_to_host",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
-    "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_set_profiling", "pk_indexer_profile",
+    "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_window_log2", "pk_indexer_set_profiling", "pk_indexer_profile",
     "pk_indexer_prime", "pk_indexer_scan_result", "pk_indexer_export_segments",
     "pk_indexer_import_segments", "pk_indexer_pool_ipc_handle", "pk_indexer_open_peer_pool",
     "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
@@ -72,6 +72,7 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_table_to_host": [vp, vp, sz, sz],
         "pk_indexer_launch_count": [vp, c.POINTER(u64)],
         "pk_indexer_mode": [vp, c.POINTER(i32), c.POINTER(i32)],
+        "pk_indexer_window_log2": [vp, c.POINTER(i32)],
         "pk_indexer_set_profiling": [vp, i32],
         "pk_indexer_profile": [vp, vp, vp],
         "pk_indexer_prime": [vp, vp, sz, u64, vp],

@@ -47,6 +47,10 @@ constexpr int kMaxBuckets = 16384;          // windows per handle in PARTITION /
 constexpr int kMaxSegments = 128;           // feeds buffered between two flushes
 constexpr size_t kMaxFeed = 1u << 30;       // bases per partition pass (one segment each)
 constexpr int kTileEntries = kScanWarps * 31 * 16;   // most entries one block tile can emit
+// a buffered k-mer entry: (run length - 1) << 28 | offset inside the window.  A run never
+// exceeds the 16 windows of one group (pk_scan_group), windows never exceed 2^26 entries.
+constexpr uint32_t kEntShift = 28;
+constexpr uint32_t kEntMask = (1u << kEntShift) - 1u;
 
 struct ScanParams {
     const uint8_t *seq;       // this feed (16-byte aligned)
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restri
 
 // pass 2: the same scan again; entries are ranked per window in shared memory, staged
 // window by window, and written out as contiguous runs into the segments pass 1 sized.
-// entry = (run length - 1) << 24 | offset inside the window.
+// entry = (run length - 1) << kEntShift | offset inside the window.
 template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(const ScanParams p) {
     extern __shared__ uint32_t sm[];
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
                     [&](int slot, auto off, uint32_t cnt) {
                         const uint32_t b = (uint32_t)(off >> wl);
                         const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
-                        ent[slot] = ((uint32_t)off & wmask) | ((cnt - 1u) << 24);
+                        ent[slot] = ((uint32_t)off & wmask) | ((cnt - 1u) << kEntShift);
                         key[slot] = (b << 16) | rank;
                     });
         }
@@ -346,8 +350,8 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
 // address), the SMs idle: so a warp first merges its equal addresses (microsatellites put
 // the same two or three k-mers into every lane) and issues one red.add per distinct one.
 __device__ __forceinline__ void window_add(uint32_t *scratch, uint32_t e, bool live, uint32_t lane) {
-    const uint32_t addr = live ? (e & 0xFFFFFFu) : (0x80000000u | lane);   // dead lanes: unique
-    uint32_t val = live ? (e >> 24) + 1u : 0u;
+    const uint32_t addr = live ? (e & kEntMask) : (0x80000000u | lane);    // dead lanes: unique
+    uint32_t val = live ? (e >> kEntShift) + 1u : 0u;
     // cheap screen first (MATCH.ANY is slow): short-period repeats show up as an equal
     // address one, two or three lanes away
     const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, addr, 1), a2 = __shfl_up_sync(0xFFFFFFFFu, addr, 2),
@@ -487,6 +491,236 @@ __global__ void __launch_bounds__(256) k_reduce_bins(const unsigned long long *_
     bins[threadIdx.x] = s;
 }
 
+// ------------------------------------------------------------------------------ byte windows
+// Sparse tables (K >= 17: a few k-mers per hundred entries) pay for the 32-bit counters twice:
+// a window covers only 2^24 entries, and every commit reads 4 bytes to write one.  Here the
+// L2-resident window holds the table's own 8-bit lanes, four to a word, so 64 MiB of L2 cover
+// 2^26 entries and the commit is a plain copy.  atomicAdd(word, cnt << 8*lane) is not
+// saturating, so the add RETURNS the old word (ATOMG, measured 128 G/s against 190 G/s for
+// RED): the thread whose add carried out of a lane sees it, and books the exact correction
+//     true(lane) = physical(lane) + 256 * carries_out(lane) - carries_in(lane)
+// as +256 / -1 deltas in a small hash table keyed by lane.  The last block to finish a
+// window's count applies the deltas -- lane = min(255, true) -- before the commit reads it.
+// Carries are rare (a k-mer must pass 255 inside one window); if the hash table ever fills
+// up, the last block recounts the whole window with the exact compare-and-swap rule.
+struct OvfTable {
+    uint32_t *keys;                 // [cap] lane index inside the window, 0xFFFFFFFF = empty
+    unsigned long long *vals;       // [cap] signed delta (two's complement)
+    uint32_t *list;                 // [cap] occupied slots in insertion order
+    uint32_t *meta;                 // [0] occupied slots, [1] finished blocks, [2] table overflowed
+    uint32_t mask;                  // cap - 1
+};
+
+__device__ __forceinline__ void ovf_add(const OvfTable &t, uint32_t lane_idx, long long delta) {
+    uint32_t h = (lane_idx * 0x9E3779B1u) >> 7;
+    for (uint32_t probe = 0; probe <= t.mask; probe++, h++) {
+        const uint32_t slot = h & t.mask;
+        uint32_t k = __ldcg(t.keys + slot);
+        if (k == 0xFFFFFFFFu) {
+            k = atomicCAS(t.keys + slot, 0xFFFFFFFFu, lane_idx);
+            if (k == 0xFFFFFFFFu) {
+                t.list[atomicAdd(t.meta, 1u)] = slot;
+                k = lane_idx;
+            }
+        }
+        if (k == lane_idx) {
+            atomicAdd(t.vals + slot, (unsigned long long)delta);
+            return;
+        }
+    }
+    atomicExch(t.meta + 2, 1u);                           // full: the window is recounted exactly
+}
+
+// the add `val << 8*(lane_idx & 3)` onto `old` carried out of its lane: book every carry of the ripple
+__device__ __noinline__ void ovf_book(const OvfTable &t, uint32_t old, uint32_t lane_idx, uint32_t val) {
+    const uint32_t first = lane_idx & 3u, base = lane_idx & ~3u;
+    uint32_t carry = 0;
+    for (uint32_t j = first; j < 4; j++) {
+        const uint32_t s = ((old >> (8 * j)) & 0xFFu) + (j == first ? val : 0u) + carry;
+        carry = s >> 8;
+        if (!carry) break;
+        ovf_add(t, base + j, 256);
+        if (j < 3) ovf_add(t, base + j + 1, -1);          // a carry out of lane 3 leaves the word
+    }
+}
+
+__device__ __forceinline__ void lane_add(uint32_t *scratch, uint32_t lane_idx, uint32_t val, const OvfTable &t) {
+    const uint32_t sh = 8u * (lane_idx & 3u);
+    const uint32_t old = atomicAdd(scratch + (lane_idx >> 2), val << sh);
+    if (((old >> sh) & 0xFFu) + val > 255u) ovf_book(t, old, lane_idx, val);
+}
+
+// same duplicate merging as window_add; a merged count beyond 255 saturates the lane anyway
+__device__ __forceinline__ void window_add8(uint32_t *scratch, uint32_t e, bool live, uint32_t lane,
+                                            const OvfTable &t) {
+    const uint32_t addr = live ? (e & kEntMask) : (0x80000000u | lane);
+    uint32_t val = live ? (e >> kEntShift) + 1u : 0u;
+    const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, addr, 1), a2 = __shfl_up_sync(0xFFFFFFFFu, addr, 2),
+                   a3 = __shfl_up_sync(0xFFFFFFFFu, addr, 3);
+    const bool dup = (lane >= 1 && a1 == addr) || (lane >= 2 && a2 == addr) || (lane >= 3 && a3 == addr);
+    if (__any_sync(0xFFFFFFFFu, dup)) {
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, addr);
+        if (peers != (1u << lane)) val = __reduce_add_sync(peers, val);
+        if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) lane_add(scratch, addr, min(val, 255u), t);
+    } else if (live) {
+        lane_add(scratch, addr, val, t);
+    }
+}
+
+// exact saturating add on a packed lane (the rule of sat_add_u8) for the recount
+__device__ __forceinline__ void lane_add_exact(uint32_t *scratch, uint32_t lane_idx, uint32_t val) {
+    uint32_t *wp = scratch + (lane_idx >> 2);
+    const uint32_t sh = 8u * (lane_idx & 3u);
+    uint32_t old = __ldcg(wp);
+    for (;;) {
+        const uint32_t b = (old >> sh) & 0xFFu;
+        if (b == 255u) return;
+        const uint32_t assumed = old;
+        old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (min(255u, b + val) << sh));
+        if (old == assumed) return;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_window_count8(const uint32_t *__restrict__ pool,
+                                                       const uint32_t *__restrict__ seg_off,
+                                                       const uint32_t *__restrict__ seg_cnt,
+                                                       int nseg, uint32_t nb, uint32_t b,
+                                                       uint32_t *__restrict__ scratch, size_t scratch_words,
+                                                       const OvfTable t) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t span = gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (int f = 0; f < nseg; f++) {
+        const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
+        const uint32_t *src = pool + off;
+        for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cnt; base += U * span) {
+            uint32_t e[U];
+            bool live[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = base + u * span + lane;
+                live[u] = i < cnt;
+                e[u] = live[u] ? __ldcs(src + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (base + u * span < cnt) window_add8(scratch, e[u], live[u], lane, t);
+        }
+    }
+    // the last block to get here settles the carries
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(t.meta + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t nkeys = __ldcg(t.meta), failed = __ldcg(t.meta + 2);
+    if (failed) {
+        // exact recount by this one block (slow; only when > cap lanes overflowed in one window)
+        uint4 *z = reinterpret_cast<uint4 *>(scratch);
+        for (size_t i = threadIdx.x; i < scratch_words / 4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i <= t.mask; i += blockDim.x) { t.keys[i] = 0xFFFFFFFFu; t.vals[i] = 0ull; }
+        __threadfence();
+        __syncthreads();
+        for (int f = 0; f < nseg; f++) {
+            const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const uint32_t e = __ldcs(pool + off + i);
+                lane_add_exact(scratch, e & kEntMask, (e >> kEntShift) + 1u);
+            }
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < nkeys; i += blockDim.x) {
+            const uint32_t slot = __ldcg(t.list + i);
+            const uint32_t lane_idx = __ldcg(t.keys + slot);
+            const long long delta = (long long)__ldcg(t.vals + slot);
+            const uint32_t sh = 8u * (lane_idx & 3u);
+            const long long phys = (long long)((__ldcg(scratch + (lane_idx >> 2)) >> sh) & 0xFFu);
+            long long want = phys + delta;                 // the lane's true count, >= 0
+            want = want > 255 ? 255 : want;
+            atomicAdd(scratch + (lane_idx >> 2), (uint32_t)(int32_t)(want - phys) << sh);
+            t.keys[slot] = 0xFFFFFFFFu;
+            t.vals[slot] = 0ull;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { t.meta[0] = 0; t.meta[1] = 0; t.meta[2] = 0; }
+}
+
+// per window: table = [table +sat] lanes (indexer.py:239,262), lanes back to zero, histogram of the
+// bytes written (tools.py:250).  One thread moves 16 table entries per step.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) k_window_commit8(uint32_t *__restrict__ scratch,
+                                                        uint8_t *__restrict__ table, size_t n,
+                                                        unsigned long long *__restrict__ bins) {
+    __shared__ uint32_t sh[8][256];
+    if (bins) {
+        for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5;
+    uint32_t c1 = 0, c2 = 0, c3 = 0;
+    auto tally = [&](uint32_t x) {
+        if (!bins || !x) return;
+        c1 += __popc(__vcmpeq4(x, 0x01010101u)) >> 3;
+        c2 += __popc(__vcmpeq4(x, 0x02020202u)) >> 3;
+        c3 += __popc(__vcmpeq4(x, 0x03030303u)) >> 3;
+        if (x & 0xFCFCFCFCu) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t val = (x >> (8 * b)) & 0xFFu;
+                if (val > 3u) atomicAdd(&sh[warp][val], 1u);
+            }
+        }
+    };
+    const size_t nv = n / 16;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint4 *sv = reinterpret_cast<uint4 *>(scratch);
+    uint4 *tv = reinterpret_cast<uint4 *>(table);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    constexpr int U = 4;
+    auto one = [&](size_t i, uint4 c, uint4 old) {
+        if (c.x | c.y | c.z | c.w) sv[i] = zero;            // sparse tables: mostly clean already
+        if (ACCUM) {
+            c.x = __vaddus4(c.x, old.x); c.y = __vaddus4(c.y, old.y);
+            c.z = __vaddus4(c.z, old.z); c.w = __vaddus4(c.w, old.w);
+        }
+        __stcs(tv + i, c);
+        tally(c.x); tally(c.y); tally(c.z); tally(c.w);
+    };
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < nv; i += U * stride) {
+        uint4 c[U], old[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            c[u] = __ldcg(sv + i + u * stride);
+            old[u] = ACCUM ? __ldcs(tv + i + u * stride) : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) one(i + u * stride, c[u], old[u]);
+    }
+    for (; i < nv; i += stride) one(i, __ldcg(sv + i), ACCUM ? __ldcs(tv + i) : zero);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {             // < 16 tail entries
+        uint8_t *sb = reinterpret_cast<uint8_t *>(scratch);
+        for (size_t k = nv * 16; k < n; k++) {
+            uint32_t val = sb[k];
+            sb[k] = 0;
+            if (ACCUM) val = min(255u, val + table[k]);
+            table[k] = (uint8_t)val;
+            if (bins && val) atomicAdd(&sh[0][val], 1u);
+        }
+    }
+    if (!bins) return;
+    if (c1) atomicAdd(&sh[warp][1], c1);
+    if (c2) atomicAdd(&sh[warp][2], c2);
+    if (c3) atomicAdd(&sh[warp][3], c3);
+    __syncthreads();
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += sh[k][threadIdx.x];
+    if (s && threadIdx.x) bins[(size_t)blockIdx.x * 256 + threadIdx.x] += s;
+}
 
 // ------------------------------------------------------------------------------ smem flush
 // Second level of the partition (dense tables): the entries of every 2^24 window are split
@@ -651,7 +885,7 @@ __global__ void __launch_bounds__(1024, 1) k_sub_tally(const uint32_t *__restric
     const uint32_t off = sub_off[si], m = sub_cnt[si];
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         const uint32_t e = __ldcs(pool2 + off + i);
-        atomicAdd(&cnt[e & ((1u << kSubLog2) - 1u)], (e >> 24) + 1u);
+        atomicAdd(&cnt[e & ((1u << kSubLog2) - 1u)], (e >> kEntShift) + 1u);
     }
     __syncthreads();
     const int warp = (threadIdx.x >> 5) & 7;
@@ -817,6 +1051,9 @@ struct pk_indexer {
     uint32_t *pool2 = nullptr;                 // smem flush: entries regrouped by sub-bucket
     uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
     bool flush_smem = false;                   // second-level shared-memory flush (else L2 counters)
+    bool count8 = false;                       // byte windows: the L2 window holds 8-bit lanes (k_window_count8)
+    size_t scratch_bytes = 0;
+    OvfTable ovf = {nullptr, nullptr, nullptr, nullptr, 0};
     bool sub_smem_set = false;
     cudaEvent_t committed[2] = {nullptr, nullptr};
     int nseg = 0;
@@ -871,7 +1108,7 @@ static uint32_t *seg_fill(pk_indexer *ix, int f) {
 // streaming) for the two window kernels.
 static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     if (!ix->l2_persist_bytes) return 0;
-    const size_t bytes = sizeof(uint32_t) << ix->win_log2;
+    const size_t bytes = ix->scratch_bytes;
     attr->id = cudaLaunchAttributeAccessPolicyWindow;
     attr->val.accessPolicyWindow.base_ptr = ix->scratch;
     attr->val.accessPolicyWindow.num_bytes = bytes;
@@ -909,18 +1146,29 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
             cfg.gridDim = dim3(grid);
-            PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool,
-                                       (const uint32_t *)seg_off(ix, 0), (const uint32_t *)seg_cnt(ix, 0),
-                                       ix->nseg, ix->nbuckets, b, ix->scratch));
+            const uint32_t *src = ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool;
+            if (ix->count8)
+                PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count8, src, (const uint32_t *)seg_off(ix, 0),
+                                           (const uint32_t *)seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, ix->scratch,
+                                           ix->scratch_bytes / sizeof(uint32_t), ix->ovf));
+            else
+                PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, src, (const uint32_t *)seg_off(ix, 0),
+                                           (const uint32_t *)seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, ix->scratch));
             ix->launches++;
         }
         uint8_t *tw = ix->table + (size_t)b * win;
-        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows, (n / 4 + 255) / 256));
+        const size_t per_thread = ix->count8 ? 16 : 4;       // table entries one commit thread moves per step
+        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows, (n / per_thread + 255) / 256));
         {
             prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
             cfg.gridDim = dim3(cgrid);
-            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, ix->scratch, tw, n, bins));
-            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, ix->scratch, tw, n, bins));
+            if (ix->count8) {
+                if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit8<true>, ix->scratch, tw, n, bins));
+                else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit8<false>, ix->scratch, tw, n, bins));
+            } else {
+                if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, ix->scratch, tw, n, bins));
+                else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, ix->scratch, tw, n, bins));
+            }
         }
         ix->launches++;
         if (table_host) {                                   // ship this window while the next is counted
@@ -1194,10 +1442,21 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
 
     // window size: 2^24 counters (64 MiB of u32) stay L2-resident on B200; the
     // environment override exists so that tests can force many windows on small tables
-    uint32_t win_log2 = 24;
+    // how a window is counted (PYKMER_B200_FLUSH = l2 | byte | smem):
+    //   l2    32-bit counters kept in L2 (default for K <= 15)
+    //   byte  the window holds the table's own 8-bit lanes, 2^26 entries per window (default for
+    //         K >= 17, where a window sees few k-mers and the per-window passes dominate).  The
+    //         rule depends on K alone so that every handle of a multi-GPU job picks the same windows.
+    //   smem  second-level split + shared-memory counters.  Measured on config 2
+    //         (profiles/r01_ncu_sub_kernels.txt): L2 flush 6.5 ms, smem flush 13.8 ms; kept as the
+    //         second, independent implementation the tests cross-check.
+    const char *fe = getenv("PYKMER_B200_FLUSH");
+    ix->flush_smem = fe && strcmp(fe, "smem") == 0;
+    ix->count8 = fe ? strcmp(fe, "byte") == 0 : kmer_len >= 17;
+    uint32_t win_log2 = ix->count8 ? 26 : 24;
     if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
         const int v = atoi(env);
-        if (v >= 4 && v <= 24) win_log2 = (uint32_t)v;
+        if (v >= 4 && v <= (ix->count8 ? 26 : 24)) win_log2 = (uint32_t)v;
     }
     const uint64_t nb = (ix->table_bytes + ((1ull << win_log2) - 1)) >> win_log2;
     if (mode == PK_MODE_AUTO)
@@ -1242,20 +1501,32 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
         if (mode == PK_MODE_PARTITION) {
-            // how a window is counted: 32-bit counters kept in L2 (default), or a second-level
-            // split + shared-memory counters (PYKMER_B200_FLUSH=smem).  Measured on config 2
-            // (profiles/r01_ncu_sub_kernels.txt): L2 flush 6.5 ms, smem flush 13.8 ms -- its three
-            // extra passes over the 3.1 GB of entries are latency bound as written (scalar entry
-            // loads, one tile in flight per CTA); kept as the second, independent implementation
-            // the tests cross-check, and as the starting point for the next round.
-            const char *fe = getenv("PYKMER_B200_FLUSH");
-            ix->flush_smem = fe && strcmp(fe, "smem") == 0;
             step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
             if (ix->flush_smem) {
                 step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
                 step(cudaMalloc(&ix->sub, (size_t)3 * 64 * kSubs * sizeof(uint32_t)));
             } else {
-                step(cudaMalloc(&ix->scratch, sizeof(uint32_t) << win_log2));
+                ix->scratch_bytes = ix->count8 ? std::max<size_t>((size_t)1 << win_log2, 16)
+                                               : sizeof(uint32_t) << win_log2;
+                step(cudaMalloc(&ix->scratch, ix->scratch_bytes));
+            }
+            if (ix->count8) {
+                uint32_t ovf_log2 = 16;
+                if (const char *env = getenv("PYKMER_B200_OVF_LOG2")) {
+                    const int v = atoi(env);
+                    if (v >= 1 && v <= 22) ovf_log2 = (uint32_t)v;
+                }
+                const size_t oc = (size_t)1 << ovf_log2;
+                ix->ovf.mask = (uint32_t)oc - 1u;
+                step(cudaMalloc(&ix->ovf.keys, oc * sizeof(uint32_t)));
+                step(cudaMalloc(&ix->ovf.vals, oc * sizeof(unsigned long long)));
+                step(cudaMalloc(&ix->ovf.list, oc * sizeof(uint32_t)));
+                step(cudaMalloc(&ix->ovf.meta, 256));
+                if (e == cudaSuccess) {
+                    step(cudaMemsetAsync(ix->ovf.keys, 0xFF, oc * sizeof(uint32_t), ix->work_stream));
+                    step(cudaMemsetAsync(ix->ovf.vals, 0, oc * sizeof(unsigned long long), ix->work_stream));
+                    step(cudaMemsetAsync(ix->ovf.meta, 0, 256, ix->work_stream));
+                }
             }
         }
         for (int i = 0; i < 2; i++)
@@ -1266,7 +1537,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            const size_t want = sizeof(uint32_t) << win_log2;
+            const size_t want = ix->scratch_bytes;
             size_t grant = std::min<size_t>(want, (size_t)std::max(max_persist, 0));
             if (grant && (size_t)max_window >= want &&
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess)
@@ -1281,7 +1552,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
             step(cudaMemsetAsync(ix->seg, 0, seg_bytes, ix->work_stream));
             step(cudaMemsetAsync(ix->cursor, 0, 256, ix->work_stream));
             if (ix->scratch)
-                step(cudaMemsetAsync(ix->scratch, 0, sizeof(uint32_t) << win_log2, ix->work_stream));
+                step(cudaMemsetAsync(ix->scratch, 0, ix->scratch_bytes, ix->work_stream));
         }
     }
     if (e == cudaSuccess) {
@@ -1312,6 +1583,7 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part); cudaFree(ix->route); cudaFree(ix->pool2); cudaFree(ix->sub);
+    cudaFree(ix->ovf.keys); cudaFree(ix->ovf.vals); cudaFree(ix->ovf.list); cudaFree(ix->ovf.meta);
     if (ix->l2_persist_bytes) cudaCtxResetPersistingL2Cache();   // give the carve-out's lines back
     for (int i = 0; i < 16; i++)
         if (ix->peer_ipc[i]) cudaIpcCloseMemHandle(ix->peer_ipc[i]);
@@ -1767,6 +2039,12 @@ PK_API int pk_indexer_mode(pk_indexer *ix, int *mode, int *windows) {
     PK_REQUIRE(ix != nullptr, "pk_indexer_mode: NULL handle");
     if (mode) *mode = ix->mode;
     if (windows) *windows = ix->mode != PK_MODE_DIRECT ? (int)ix->nbuckets : 0;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_window_log2(pk_indexer *ix, int *window_log2) {
+    PK_REQUIRE(ix != nullptr && window_log2 != nullptr, "pk_indexer_window_log2: NULL argument");
+    *window_log2 = ix->mode != PK_MODE_DIRECT ? (int)ix->win_log2 : 0;
     return PK_OK;
 }
 

@@ -156,6 +156,12 @@ class Indexer:
         nat.check(lib.pk_indexer_mode(self._h, ctypes.byref(m), ctypes.byref(w)))
         return m.value, w.value
 
+    def window_log2(self) -> int:
+        """log2 of the table entries per counting window (0 in DIRECT mode)."""
+        v = ctypes.c_int(0)
+        nat.check(lib.pk_indexer_window_log2(self._h, ctypes.byref(v)))
+        return v.value
+
     # ---- sequence-sharded multi-GPU (see include/pykmer_b200.h) ------------------------------
     def prime(self, halo: Optional[torch.Tensor], stream_off: int, stream=None) -> None:
         """Begin a slice in mid-stream: `halo` = the <= 32 bytes preceding it (CUDA uint8)."""

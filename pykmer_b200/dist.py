@@ -18,7 +18,6 @@ import torch
 import torch.distributed as dist
 
 ALIGN = 4096          # shard boundaries are multiples of this many table entries
-WINDOW = 1 << 24      # table window of the PARTITION counting scheme (include/pykmer_b200.h)
 
 
 def world() -> Tuple[int, int]:

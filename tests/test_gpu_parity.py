@@ -27,13 +27,13 @@ def env():
 
 
 def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0,
-                  window_log2=None, pool_log2=None, flush=None):
+                  window_log2=None, pool_log2=None, flush=None, ovf_log2=None):
     import torch
     hi = 4 ** K if hi is None else hi
     # test hooks of the library: small table windows / small k-mer buffer / flush scheme
     # (read at create time)
     for name, val in (("PYKMER_B200_WINDOW_LOG2", window_log2), ("PYKMER_B200_POOL_LOG2", pool_log2),
-                      ("PYKMER_B200_FLUSH", flush)):
+                      ("PYKMER_B200_FLUSH", flush), ("PYKMER_B200_OVF_LOG2", ovf_log2)):
         if val is None:
             os.environ.pop(name, None)
         else:
@@ -44,6 +44,7 @@ def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=
         os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
         os.environ.pop("PYKMER_B200_POOL_LOG2", None)
         os.environ.pop("PYKMER_B200_FLUSH", None)
+        os.environ.pop("PYKMER_B200_OVF_LOG2", None)
     with ix:
         if starts is not None:
             ix.set_records(starts)
@@ -425,7 +426,7 @@ PART = 2   # PK_MODE_PARTITION
 @pytest.mark.parametrize("K,wlog", [(5, 4), (5, 24), (9, 6), (9, 10), (11, 10), (11, 16), (13, 14), (13, 24)])
 @pytest.mark.parametrize("n", [0, 17, 4000, 100_003, 1_000_003])
 @pytest.mark.parametrize("plog", [12, 30])
-@pytest.mark.parametrize("flush", ["smem", "l2"])
+@pytest.mark.parametrize("flush", ["smem", "l2", "byte"])
 def test_partition_mode_random_streams_vs_oracle(env, K, wlog, n, plog, flush):
     """Window-partitioned counting (many windows, and a tiny k-mer buffer that forces
     repeated saturating flushes) gives the oracle's table, statistics and num_kmers."""
@@ -450,7 +451,8 @@ def test_partition_mode_matches_reference_golden(env, case):
     gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
     stream, names, starts, lengths = fasta.read_fasta_stream(os.path.join(GOLD, "inputs", fname))
     wlog = 4 if K <= 7 else 12
-    for pieces, flush in ((None, "smem"), ([7, 100, 101, 5000], "smem"), ([7, 100, 101, 5000], "l2")):
+    for pieces, flush in ((None, "smem"), ([7, 100, 101, 5000], "smem"), ([7, 100, 101, 5000], "l2"),
+                          (None, "byte"), ([7, 100, 101, 5000], "byte")):
         pieces = [c for c in (pieces or []) if c < len(stream)] or None
         table, hist, st, flags = _index_stream(env["dev"], stream, K, starts=starts, mode=PART,
                                                window_log2=wlog, pieces=pieces, flush=flush)
@@ -474,6 +476,45 @@ def test_partition_mode_wide_k_range(env, K):
         table, hist, st, _ = _index_stream(env["dev"], s, K, hi=hi, mode=PART, window_log2=12, host=host,
                                            pieces=[1000, 1001, 20_000])
         assert st["num_kmers"] == num and np.array_equal(table, want)
+
+
+def _repeat_heavy_stream(rng, n_motifs, copies, spacer=True):
+    """Many k-mers far beyond 255 occurrences: homopolymers, (AT)n, (AAT)n and random motifs
+    repeated `copies` times -- what makes the 8-bit lanes of the byte windows carry."""
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    parts = [np.full(3000, ord("A"), dtype=np.uint8), np.frombuffer(b"N", dtype=np.uint8),
+             np.tile(np.frombuffer(b"AT", dtype=np.uint8), 1200), np.frombuffer(b"N", dtype=np.uint8),
+             np.tile(np.frombuffer(b"AAT", dtype=np.uint8), 900), np.frombuffer(b"N", dtype=np.uint8),
+             np.full(700, ord("c"), dtype=np.uint8)]
+    motifs = [acgt[rng.integers(0, 4, size=int(rng.integers(20, 60)))] for _ in range(n_motifs)]
+    order = rng.integers(0, n_motifs, size=n_motifs * copies)
+    for m in order:
+        parts.append(motifs[m])
+        if spacer and rng.random() < 0.3:
+            parts.append(acgt[rng.integers(0, 4, size=int(rng.integers(1, 9)))])
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("K,wlog", [(7, 8), (9, 18), (11, 12), (13, 26), (17, 26)])
+@pytest.mark.parametrize("ovf_log2", [None, 10, 3, 1])
+@pytest.mark.parametrize("pieces", [None, [5000, 90_001]])
+def test_byte_windows_settle_carries_exactly(env, K, wlog, ovf_log2, pieces):
+    """Byte windows (PYKMER_B200_FLUSH=byte): 8-bit lanes that carry into their neighbours are
+    corrected exactly -- through the carry table, and through the compare-and-swap recount when the
+    table is too small (ovf_log2 1 and 3) -- also across several saturating flushes."""
+    rng = np.random.default_rng(1000 + K)
+    s = _repeat_heavy_stream(rng, 40, 400)
+    hi = None if K <= 13 else 1 << 28
+    want, num, _ = env["oracle"].index_stream(s, K, range_hi=hi) if hi else env["oracle"].index_stream(s, K)
+    assert (want == 255).sum() > 20                    # the case really saturates many lanes
+    table, hist, st, _ = _index_stream(env["dev"], s, K, hi=hi, mode=PART, window_log2=wlog, flush="byte",
+                                       ovf_log2=ovf_log2, pieces=pieces, pool_log2=18 if pieces else None)
+    assert st["num_kmers"] == num
+    assert np.array_equal(table, want)
+    oh, ost = env["oracle"].table_stats(want)
+    assert hist == oh and all(st[k] == ost[k] for k in ("vals_sum", "vals_count", "vals_min", "vals_max"))
+    ref, _, st2, _ = _index_stream(env["dev"], s, K, hi=hi, mode=PART, window_log2=min(wlog, 24), flush="l2")
+    assert np.array_equal(ref, table) and st2 == st
 
 
 def test_partition_mode_feed_after_finalize_and_reset(env):
