@@ -409,6 +409,26 @@ def run_indexer(args, rank, local_rank, world):
     if args.emulate_shard:
         er, en = (int(x) for x in args.emulate_shard.split("/"))
         lo, hi = pdist.shard_range(T, er, en)
+    plan = None
+    if world > 1 and K >= 19 and args.mode == 0:
+        # very sparse tables count DIRECT: balance the shards on where the k-mers really fall.
+        # One planning pass (each rank buckets 1/N of the stream per 2^26-entry window, the counts
+        # are all-gathered), done once per genome and outside the timed steps like handle creation.
+        from pykmer_b200 import _native as nat
+        t0 = time.perf_counter()
+        a, b = pdist.slice_bounds(stream.size, rank, world)
+        scanner = dev.Indexer(K, device=local_rank, mode=nat.PK_MODE_SCAN)
+        d_halo = torch.from_numpy(np.ascontiguousarray(stream[max(0, a - 32):a])).cuda() if a > 0 else None
+        d_part = torch.from_numpy(np.ascontiguousarray(stream[a:b])).cuda()
+        scanner.prime(d_halo, a)
+        scanner.feed_device(d_part)
+        per_window = pdist.gather_window_counts(scanner).sum(axis=(0, 1))      # synchronises
+        del d_halo, d_part
+        ranges = pdist.balanced_kmer_ranges(per_window, world, scanner.window_log2(), T)
+        scanner.close()
+        lo, hi = ranges[rank]
+        plan = {"ranges_GiB": [round((h - l) / 2 ** 30, 2) for l, h in ranges],
+                "plan_ms_untimed": round(1e3 * (time.perf_counter() - t0), 1)}
 
     d_stream = torch.from_numpy(stream).cuda()
     ix = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=args.mode)
@@ -505,7 +525,8 @@ def run_indexer(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": f"indexer K={K}, synthetic tomato-sized multi-FASTA stream "
                                    f"({L} bp, 13 records), 4^{K}-byte table",
-                       "parallelism": f"kmer-range x{world}" if world > 1 else
+                       "parallelism": (f"kmer-range x{world}" + (", shards balanced on the k-mer distribution" if plan else ""))
+                                      if world > 1 else
                                       (f"ONE shard ({args.emulate_shard}) of a k-mer-range job, development run"
                                        if args.emulate_shard else "single GPU"),
                        "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
@@ -514,6 +535,8 @@ def run_indexer(args, rank, local_rank, world):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if plan is not None:
+            line["config"]["shard_plan"] = plan
         print(json.dumps(line), flush=True)
     ix.close()
 

@@ -30,6 +30,7 @@
 //   k_update_carry             keeps the last 32 stream bytes for the next feed.
 #include <algorithm>
 #include <new>
+#include <type_traits>
 #include <vector>
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +61,7 @@ struct ScanParams {
     uint64_t lo, span;        // canonical range [lo, lo + span) owned by this handle
     uint8_t *table;           // [span]                                  (DIRECT)
     unsigned long long *num_kmers;
+    unsigned long long *bins;    // [256] histogram of the table, kept as transitions   (DIRECT)
     const uint64_t *rec_starts;
     size_t nrec;
     uint8_t *rec_flags;
@@ -98,21 +100,32 @@ __device__ __forceinline__ void load_group(const ScanParams &p, long long g, lon
     }
 }
 
-// table[idx] = min(255, table[idx] + cnt)  (indexer.py:239,262).  Counters only
-// grow, so a (possibly stale) read of 255 is final and needs no atomic at all.
-__device__ __forceinline__ void sat_add_u8(uint8_t *table, uint64_t idx, uint32_t cnt) {
-    uint32_t *wp = reinterpret_cast<uint32_t *>(table + (idx & ~3ull));
-    const uint32_t sh = (uint32_t)(idx & 3) * 8;
-    uint32_t old = __ldcg(wp);
-    for (;;) {
-        const uint32_t b = (old >> sh) & 0xFFu;
-        if (b == 255u) return;
-        const uint32_t nb = min(255u, b + cnt);
-        const uint32_t assumed = old;
-        old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (nb << sh));
-        if (old == assumed) return;
+// The histogram (tools.py:250) is kept incrementally: an atomic that returns the old value tells
+// exactly how its lane moved, so bins[old]--, bins[new]++ follows the table without ever reading
+// it back.  Per-block transitions; 0 -> 1 (most of a sparse table) stays in a register.
+struct HistTally {
+    uint32_t *sh;                   // [256] wrapping counters of the block
+    unsigned long long *g;          // global bins[256]
+    uint32_t c1;
+    __device__ __forceinline__ void move(uint32_t from, uint32_t to) {
+        if (from == 0u && to == 1u) { c1++; return; }
+        if (from == to) return;
+        if (from) atomicSub(sh + from, 1u);
+        atomicAdd(sh + to, 1u);
     }
-}
+    // all threads of the block: add the block's transitions to the global bins
+    __device__ __forceinline__ void flush() {
+        if (c1) atomicAdd(sh + 1, c1);
+        c1 = 0;
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x) {
+            const int d = (int)sh[v];
+            if (d) atomicAdd(g + v, (unsigned long long)(long long)d);
+            sh[v] = 0;
+        }
+        __syncthreads();
+    }
+};
 
 __device__ __forceinline__ long long find_record(const uint64_t *starts, size_t nrec, uint64_t pos) {
     size_t lo = 0, hi = nrec;                            // upper_bound - 1
@@ -167,28 +180,87 @@ __device__ __forceinline__ void add_num_kmers(unsigned long long *dst, unsigned 
 }
 
 // ------------------------------------------------------------------------------ DIRECT
+// A warp first queues the runs of its tile in shared memory and only then applies them, every
+// lane taking queue entries in turn: the table updates are independent memory operations in
+// flight together (four per lane) instead of a chain of DRAM round trips inside the window
+// loop, and all 32 lanes work even when a shard keeps one k-mer in eight (measured at K=19, one
+// shard of eight: 24 ms chained).  SPARSE (K > 16): the table is almost empty, so the first
+// attempt is a blind compare-and-swap against zero -- one round trip instead of load +
+// compare-and-swap.  Queue entry: (run length - 1) << 60 | offset (offsets stay below the
+// shard's span, far below 2^60).
 template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanParams p) {
     __shared__ uint8_t lut[256];
+    __shared__ uint32_t s_bins[256];
+    __shared__ unsigned long long s_q[kScanWarps][32 * 17];
+    __shared__ uint32_t s_qn[kScanWarps];
     lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
+    s_bins[threadIdx.x] = 0;
     __syncthreads();
+    HistTally ht{s_bins, p.bins, 0u};
     using WT = WarpTile<WIDE>;
+    constexpr bool SPARSE = WIDE;
+    constexpr int U = 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *q = s_q[warp];
     const long long ngroups = (long long)((p.n + 15) / 16);
     const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     unsigned long long counted = 0;
     for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles;
          tile += nwarps) {
+        if (lane == 0) s_qn[warp] = 0;
+        __syncwarp();
         WT t;
         t.load(p, tile, ngroups, lut);
-        if (!t.emits) continue;
-        const uint32_t cm = pk_scan_group<WIDE, FULL>(
-            p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
-            [&](int, uint64_t off, uint32_t cnt) { sat_add_u8(p.table, off, cnt); });
-        counted += __popc(cm);
-        flag_records(p, t.g, t.cv, cm);
+        if (t.emits) {
+            const uint32_t cm = pk_scan_group<WIDE, FULL>(
+                p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+                [&](int, auto o, uint32_t c) {
+                    q[atomicAdd(&s_qn[warp], 1u)] = ((unsigned long long)(c - 1u) << 60) | (unsigned long long)o;
+                });
+            counted += __popc(cm);
+            flag_records(p, t.g, t.cv, cm);
+        }
+        __syncwarp();
+        const uint32_t nq = s_qn[warp];
+        for (uint32_t base = 0; base < nq; base += 32 * U) {
+            unsigned long long e[U];
+            uint32_t seen[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {                 // first round: independent operations
+                const uint32_t i = base + u * 32 + lane;
+                e[u] = i < nq ? q[i] : ~0ull;
+                if (e[u] == ~0ull) continue;
+                const unsigned long long off = e[u] & ((1ull << 60) - 1ull);
+                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off & ~3ull));
+                const uint32_t c = (uint32_t)(e[u] >> 60) + 1u;
+                seen[u] = SPARSE ? atomicCAS(wp, 0u, c << (8u * ((uint32_t)off & 3u))) : __ldcg(wp);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {                 // second round: settle against what was seen
+                if (e[u] == ~0ull) continue;
+                const unsigned long long off = e[u] & ((1ull << 60) - 1ull);
+                const uint32_t c = (uint32_t)(e[u] >> 60) + 1u;
+                if (SPARSE && seen[u] == 0u) { ht.move(0u, c); continue; }
+                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off & ~3ull));
+                const uint32_t sh = 8u * ((uint32_t)off & 3u);
+                uint32_t old = seen[u];
+                for (;;) {                                // table[idx] = min(255, table[idx] + c), indexer.py:239,262;
+                                                          // counters only grow, so a read of 255 is final
+                    const uint32_t b = (old >> sh) & 0xFFu;
+                    if (b == 255u) break;
+                    const uint32_t nb = min(255u, b + c);
+                    const uint32_t assumed = old;
+                    old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (nb << sh));
+                    if (old == assumed) { ht.move(b, nb); break; }
+                }
+            }
+        }
+        __syncwarp();
     }
     add_num_kmers(p.num_kmers, counted);
+    ht.flush();                                            // histogram of the table, kept as transitions
 }
 
 // ------------------------------------------------------------------------------ PARTITION
@@ -495,14 +567,21 @@ __global__ void __launch_bounds__(256) k_reduce_bins(const unsigned long long *_
 // Sparse tables (K >= 17: a few k-mers per hundred entries) pay for the 32-bit counters twice:
 // a window covers only 2^24 entries, and every commit reads 4 bytes to write one.  Here the
 // L2-resident window holds the table's own 8-bit lanes, four to a word, so 64 MiB of L2 cover
-// 2^26 entries and the commit is a plain copy.  atomicAdd(word, cnt << 8*lane) is not
-// saturating, so the add RETURNS the old word (ATOMG, measured 128 G/s against 190 G/s for
-// RED): the thread whose add carried out of a lane sees it, and books the exact correction
+// 2^26 entries.  atomicAdd(word, cnt << 8*lane) is not saturating, so the add RETURNS the old
+// word (ATOMG, measured 128 G/s against 190 G/s for RED): the thread whose add carried out of a
+// lane sees it, and books the exact correction
 //     true(lane) = physical(lane) + 256 * carries_out(lane) - carries_in(lane)
 // as +256 / -1 deltas in a small hash table keyed by lane.  The last block to finish a
-// window's count applies the deltas -- lane = min(255, true) -- before the commit reads it.
-// Carries are rare (a k-mer must pass 255 inside one window); if the hash table ever fills
-// up, the last block recounts the whole window with the exact compare-and-swap rule.
+// window's count applies the deltas -- lane = min(255, true).  Carries are rare (a k-mer must
+// pass 255 inside one window); if the hash table ever fills up, the last block recounts the
+// whole window with the exact compare-and-swap rule.
+//
+// First flush of a table (the normal case): the window IS the table slice -- k_window_zero
+// puts it into L2 as zeros, k_window_count8<true> counts in place, and since every returned old
+// word tells exactly how each lane moved, the histogram (tools.py:250) is kept as transitions
+// old -> new (bins[old]--, bins[new]++): no commit pass, no statistics pass, the table is
+// written to DRAM once when L2 evicts it.  Later flushes onto a table that already holds
+// counts go through a zeroed scratch window and k_window_commit8<true> (saturating byte add).
 struct OvfTable {
     uint32_t *keys;                 // [cap] lane index inside the window, 0xFFFFFFFF = empty
     unsigned long long *vals;       // [cap] signed delta (two's complement)
@@ -531,28 +610,45 @@ __device__ __forceinline__ void ovf_add(const OvfTable &t, uint32_t lane_idx, lo
     atomicExch(t.meta + 2, 1u);                           // full: the window is recounted exactly
 }
 
-// the add `val << 8*(lane_idx & 3)` onto `old` carried out of its lane: book every carry of the ripple
-__device__ __noinline__ void ovf_book(const OvfTable &t, uint32_t old, uint32_t lane_idx, uint32_t val) {
+// one lane moved from `from` to `to`: histogram bookkeeping in global memory (rare paths)
+__device__ __forceinline__ void bins_move(unsigned long long *g_bins, uint32_t from, uint32_t to) {
+    if (from == to) return;
+    if (from) atomicAdd(g_bins + from, ~0ull);            // -1
+    if (to) atomicAdd(g_bins + to, 1ull);
+}
+
+// the add `val << 8*(lane_idx & 3)` onto `old` carried out of its lane: book every carry of the
+// ripple (and, with g_bins, every lane the ripple moved)
+__device__ __noinline__ void ovf_book(const OvfTable &t, uint32_t old, uint32_t lane_idx, uint32_t val,
+                                      unsigned long long *g_bins) {
     const uint32_t first = lane_idx & 3u, base = lane_idx & ~3u;
-    uint32_t carry = 0;
-    for (uint32_t j = first; j < 4; j++) {
-        const uint32_t s = ((old >> (8 * j)) & 0xFFu) + (j == first ? val : 0u) + carry;
-        carry = s >> 8;
-        if (!carry) break;
-        ovf_add(t, base + j, 256);
-        if (j < 3) ovf_add(t, base + j + 1, -1);          // a carry out of lane 3 leaves the word
+    uint32_t add = val;
+    for (uint32_t j = first; j < 4 && add; j++) {
+        const uint32_t was = (old >> (8 * j)) & 0xFFu;
+        const uint32_t s = was + add;
+        if (g_bins) bins_move(g_bins, was, s & 0xFFu);
+        add = s >> 8;                                     // carry into the next lane
+        if (add) {
+            ovf_add(t, base + j, 256);
+            if (j < 3) ovf_add(t, base + j + 1, -1);      // a carry out of lane 3 leaves the word
+        }
     }
 }
 
-__device__ __forceinline__ void lane_add(uint32_t *scratch, uint32_t lane_idx, uint32_t val, const OvfTable &t) {
+template <bool HIST>
+__device__ __forceinline__ void lane_add(uint32_t *win, uint32_t lane_idx, uint32_t val, const OvfTable &t,
+                                         HistTally &ht) {
     const uint32_t sh = 8u * (lane_idx & 3u);
-    const uint32_t old = atomicAdd(scratch + (lane_idx >> 2), val << sh);
-    if (((old >> sh) & 0xFFu) + val > 255u) ovf_book(t, old, lane_idx, val);
+    const uint32_t old = atomicAdd(win + (lane_idx >> 2), val << sh);
+    const uint32_t was = (old >> sh) & 0xFFu;
+    if (was + val > 255u) ovf_book(t, old, lane_idx, val, HIST ? ht.g : nullptr);
+    else if (HIST) ht.move(was, was + val);
 }
 
 // same duplicate merging as window_add; a merged count beyond 255 saturates the lane anyway
-__device__ __forceinline__ void window_add8(uint32_t *scratch, uint32_t e, bool live, uint32_t lane,
-                                            const OvfTable &t) {
+template <bool HIST>
+__device__ __forceinline__ void window_add8(uint32_t *win, uint32_t e, bool live, uint32_t lane,
+                                            const OvfTable &t, HistTally &ht) {
     const uint32_t addr = live ? (e & kEntMask) : (0x80000000u | lane);
     uint32_t val = live ? (e >> kEntShift) + 1u : 0u;
     const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, addr, 1), a2 = __shfl_up_sync(0xFFFFFFFFu, addr, 2),
@@ -561,32 +657,54 @@ __device__ __forceinline__ void window_add8(uint32_t *scratch, uint32_t e, bool 
     if (__any_sync(0xFFFFFFFFu, dup)) {
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, addr);
         if (peers != (1u << lane)) val = __reduce_add_sync(peers, val);
-        if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) lane_add(scratch, addr, min(val, 255u), t);
+        if (live && lane == (uint32_t)(__ffs((int)peers) - 1)) lane_add<HIST>(win, addr, min(val, 255u), t, ht);
     } else if (live) {
-        lane_add(scratch, addr, val, t);
+        lane_add<HIST>(win, addr, val, t, ht);
     }
 }
 
-// exact saturating add on a packed lane (the rule of sat_add_u8) for the recount
-__device__ __forceinline__ void lane_add_exact(uint32_t *scratch, uint32_t lane_idx, uint32_t val) {
-    uint32_t *wp = scratch + (lane_idx >> 2);
+// exact saturating add on a packed lane (compare-and-swap; a read of 255 is final) for the recount
+template <bool HIST>
+__device__ __forceinline__ void lane_add_exact(uint32_t *win, uint32_t lane_idx, uint32_t val, HistTally &ht) {
+    uint32_t *wp = win + (lane_idx >> 2);
     const uint32_t sh = 8u * (lane_idx & 3u);
     uint32_t old = __ldcg(wp);
     for (;;) {
         const uint32_t b = (old >> sh) & 0xFFu;
         if (b == 255u) return;
+        const uint32_t nb = min(255u, b + val);
         const uint32_t assumed = old;
-        old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (min(255u, b + val) << sh));
-        if (old == assumed) return;
+        old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (nb << sh));
+        if (old == assumed) {
+            if (HIST) ht.move(b, nb);
+            return;
+        }
     }
 }
 
+__global__ void __launch_bounds__(256) k_window_zero(uint4 *__restrict__ dst, size_t nvec) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) dst[i] = zero;
+}
+
+// HIST = false: `win` is the zeroed scratch window (k_window_commit8 follows).
+// HIST = true:  `win` is the zeroed table slice itself; g_bins follows every lane.
+// win_words = 32-bit words of the window (a multiple of 4; the allocation is padded).
+template <bool HIST>
 __global__ void __launch_bounds__(256) k_window_count8(const uint32_t *__restrict__ pool,
                                                        const uint32_t *__restrict__ seg_off,
                                                        const uint32_t *__restrict__ seg_cnt,
                                                        int nseg, uint32_t nb, uint32_t b,
-                                                       uint32_t *__restrict__ scratch, size_t scratch_words,
-                                                       const OvfTable t) {
+                                                       uint32_t *__restrict__ win, size_t win_words,
+                                                       const OvfTable t, unsigned long long *__restrict__ g_bins) {
+    __shared__ uint32_t s_bins[256];
+    __shared__ uint32_t s_last;
+    HistTally ht{s_bins, g_bins, 0u};
+    if (HIST) {
+        s_bins[threadIdx.x] = 0;
+        __syncthreads();
+    }
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t span = gridDim.x * blockDim.x;
     constexpr int U = 4;
@@ -604,11 +722,11 @@ __global__ void __launch_bounds__(256) k_window_count8(const uint32_t *__restric
             }
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (base + u * span < cnt) window_add8(scratch, e[u], live[u], lane, t);
+                if (base + u * span < cnt) window_add8<HIST>(win, e[u], live[u], lane, t, ht);
         }
     }
+    if (HIST) ht.flush();
     // the last block to get here settles the carries
-    __shared__ uint32_t s_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(t.meta + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
@@ -618,8 +736,22 @@ __global__ void __launch_bounds__(256) k_window_count8(const uint32_t *__restric
     const uint32_t nkeys = __ldcg(t.meta), failed = __ldcg(t.meta + 2);
     if (failed) {
         // exact recount by this one block (slow; only when > cap lanes overflowed in one window)
-        uint4 *z = reinterpret_cast<uint4 *>(scratch);
-        for (size_t i = threadIdx.x; i < scratch_words / 4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        uint4 *z = reinterpret_cast<uint4 *>(win);
+        for (size_t i = threadIdx.x; i < win_words / 4; i += blockDim.x) {
+            if (HIST) {                                   // take back what the lanes stood for
+                const uint4 q = __ldcg(z + i);
+                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (ws[k])
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t v = (ws[k] >> (8 * j)) & 0xFFu;
+                            if (v) atomicSub(s_bins + v, 1u);
+                        }
+            }
+            z[i] = make_uint4(0, 0, 0, 0);
+        }
         for (uint32_t i = threadIdx.x; i <= t.mask; i += blockDim.x) { t.keys[i] = 0xFFFFFFFFu; t.vals[i] = 0ull; }
         __threadfence();
         __syncthreads();
@@ -627,19 +759,21 @@ __global__ void __launch_bounds__(256) k_window_count8(const uint32_t *__restric
             const uint32_t off = seg_off[(size_t)f * nb + b], cnt = seg_cnt[(size_t)f * nb + b];
             for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
                 const uint32_t e = __ldcs(pool + off + i);
-                lane_add_exact(scratch, e & kEntMask, (e >> kEntShift) + 1u);
+                lane_add_exact<HIST>(win, e & kEntMask, (e >> kEntShift) + 1u, ht);
             }
         }
+        if (HIST) ht.flush();
     } else {
         for (uint32_t i = threadIdx.x; i < nkeys; i += blockDim.x) {
             const uint32_t slot = __ldcg(t.list + i);
             const uint32_t lane_idx = __ldcg(t.keys + slot);
             const long long delta = (long long)__ldcg(t.vals + slot);
             const uint32_t sh = 8u * (lane_idx & 3u);
-            const long long phys = (long long)((__ldcg(scratch + (lane_idx >> 2)) >> sh) & 0xFFu);
+            const long long phys = (long long)((__ldcg(win + (lane_idx >> 2)) >> sh) & 0xFFu);
             long long want = phys + delta;                 // the lane's true count, >= 0
             want = want > 255 ? 255 : want;
-            atomicAdd(scratch + (lane_idx >> 2), (uint32_t)(int32_t)(want - phys) << sh);
+            atomicAdd(win + (lane_idx >> 2), (uint32_t)(int32_t)(want - phys) << sh);
+            if (HIST) bins_move(g_bins, (uint32_t)phys, (uint32_t)want);
             t.keys[slot] = 0xFFFFFFFFu;
             t.vals[slot] = 0ull;
         }
@@ -1127,7 +1261,50 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
 // stream, so the device-to-host transfer of the table overlaps the rest of the flush.
 static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host);
 
+// byte windows, first flush of a table: zero the table slice into L2, count in place with the
+// histogram kept as transitions; nothing is committed and nothing is read back
+static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table_host) {
+    const size_t win = (size_t)1 << ix->win_log2;
+    PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
+    const uint32_t *src = ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool;
+    for (uint32_t b = 0; b < ix->nbuckets; b++) {
+        const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
+        const size_t nvec = (n + 15) / 16;                  // the allocation is padded to 256 bytes
+        uint8_t *tw = ix->table + (size_t)b * win;
+        {
+            prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
+            const int zgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * 4, (nvec + 255) / 256));
+            k_window_zero<<<zgrid, 256, 0, st>>>(reinterpret_cast<uint4 *>(tw), nvec);
+        }
+        ix->launches++;
+        if (ix->nseg) {
+            prof_scope ps(ix, st, PROF_WINDOW_COUNT);
+            k_window_count8<true><<<ix->sm_count * 8, 256, 0, st>>>(
+                src, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, reinterpret_cast<uint32_t *>(tw),
+                nvec * 4, ix->ovf, ix->counters + 1);
+            ix->launches++;
+        }
+        if (table_host) {                                   // ship this window while the next is counted
+            PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
+            PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
+            PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+        }
+    }
+    PK_CUDA(cudaGetLastError());
+    const int rc = indexer_flush_finish(ix, st, false, table_host);
+    ix->stats_valid = true;                                 // counters + 1 already hold the histogram
+    return rc;
+}
+
 static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
+    if (ix->count8 && !ix->table_valid) return indexer_flush_inplace(ix, st, table_host);
+    if (ix->count8 && !ix->scratch) {
+        // a later flush onto a table that already holds counts (k-mer buffer overflow, feeding after
+        // finalize): count into a zeroed scratch window, then add it in with byte saturation
+        ix->scratch_bytes = std::max<size_t>((size_t)1 << ix->win_log2, 16);
+        PK_CUDA(cudaMalloc(&ix->scratch, ix->scratch_bytes));
+        PK_CUDA(cudaMemsetAsync(ix->scratch, 0, ix->scratch_bytes, st));
+    }
     const size_t win = (size_t)1 << ix->win_log2;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg;
@@ -1148,9 +1325,10 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
             cfg.gridDim = dim3(grid);
             const uint32_t *src = ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool;
             if (ix->count8)
-                PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count8, src, (const uint32_t *)seg_off(ix, 0),
+                PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count8<false>, src, (const uint32_t *)seg_off(ix, 0),
                                            (const uint32_t *)seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, ix->scratch,
-                                           ix->scratch_bytes / sizeof(uint32_t), ix->ovf));
+                                           ix->scratch_bytes / sizeof(uint32_t), ix->ovf,
+                                           (unsigned long long *)nullptr));
             else
                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, src, (const uint32_t *)seg_off(ix, 0),
                                            (const uint32_t *)seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, ix->scratch));
@@ -1283,7 +1461,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     ScanParams p;
     memset(&p, 0, sizeof p);
     p.seq = seq_dev; p.n = n; p.carry = ix->carry; p.K = ix->K; p.lo = ix->lo; p.span = ix->hi - ix->lo;
-    p.table = ix->table; p.num_kmers = ix->counters;
+    p.table = ix->table; p.num_kmers = ix->counters; p.bins = ix->counters + 1;
     p.rec_starts = ix->rec_starts; p.nrec = ix->nrec; p.rec_flags = ix->nrec ? ix->rec_flags : nullptr;
     p.stream_off = ix->stream_off;
     const bool wide = ix->K > 16;
@@ -1459,9 +1637,12 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         if (v >= 4 && v <= (ix->count8 ? 26 : 24)) win_log2 = (uint32_t)v;
     }
     const uint64_t nb = (ix->table_bytes + ((1ull << win_log2) - 1)) >> win_log2;
+    // AUTO: tables that fit L2 and very sparse ones (K >= 19: a genome fills well under 1 % of
+    // 4^19 entries, so sweeping the table window by window costs more than one random DRAM update
+    // per k-mer) count DIRECT; everything between is PARTITIONed.
     if (mode == PK_MODE_AUTO)
-        mode = (ix->table_bytes > (1ull << 26) && nb <= (uint64_t)kMaxBuckets) ? PK_MODE_PARTITION
-                                                                              : PK_MODE_DIRECT;
+        mode = (ix->table_bytes > (1ull << 26) && kmer_len < 19 && nb <= (uint64_t)kMaxBuckets)
+                   ? PK_MODE_PARTITION : PK_MODE_DIRECT;
     if ((mode == PK_MODE_PARTITION || mode == PK_MODE_SCAN) && nb > (uint64_t)kMaxBuckets) {
         delete ix;
         return pk_set_error(PK_ERR_ARG, "pk_indexer_create: range needs %llu windows, at most %d "
@@ -1505,9 +1686,8 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
             if (ix->flush_smem) {
                 step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
                 step(cudaMalloc(&ix->sub, (size_t)3 * 64 * kSubs * sizeof(uint32_t)));
-            } else {
-                ix->scratch_bytes = ix->count8 ? std::max<size_t>((size_t)1 << win_log2, 16)
-                                               : sizeof(uint32_t) << win_log2;
+            } else if (!ix->count8) {                       // byte windows count in the table itself
+                ix->scratch_bytes = sizeof(uint32_t) << win_log2;
                 step(cudaMalloc(&ix->scratch, ix->scratch_bytes));
             }
             if (ix->count8) {
@@ -1746,15 +1926,8 @@ static int indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t sta
         const int rc = indexer_flush(ix, st, true, table_host);   // statistics fused into the commit
         if (rc != PK_OK) return rc;
         copied = table_host != nullptr;
-    } else if (ix->mode == PK_MODE_DIRECT) {
-        PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
-        {
-            prof_scope ps(ix, st, PROF_TABLE_STATS);
-            k_table_stats<<<ix->sm_count * 8, 256, 0, st>>>(ix->table, ix->table_bytes, ix->counters + 1);
-        }
-        PK_CUDA(cudaGetLastError());
-        ix->launches += 1;
     }
+    // DIRECT: counters + 1 already hold the histogram (kept as transitions by every update)
     if (table_host && !copied)
         PK_CUDA(cudaMemcpyAsync(table_host, ix->table, ix->table_bytes, cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaMemcpyAsync(ix->h_counters, ix->counters, 257 * sizeof(unsigned long long),

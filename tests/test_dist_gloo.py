@@ -139,3 +139,23 @@ def test_exchange_plan_routes_every_entry_to_its_window_owner():
                     assert got == [(s, f, w0 + wl, i) for i in range(all_cnt[s, f, w0 + wl])]
     bal = pdist.balanced_window_owners(np.array([100, 1, 1, 1, 1, 1, 1, 1]), 2, overhead=0)
     assert bal == [(0, 1), (1, 8)]
+
+
+def test_balanced_kmer_ranges_tile_the_axis_and_even_out_cost():
+    """Shards of the DIRECT (K >= 19) multi-GPU path: contiguous, window aligned, they tile
+    [0, 4^K), and with k-mers crowding the low windows no shard costs much more than the mean."""
+    from pykmer_b200 import dist as pdist
+    K, wl = 19, 26
+    T = 4 ** K
+    nwin = T >> wl
+    x = (np.arange(nwin) + 0.5) / nwin
+    per_window = (780e6 * 2 * (1 - x) / nwin).astype(np.int64)         # density of min(fwd, rc)
+    for n in (2, 4, 8):
+        ranges = pdist.balanced_kmer_ranges(per_window, n, wl, T)
+        assert ranges[0][0] == 0 and ranges[-1][1] == T
+        assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
+        assert all(lo % (1 << wl) == 0 and hi > lo for lo, hi in ranges)
+        cost = [per_window[lo >> wl:hi >> wl].sum() + 180_000 * ((hi - lo) >> wl) for lo, hi in ranges]
+        assert max(cost) < 1.05 * (sum(cost) / n)
+        equal = [per_window[nwin * r // n:nwin * (r + 1) // n].sum() for r in range(n)]
+        assert max(equal) > 1.3 * (sum(equal) / n)                       # what balancing avoids

@@ -235,7 +235,7 @@ def test_indexer_reset_and_reuse(env):
             want, num, _ = oracle.index_stream(s, 9)
             assert st["num_kmers"] == num
             assert np.array_equal(ix.table_to_host().numpy(), want)
-        assert ix.launch_count() >= 9
+        assert ix.launch_count() >= 6          # scan + carry per feed (the histogram rides along)
 
 
 def test_indexer_rejects_bad_arguments(env):
