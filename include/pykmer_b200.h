@@ -64,7 +64,7 @@ int         pk_host_free(void *ptr);
  * windows whose canonical value falls outside are ignored.  range 0..4^K is the
  * whole .kin; a sub-range is one shard of the k-mer-axis partition.
  */
-#define PK_MODE_AUTO      0   /* PARTITION for tables beyond 64 Mi entries and K <= 17, else DIRECT */
+#define PK_MODE_AUTO      0   /* PARTITION for 11 <= K <= 17, else DIRECT */
 #define PK_MODE_DIRECT    1   /* saturating byte compare-and-swap straight into the table */
 #define PK_MODE_PARTITION 2   /* bucket k-mers by table window, count each window in L2 and write
                                  it once: 2^24-entry windows with 32-bit counters for K <= 15,

@@ -21,6 +21,7 @@
 // columns); 64 uses M=64 MMAs (half the A-operand traffic from shared memory, which is what
 // bounds that small tile).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -129,7 +130,7 @@ struct GramCfg {
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kPad + 256 + 1024;
 };
 
-template <int NP>
+template <int NP, int AHEAD>
 __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint32_t *__restrict__ bits, int nsamples,
                                                           size_t words, size_t stride_words,
                                                           unsigned long long *__restrict__ gram) {
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
         constexpr int kGroups = C::kGroups;
         constexpr int kGroupThreads = kProducerThreads / kGroups;
         constexpr int kRowsPerThread = NP / kGroupThreads;
-        constexpr int kAhead = 2;                  // stages of global loads in flight per group
+        constexpr int kAhead = AHEAD;              // stages of global loads in flight per group
         const int group = threadIdx.x / kGroupThreads, tg = threadIdx.x % kGroupThreads;
         const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
         uint32_t wv[kAhead][kRowsPerThread][kKB];
@@ -315,19 +316,19 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
     }
 }
 
-template <int NP>
+template <int NP, int AHEAD>
 int launch_gram_i8(const uint32_t *bits, int nsamples, size_t words, size_t stride_words,
                    unsigned long long *gram, int device, cudaStream_t st) {
     using C = GramCfg<NP>;
     constexpr int kKB = C::kKB;
-    PK_CUDA(cudaFuncSetAttribute(k_gram_i8<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    PK_CUDA(cudaFuncSetAttribute(k_gram_i8<NP, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const size_t total_stages = (words + kKB - 1) / kKB;
     // a CTA's s32 accumulators must stay below 2^31: at most 2^31 / 32 words each
     const size_t min_ctas = (words + ((1ull << 25) - 1)) >> 25;
     size_t grid = (size_t)pk_sm_count(device);
     grid = std::max(grid, min_ctas);
     grid = std::max<size_t>(1, std::min(grid, total_stages));
-    k_gram_i8<NP><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
+    k_gram_i8<NP, AHEAD><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -338,8 +339,23 @@ int launch_gram_i8(const uint32_t *bits, int nsamples, size_t words, size_t stri
 int pk_gram_i8_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
                       int64_t *gram_dev, int device, cudaStream_t st) {
     unsigned long long *g = reinterpret_cast<unsigned long long *>(gram_dev);
-    if (nsamples <= 64) return launch_gram_i8<64>(bits_dev, nsamples, words, stride_words, g, device, st);
-    if (nsamples <= 128) return launch_gram_i8<128>(bits_dev, nsamples, words, stride_words, g, device, st);
-    if (nsamples <= 256) return launch_gram_i8<256>(bits_dev, nsamples, words, stride_words, g, device, st);
+    // stages of bitmask loads a producer keeps in flight.  Measured (N=50: 6.60 / 6.54 / 6.49 ms at
+    // 2 / 4 / 6, N=100: 12.0 / 13.3 / 13.6 ms, N=255: 34.5 / 36.6 ms at 2 / 3): the producers are not
+    // load-latency bound (at 64 rows shared-memory bandwidth is: 2 KB stored + 4 KB read per MMA).
+    int ahead = 0;
+    if (const char *env = getenv("PYKMER_B200_GRAM_AHEAD")) ahead = atoi(env);
+    if (nsamples <= 64) {
+        if (ahead == 2) return launch_gram_i8<64, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
+        if (ahead == 4) return launch_gram_i8<64, 4>(bits_dev, nsamples, words, stride_words, g, device, st);
+        return launch_gram_i8<64, 6>(bits_dev, nsamples, words, stride_words, g, device, st);
+    }
+    if (nsamples <= 128) {
+        if (ahead == 4) return launch_gram_i8<128, 4>(bits_dev, nsamples, words, stride_words, g, device, st);
+        return launch_gram_i8<128, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
+    }
+    if (nsamples <= 256) {
+        if (ahead == 3) return launch_gram_i8<256, 3>(bits_dev, nsamples, words, stride_words, g, device, st);
+        return launch_gram_i8<256, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
+    }
     return pk_set_error(PK_ERR_ARG, "pk_gram_i8_launch: %d samples exceed one tensor-core tile (256)", nsamples);
 }

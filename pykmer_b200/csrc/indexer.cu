@@ -1637,11 +1637,13 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         if (v >= 4 && v <= (ix->count8 ? 26 : 24)) win_log2 = (uint32_t)v;
     }
     const uint64_t nb = (ix->table_bytes + ((1ull << win_log2) - 1)) >> win_log2;
-    // AUTO: tables that fit L2 and very sparse ones (K >= 19: a genome fills well under 1 % of
+    // AUTO: tiny tables (K <= 9) and very sparse ones (K >= 19: a genome fills well under 1 % of
     // 4^19 entries, so sweeping the table window by window costs more than one random DRAM update
-    // per k-mer) count DIRECT; everything between is PARTITIONed.
+    // per k-mer) count DIRECT; everything between is PARTITIONed -- also K = 11 and 13, whose
+    // tables would fit L2: their k-mers repeat so often that compare-and-swap keeps colliding
+    // (measured on the 782 Mbp stream: K=11 26.0 ms DIRECT / 10.6 ms PARTITION, K=13 27.9 / 9.5).
     if (mode == PK_MODE_AUTO)
-        mode = (ix->table_bytes > (1ull << 26) && kmer_len < 19 && nb <= (uint64_t)kMaxBuckets)
+        mode = (ix->table_bytes >= (1ull << 22) && kmer_len < 19 && nb <= (uint64_t)kMaxBuckets)
                    ? PK_MODE_PARTITION : PK_MODE_DIRECT;
     if ((mode == PK_MODE_PARTITION || mode == PK_MODE_SCAN) && nb > (uint64_t)kMaxBuckets) {
         delete ix;

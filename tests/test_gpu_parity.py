@@ -549,9 +549,17 @@ def test_partition_mode_feed_after_finalize_and_reset(env):
 
 
 def test_auto_mode_picks_partition_for_k15(env):
+    """AUTO: DIRECT for tiny (K <= 9) and very sparse (K >= 19) tables, PARTITION between --
+    2^24-entry windows of 32-bit counters up to K=15, 2^26-entry byte windows at K=17."""
     with env["dev"].Indexer(15) as ix:
-        assert ix.mode() == (PART, 64)
+        assert ix.mode() == (PART, 64) and ix.window_log2() == 24
     with env["dev"].Indexer(11) as ix:
+        assert ix.mode() == (PART, 1)
+    with env["dev"].Indexer(9) as ix:
+        assert ix.mode()[0] == 1 and ix.window_log2() == 0
+    with env["dev"].Indexer(17, range_hi=1 << 30) as ix:
+        assert ix.mode() == (PART, 16) and ix.window_log2() == 26
+    with env["dev"].Indexer(19, range_hi=1 << 30) as ix:
         assert ix.mode()[0] == 1
 
 
