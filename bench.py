@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--shard", default="auto", choices=["auto", "sequence", "kmer"],
                     help="N > 1 indexer: 'sequence' = each rank scans 1/N of the stream and the k-mer entries "
                          "are exchanged all-to-all; 'kmer' = every rank scans everything, keeps its k-mer range")
-    ap.add_argument("--emulate-shard", default=None, metavar="R/N",
+    ap.add_argument("--emulate-shard", default=None, metavar="R/N | LO:HI",
                     help="development aid: on ONE GPU, run the k-mer-range shard that rank R of N would own "
                          "(not a bench line: one rank's share of a multi-GPU job)")
     ap.add_argument("--cpu-sample-mbp", type=float, default=128.0)
@@ -407,8 +407,11 @@ def run_indexer(args, rank, local_rank, world):
     from pykmer_b200 import dist as pdist
     lo, hi = pdist.shard_range(T, rank, world)               # k-mer-axis shard of this rank
     if args.emulate_shard:
-        er, en = (int(x) for x in args.emulate_shard.split("/"))
-        lo, hi = pdist.shard_range(T, er, en)
+        if ":" in args.emulate_shard:                        # "lo:hi" in GiB of the k-mer axis
+            lo, hi = (int(float(x) * 2 ** 30) for x in args.emulate_shard.split(":"))
+        else:
+            er, en = (int(x) for x in args.emulate_shard.split("/"))
+            lo, hi = pdist.shard_range(T, er, en)
     plan = None
     if world > 1 and K >= 19 and args.mode == 0:
         # very sparse tables count DIRECT: balance the shards on where the k-mers really fall.
@@ -464,6 +467,15 @@ def run_indexer(args, rank, local_rank, world):
     mode, windows = ix.mode()
     n_k_local = st_l["num_kmers"]
     table_bytes = hi - lo
+    per_rank = None
+    if world > 1:
+        # every rank's share, for reading the max-over-ranks step time
+        mine = torch.tensor([table_bytes / 2 ** 30, n_k_local / 1e6, sum(v[0] for v in prof.values())],
+                            dtype=torch.float64, device="cuda")
+        every = torch.empty((world, 3), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(every.view(-1), mine)
+        per_rank = [{"table_GiB": round(a, 2), "num_kmers_M": round(b, 1), "kernel_ms": round(c, 3)}
+                    for a, b, c in every.cpu().tolist()]
     big = table_bytes > 126e6
     # algorithmic bytes (SURVEY 8d / DESIGN.md): 1 B per base scanned, 64 B per counted k-mer
     # when the table exceeds L2 (one 32 B sector fetched + written back), 2 B per table entry
@@ -537,6 +549,8 @@ def run_indexer(args, rank, local_rank, world):
             line["cpu_baseline"] = cpu
         if plan is not None:
             line["config"]["shard_plan"] = plan
+        if per_rank is not None:
+            line["config"]["per_rank"] = per_rank
         print(json.dumps(line), flush=True)
     ix.close()
 
@@ -652,10 +666,12 @@ def run_merger(args, rank, local_rank, world):
             peak_t = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) \
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 2.0 * 1590.0
             ach = ops / (ms_step * 1e-3) / 1e12
+            peak_t *= world                                   # whole-job rate against the whole job's pipes
             roof = {"bound": "tensor", "kernel": "k_gram_i8", "achieved": ach, "peak": peak_t,
                     "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": None,
-                    "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json); int8 ops, nominal dense 4500",
-                    "hbm_GBps": value, "hbm_frac": value / hbm_peak}
+                    "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json)" + (f" x {world} GPUs" if world > 1 else "")
+                                   + "; int8 ops, nominal dense 4500 per GPU",
+                    "hbm_GBps": value, "hbm_frac": value / (hbm_peak * world)}
         else:
             popc = N * (N + 1) / 2 * T / 32
             roof = {"bound": "hbm", "kernel": "k_gram_popc", "achieved": value, "peak": hbm_peak,

@@ -71,6 +71,15 @@ struct ScanParams {
     uint32_t *seg_cnt;        // [nbuckets] entries of this feed per window (pass 1 out)
     const uint32_t *seg_off;  // [nbuckets] pool index of each segment      (pass 2 in)
     uint32_t *seg_fill;       // [nbuckets] fill cursors                    (pass 2)
+    // estimated pass 1 (see indexer_launch_scan): pass 1 looks at one tile in 2^sample_shift and
+    // does no bookkeeping; pass 2 checks its reservations against seg_cap, counts num_kmers into
+    // ctl and flags the records.  Kernels given run_if return at once when *run_if == 0.
+    uint32_t sample_shift;
+    uint32_t pass1_tally;     // pass 1 adds to num_kmers and flags records (the exact pass)
+    uint32_t pass2_tally;     // pass 2 does (the estimated pass)
+    const uint32_t *seg_cap;  // [nbuckets] room reserved per window, NULL = exact sizes
+    uint32_t *ctl;            // [0] pool cursor [1] overflow flag [2] cursor before this feed [4..5] num_kmers of pass 2
+    const uint32_t *run_if;
     uint32_t *pool;
     // pass 2 with remote destinations (sequence-sharded multi-GPU): window b's entries go to
     // peer[win_owner[b]] + dest_off[b] -- peer-mapped pools of the window owners (NVLink stores)
@@ -147,6 +156,39 @@ __device__ __forceinline__ void flag_records(const ScanParams &p, long long g, u
     });
 }
 
+// The same for a whole warp tile (all 32 lanes, converged; cm = 0 for lanes that count nothing).
+// A tile covers 496 bases and records are long, so nearly always the first and the last counted
+// window of the tile lie in one record, and nearly always it is the record the warp met last
+// time: RecCache keeps that record's extent (warp-uniform), two compares settle the tile.
+struct RecCache {
+    uint64_t lo = 1, hi = 0;        // stream extent [lo, hi) of the cached record (empty at first)
+    long long r = -1;
+};
+
+__device__ __forceinline__ void flag_records_warp(const ScanParams &p, long long g, uint32_t cv, uint32_t cm,
+                                                  RecCache &rc) {
+    if (!p.rec_flags) return;
+    const unsigned have = __ballot_sync(0xFFFFFFFFu, cm != 0u);
+    if (!have) return;
+    const int lane = threadIdx.x & 31, first = __ffs((int)have) - 1, last = 31 - __clz((int)have);
+    const uint32_t cm_first = __shfl_sync(0xFFFFFFFFu, cm, first), cm_last = __shfl_sync(0xFFFFFFFFu, cm, last);
+    const uint64_t base = p.stream_off + (uint64_t)(g - lane) * 16;          // group of lane 0
+    const uint64_t pos_lo = base + (uint64_t)first * 16 + (uint64_t)(15 - (31 - __clz((int)cm_first)));
+    const uint64_t pos_hi = base + (uint64_t)last * 16 + (uint64_t)(15 - (__ffs((int)cm_last) - 1));
+    if (pos_lo >= rc.lo && pos_hi < rc.hi) return;        // the record flagged last time
+    const long long r_lo = find_record(p.rec_starts, p.nrec, pos_lo);
+    const long long r_hi = find_record(p.rec_starts, p.nrec, pos_hi);
+    if (r_lo == r_hi) {
+        if (r_lo < 0) return;
+        if (lane == 0 && !p.rec_flags[r_lo]) p.rec_flags[r_lo] = 1;
+        rc.r = r_lo;
+        rc.lo = __ldg(p.rec_starts + r_lo);
+        rc.hi = (size_t)(r_lo + 1) < p.nrec ? __ldg(p.rec_starts + r_lo + 1) : ~0ull;
+    } else {
+        flag_records(p, g, cv, cm);
+    }
+}
+
 // One warp tile: lane l encodes group tile*GPW - H + l and receives its halo by shuffle.
 template <bool WIDE>
 struct WarpTile {
@@ -207,22 +249,24 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanPa
     const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     unsigned long long counted = 0;
+    RecCache rcache;
     for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles;
          tile += nwarps) {
         if (lane == 0) s_qn[warp] = 0;
         __syncwarp();
         WT t;
         t.load(p, tile, ngroups, lut);
+        uint32_t cm = 0;
         if (t.emits) {
-            const uint32_t cm = pk_scan_group<WIDE, FULL>(
+            cm = pk_scan_group<WIDE, FULL>(
                 p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
                 [&](int, auto o, uint32_t c) {
                     q[atomicAdd(&s_qn[warp], 1u)] = ((unsigned long long)(c - 1u) << 60) | (unsigned long long)o;
                 });
             counted += __popc(cm);
-            flag_records(p, t.g, t.cv, cm);
         }
         __syncwarp();
+        flag_records_warp(p, t.g, t.cv, cm, rcache);
         const uint32_t nq = s_qn[warp];
         for (uint32_t base = 0; base < nq; base += 32 * U) {
             unsigned long long e[U];
@@ -264,9 +308,17 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanPa
 }
 
 // ------------------------------------------------------------------------------ PARTITION
-// pass 1: per-window entry counts of this feed (+ num_kmers and record flags)
+// pass 1: per-window entry counts of this feed (+ num_kmers and record flags); with
+// sample_shift, of a pseudo-random 1 / 2^sample_shift of the tiles only
+__device__ __forceinline__ uint32_t tile_hash(long long tile) {
+    uint32_t x = (uint32_t)tile * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+    return x;
+}
+
 template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanParams p) {
+    if (p.run_if && *p.run_if == 0u) return;
     extern __shared__ uint32_t sm[];
     uint32_t *s_cnt = sm;                                  // [nbuckets]
     __shared__ uint8_t lut[256];
@@ -278,43 +330,93 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanPa
     const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const uint32_t wl = p.win_log2;
+    const uint32_t smask = (1u << p.sample_shift) - 1u;
     unsigned long long counted = 0;
+    RecCache rcache;
     for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles;
          tile += nwarps) {
+        if (smask && (tile_hash(tile) & smask)) continue;  // warp-uniform
         WT t;
         t.load(p, tile, ngroups, lut);
-        if (!t.emits) continue;
-        const uint32_t cm = pk_scan_group<WIDE, FULL>(
-            p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
-            [&](int, auto off, uint32_t) { atomicAdd(&s_cnt[(uint32_t)(off >> wl)], 1u); });
-        counted += __popc(cm);
-        flag_records(p, t.g, t.cv, cm);
+        uint32_t cm = 0;
+        if (t.emits)
+            cm = pk_scan_group<WIDE, FULL>(
+                p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
+                [&](int, auto off, uint32_t) { atomicAdd(&s_cnt[(uint32_t)(off >> wl)], 1u); });
+        __syncwarp();
+        if (p.pass1_tally) {
+            counted += __popc(cm);
+            flag_records_warp(p, t.g, t.cv, cm, rcache);
+        }
     }
-    add_num_kmers(p.num_kmers, counted);
+    if (p.pass1_tally) add_num_kmers(p.num_kmers, counted);
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < p.nbuckets; b += blockDim.x)
         if (s_cnt[b]) atomicAdd(&p.seg_cnt[b], s_cnt[b]);
 }
 
-// exclusive scan of one feed's window counts -> pool offsets; advances the pool cursor
-__global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restrict__ cnt,
+// exclusive scan of one feed's window counts -> pool offsets; advances the pool cursor.
+// ESTIMATE: cnt holds the sampled counts; every window gets room for
+// est * 2^shift * (1 + 1/16) + kCapSlack entries (stored in cap, cnt goes back to zero), unless
+// that adds up to more than `budget` entries -- then the overflow flag sends the feed down the
+// exact path straight away.
+constexpr uint32_t kCapSlack = 16384;
+
+template <bool ESTIMATE>
+__global__ void __launch_bounds__(256) k_bucket_offsets(uint32_t *__restrict__ cnt,
                                                         uint32_t *__restrict__ off, uint32_t nb,
-                                                        uint32_t *__restrict__ cursor) {
+                                                        uint32_t *__restrict__ ctl, uint32_t *__restrict__ cap,
+                                                        uint32_t shift, uint32_t budget, uint32_t test,
+                                                        const uint32_t *__restrict__ run_if) {
+    if (run_if && *run_if == 0u) return;
     __shared__ uint32_t part[256];
+    __shared__ uint32_t s_over;
     const uint32_t per = (nb + 255) / 256;
     const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
-    uint32_t s = 0;
-    for (uint32_t b = b0; b < b1; b++) s += cnt[b];
-    part[threadIdx.x] = s;
+    auto room = [&](uint32_t c) -> uint32_t {
+        if (!ESTIMATE) return c;
+        const unsigned long long e = (unsigned long long)c << shift;
+        const unsigned long long r = (test & 2u) ? e >> 1 : e + (e >> 4) + kCapSlack;   // test & 2: too little room
+        return r > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)r;
+    };
+    unsigned long long s64 = 0;
+    for (uint32_t b = b0; b < b1; b++) s64 += room(cnt[b]);
+    part[threadIdx.x] = s64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s64;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t run = *cursor;
-        for (int i = 0; i < 256; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
-        *cursor = run;
+        uint32_t run = ctl[0];
+        unsigned long long total = 0;
+        if (ESTIMATE) ctl[2] = run;                       // where this feed began
+        for (int i = 0; i < 256; i++) { const uint32_t v = part[i]; part[i] = run; run += v; total += v; }
+        s_over = ESTIMATE && (total > budget || (test & 1u)) ? 1u : 0u;   // test & 1: as if over budget
+        if (s_over) ctl[1] = 1u; else ctl[0] = run;
     }
     __syncthreads();
     uint32_t run = part[threadIdx.x];
-    for (uint32_t b = b0; b < b1; b++) { off[b] = run; run += cnt[b]; }
+    for (uint32_t b = b0; b < b1; b++) {
+        const uint32_t r = s_over ? 0u : room(cnt[b]);
+        off[b] = run;
+        run += r;
+        if (ESTIMATE) { cap[b] = r; cnt[b] = 0; }
+    }
+}
+
+// after the estimated pass 2: either adopt its fill counts (and its num_kmers), or -- a window
+// overflowed its reservation -- forget the attempt, so that the exact kernels, which are queued
+// behind and do nothing otherwise, redo the feed
+__global__ void __launch_bounds__(256) k_feed_settle(uint32_t *__restrict__ cnt, uint32_t *__restrict__ fill,
+                                                     uint32_t nb, uint32_t *__restrict__ ctl,
+                                                     unsigned long long *__restrict__ num_kmers) {
+    const bool over = ctl[1] != 0u;
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+        cnt[b] = over ? 0u : fill[b];
+        if (over) fill[b] = 0u;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(ctl + 4);
+        if (over) ctl[0] = ctl[2]; else *num_kmers += *tmp;
+        *tmp = 0ull;
+    }
 }
 
 // pass 2: the same scan again; entries are ranked per window in shared memory, staged
@@ -322,6 +424,8 @@ __global__ void __launch_bounds__(256) k_bucket_offsets(const uint32_t *__restri
 // entry = (run length - 1) << kEntShift | offset inside the window.
 template <bool WIDE, bool FULL>
 __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(const ScanParams p) {
+    if (p.run_if && *p.run_if == 0u) return;
+    if (p.seg_cap && p.ctl[1] != 0u) return;               // over budget already: straight to the exact path
     extern __shared__ uint32_t sm[];
     const uint32_t nb = p.nbuckets;
     uint32_t *s_cnt = sm;                                  // [nb] entries of this tile per window
@@ -341,6 +445,8 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
     const uint32_t wl = p.win_log2, wmask = (1u << wl) - 1u;
     const int warp = threadIdx.x >> 5;
     const uint32_t per = (nb + kScanThreads - 1) / kScanThreads;
+    unsigned long long counted = 0;
+    RecCache rcache;
 
     for (long long bt = blockIdx.x; bt < nblock_tiles; bt += gridDim.x) {
         for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) s_cnt[b] = 0;
@@ -353,8 +459,9 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
         if (tile < ntiles) {
             WT t;
             t.load(p, tile, ngroups, lut);
+            uint32_t cm = 0;
             if (t.emits)
-                pk_scan_group<WIDE, FULL>(
+                cm = pk_scan_group<WIDE, FULL>(
                     p.K, p.lo, p.span, t.cc, t.cv, t.pc1, t.pv1, t.pc2, t.pv2,
                     [&](int slot, auto off, uint32_t cnt) {
                         const uint32_t b = (uint32_t)(off >> wl);
@@ -362,6 +469,11 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
                         ent[slot] = ((uint32_t)off & wmask) | ((cnt - 1u) << kEntShift);
                         key[slot] = (b << 16) | rank;
                     });
+            __syncwarp();
+            if (p.pass2_tally) {
+                counted += __popc(cm);
+                flag_records_warp(p, t.g, t.cv, cm, rcache);
+            }
         }
         __syncthreads();
         // B: exclusive scan over the windows; reserve the tile's share of every segment
@@ -392,7 +504,16 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
                 const uint32_t c = s_cnt[b];
                 s_toff[b] = run;
                 run += c;
-                if (c) s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + atomicAdd(&p.seg_fill[b], c);
+                if (c) {
+                    const uint32_t room = p.seg_cap ? __ldg(p.seg_cap + b) : 0xFFFFFFFFu;   // before the atomic's round trip
+                    const uint32_t pos = atomicAdd(&p.seg_fill[b], c);
+                    if (pos + c > room) {                           // the estimate fell short: redo exactly
+                        if (*reinterpret_cast<volatile uint32_t *>(p.ctl + 1) == 0u) atomicExch(p.ctl + 1, 1u);
+                        s_gbase[b] = 0xFFFFFFFFu;
+                    } else {
+                        s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + pos;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -411,10 +532,12 @@ __global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(con
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             const uint32_t b = s_bid[i];
             uint32_t *dst = p.win_owner ? p.peer[p.win_owner[b]] : p.pool;
-            dst[s_gbase[b] + (i - s_toff[b])] = s_ent[i];
+            const uint32_t base = s_gbase[b];
+            if (base != 0xFFFFFFFFu) dst[base + (i - s_toff[b])] = s_ent[i];
         }
         // the next iteration only touches s_cnt before its first barrier
     }
+    if (p.pass2_tally) add_num_kmers(reinterpret_cast<unsigned long long *>(p.ctl + 4), counted);
 }
 
 // per window: every buffered entry of the window bumps its L2-resident 32-bit counter.
@@ -1066,8 +1189,9 @@ __global__ void __launch_bounds__(1024, 1) k_sub_tally(const uint32_t *__restric
 }
 
 // new carry = last kCarry bytes of (old carry ++ seq[0..n))
-__global__ void k_update_carry(uint8_t *carry, const uint8_t *seq, size_t n) {
+__global__ void k_update_carry(uint8_t *carry, const uint8_t *seq, size_t n, uint32_t *ctl) {
     const int i = threadIdx.x;                            // 32 threads
+    if (ctl && i == 0) ctl[1] = 0u;                       // the feed is settled either way
     const long long pos = (long long)n - kCarry + i;
     const uint8_t v = pos >= 0 ? seq[pos] : carry[kCarry + pos];
     __syncwarp();
@@ -1178,8 +1302,11 @@ struct pk_indexer {
     const uint8_t *p1_seq = nullptr;           // sequence of the pending pass 1
     size_t p1_n = 0;
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
-    uint32_t *seg = nullptr;                   // 3 x [kMaxSegments][nbuckets]: cnt, off, fill
-    uint32_t *cursor = nullptr;                // device pool cursor
+    uint32_t *seg = nullptr;                   // 4 x [kMaxSegments][nbuckets]: cnt, off, fill, cap
+    uint32_t *cursor = nullptr;                // device control words: pool cursor, overflow flag, ... (ScanParams::ctl)
+    uint32_t est_shift = 4;                    // estimated pass 1 looks at one tile in 2^est_shift (0 = always exact)
+    size_t est_min = (size_t)1 << 24;          // ... for feeds of at least this many bases
+    uint32_t est_test = 0;                     // test hook: 1 = as if over budget, 2 = reserve too little room
     uint32_t *scratch = nullptr;               // one window of 32-bit counters
     unsigned long long *bins_part = nullptr;   // [4 * sm_count][256] partial histograms
     uint32_t *pool2 = nullptr;                 // smem flush: entries regrouped by sub-bucket
@@ -1219,6 +1346,17 @@ struct prof_scope {
     ~prof_scope() { if (end) cudaEventRecord(end, st); }
 };
 
+// zero the whole table in pieces of 16 GiB: one cudaMemsetAsync over tens of GiB slows down to
+// ~2.4 TB/s (measured: 51 GiB in 22 ms, against 32 GiB in 4.8 ms = 7.2 TB/s)
+static cudaError_t table_zero(pk_indexer *ix, cudaStream_t st) {
+    const size_t bytes = (ix->table_bytes + 255) & ~(size_t)255, piece = (size_t)16 << 30;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const cudaError_t e = cudaMemsetAsync(ix->table + off, 0, std::min(piece, bytes - off), st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // make work_stream wait for whatever the caller's stream was last given
 static int indexer_join(pk_indexer *ix) {
     if (ix->last_stream != ix->work_stream) {
@@ -1235,6 +1373,9 @@ static uint32_t *seg_off(pk_indexer *ix, int f) {
 }
 static uint32_t *seg_fill(pk_indexer *ix, int f) {
     return ix->seg + ((size_t)2 * kMaxSegments + f) * ix->nbuckets;
+}
+static uint32_t *seg_cap(pk_indexer *ix, int f) {
+    return ix->seg + ((size_t)3 * kMaxSegments + f) * ix->nbuckets;
 }
 
 // The window's 32-bit counters must stay in L2 while the k-mer entries and the table
@@ -1385,8 +1526,8 @@ static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats
             }
         }
     }
-    PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
-    PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
+    PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)4 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
+    PK_CUDA(cudaMemsetAsync(ix->cursor, 0, 32, st));
     ix->nseg = 0;
     ix->pool_ub = 0;
     ix->pool_ext = nullptr;
@@ -1505,7 +1646,16 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
     } else {
-        if (phase != SCAN_PASS2_REMOTE && (ix->nseg == kMaxSegments || ix->pool_ub + n > ix->pool_cap)) {
+        // Estimated pass 1 (PARTITION, big feeds): pass 1 only has to size the segments, so it
+        // looks at one tile in 16 and every window gets room for its estimate + 1/16 + kCapSlack;
+        // pass 2 checks each reservation against that room and does the bookkeeping (num_kmers,
+        // record flags).  If a window ever overflows, k_feed_settle forgets the attempt and the
+        // exact kernels queued behind -- which otherwise return at once -- redo the feed.
+        const size_t est_need = n + n / 8 + (size_t)ix->nbuckets * kCapSlack;
+        bool estimate = phase == SCAN_BOTH && ix->mode == PK_MODE_PARTITION && ix->est_shift > 0 &&
+                        n >= ix->est_min && est_need <= ix->pool_cap && est_need < (1ull << 32);
+        const size_t need = estimate ? est_need : n;
+        if (phase != SCAN_PASS2_REMOTE && (ix->nseg == kMaxSegments || ix->pool_ub + need > ix->pool_cap)) {
             if (ix->mode == PK_MODE_SCAN)
                 return pk_set_error(PK_ERR_STATE, "scan-only handle: k-mer buffer full (%zu entries, %d segments); "
                                     "export and reset before feeding more", ix->pool_cap, ix->nseg);
@@ -1515,6 +1665,8 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         const int f = ix->nseg;
         p.win_log2 = ix->win_log2; p.nbuckets = ix->nbuckets; p.pool = ix->pool;
         p.seg_cnt = seg_cnt(ix, f); p.seg_off = seg_off(ix, f); p.seg_fill = seg_fill(ix, f);
+        p.ctl = ix->cursor;
+        p.pass1_tally = 1;
         const size_t smem1 = (size_t)ix->nbuckets * sizeof(uint32_t);
         const size_t smem2 = scatter_smem_bytes(ix->nbuckets);
         if (!ix->scatter_smem_set) {
@@ -1522,19 +1674,49 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             if (smem1 > 48 * 1024) PK_SMEM_OPT_IN(k_scan_bucket_count, smem1);
             ix->scatter_smem_set = true;
         }
-        if (phase != SCAN_PASS2_REMOTE) {
-            int per_sm = 0;
-            PK_OCCUPANCY(k_scan_bucket_count, smem1, per_sm);
-            const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm));
+        int per_sm1 = 0, per_sm2 = 0;
+        PK_OCCUPANCY(k_scan_bucket_count, smem1, per_sm1);
+        PK_OCCUPANCY(k_scan_scatter, smem2, per_sm2);
+        // grid-stride / persistent kernels: exactly as many blocks as are resident at once
+        const int grid1 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm1));
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm2));
+        if (estimate) {
+            ScanParams q = p;
+            q.sample_shift = ix->est_shift; q.pass1_tally = 0; q.pass2_tally = 1; q.seg_cap = seg_cap(ix, f);
             {
                 prof_scope ps(ix, st, PROF_BUCKET_COUNT);
-                PK_LAUNCH_SCAN(k_scan_bucket_count, grid, smem1);
+                const ScanParams keep = p; p = q;
+                PK_LAUNCH_SCAN(k_scan_bucket_count, grid1, smem1);
+                p = keep;
             }
+            {
+                prof_scope ps(ix, st, PROF_OFFSETS);
+                k_bucket_offsets<true><<<1, 256, 0, st>>>(q.seg_cnt, seg_off(ix, f), ix->nbuckets, ix->cursor,
+                                                          seg_cap(ix, f), ix->est_shift, (uint32_t)est_need,
+                                                          ix->est_test, nullptr);
+            }
+            {
+                prof_scope ps(ix, st, PROF_SCATTER);
+                const ScanParams keep = p; p = q;
+                PK_LAUNCH_SCAN(k_scan_scatter, grid2, smem2);
+                p = keep;
+            }
+            {
+                prof_scope ps(ix, st, PROF_OFFSETS);
+                k_feed_settle<<<1, 256, 0, st>>>(q.seg_cnt, q.seg_fill, ix->nbuckets, ix->cursor, ix->counters);
+            }
+            ix->launches += 4;
+            p.run_if = ix->cursor + 1;                     // the exact kernels below run only after an overflow
+        }
+        if (phase != SCAN_PASS2_REMOTE) {
+            prof_scope ps(ix, st, PROF_BUCKET_COUNT);
+            PK_LAUNCH_SCAN(k_scan_bucket_count, grid1, smem1);
             ix->launches += 1;
         }
         if (phase == SCAN_BOTH) {
             prof_scope ps(ix, st, PROF_OFFSETS);
-            k_bucket_offsets<<<1, 256, 0, st>>>(p.seg_cnt, seg_off(ix, f), ix->nbuckets, ix->cursor);
+            k_bucket_offsets<false><<<1, 256, 0, st>>>(p.seg_cnt, seg_off(ix, f), ix->nbuckets, ix->cursor,
+                                                       nullptr, 0u, 0u, 0u, p.run_if);
             ix->launches += 1;
         }
         if (phase == SCAN_PASS1) {
@@ -1549,10 +1731,6 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             p.dest_off = ix->route + ix->nbuckets;
             for (int i = 0; i < 16; i++) p.peer[i] = ix->peer_pool[i];
         }
-        // persistent kernel: exactly as many blocks as are resident at once (no second wave)
-        int per_sm = 0;
-        PK_OCCUPANCY(k_scan_scatter, smem2, per_sm);
-        const int grid2 = (int)std::max<long long>(1, std::min<long long>(want, (long long)ix->sm_count * per_sm));
         {
             prof_scope ps(ix, st, PROF_SCATTER);
             PK_LAUNCH_SCAN(k_scan_scatter, grid2, smem2);
@@ -1561,13 +1739,13 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         ix->launches += 1;
         if (phase == SCAN_BOTH) {
             ix->nseg++;
-            ix->pool_ub += n;
+            ix->pool_ub += need;
         }
         ix->stats_valid = false;
     }
     {
         prof_scope ps(ix, st, PROF_CARRY);
-        k_update_carry<<<1, 32, 0, st>>>(ix->carry, seq_dev, n);
+        k_update_carry<<<1, 32, 0, st>>>(ix->carry, seq_dev, n, ix->mode != PK_MODE_DIRECT ? ix->cursor : nullptr);
     }
     PK_CUDA(cudaGetLastError());
     ix->launches += 1;
@@ -1679,7 +1857,16 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         }
         while (cap > ((size_t)1 << 20) && cap * sizeof(uint32_t) > free_b / 4) cap >>= 1;
         ix->pool_cap = cap;
-        const size_t seg_bytes = (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t);
+        // test hooks of the estimated pass 1: PYKMER_B200_EST = "shift[:min_log2[:test]]"
+        // (shift 0 = always exact; test 1 = as if over budget, 2 = reserve too little room)
+        if (const char *env = getenv("PYKMER_B200_EST")) {
+            int sh = 4, ml = 24, test = 0;
+            sscanf(env, "%d:%d:%d", &sh, &ml, &test);
+            ix->est_shift = (uint32_t)std::min(std::max(sh, 0), 8);
+            ix->est_min = (size_t)1 << std::min(std::max(ml, 0), 40);
+            ix->est_test = (uint32_t)test;
+        }
+        const size_t seg_bytes = (size_t)4 * kMaxSegments * ix->nbuckets * sizeof(uint32_t);
         step(cudaMalloc(&ix->pool, cap * sizeof(uint32_t)));
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
@@ -1738,7 +1925,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         }
     }
     if (e == cudaSuccess) {
-        if (mode == PK_MODE_DIRECT) step(cudaMemsetAsync(ix->table, 0, alloc, ix->work_stream));
+        if (mode == PK_MODE_DIRECT) step(table_zero(ix, ix->work_stream));
         step(cudaMemsetAsync(ix->carry, 0, 64, ix->work_stream));
         step(cudaMemsetAsync(ix->counters, 0, 257 * sizeof(unsigned long long), ix->work_stream));
         step(cudaStreamSynchronize(ix->work_stream));
@@ -1796,11 +1983,11 @@ PK_API int pk_indexer_reset(pk_indexer *ix, pk_stream stream) {
     PK_CUDA(cudaEventRecord(ix->joined, ix->work_stream));
     PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
     if (ix->mode == PK_MODE_DIRECT) {
-        PK_CUDA(cudaMemsetAsync(ix->table, 0, ix->table_bytes, st));
+        PK_CUDA(table_zero(ix, st));
     } else {
         // the first flush rewrites every window, so the table itself needs no memset
-        PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)3 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
-        PK_CUDA(cudaMemsetAsync(ix->cursor, 0, sizeof(uint32_t), st));
+        PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)4 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
+        PK_CUDA(cudaMemsetAsync(ix->cursor, 0, 32, st));
         ix->nseg = 0;
         ix->pool_ub = 0;
         ix->pool_ext = nullptr;
@@ -2013,7 +2200,7 @@ PK_API int pk_indexer_prime(pk_indexer *ix, const uint8_t *halo_dev, size_t n, u
     }
     PK_CUDA(cudaMemsetAsync(ix->carry, 0, 64, st));
     if (n) {
-        k_update_carry<<<1, 32, 0, st>>>(ix->carry, halo_dev, n);
+        k_update_carry<<<1, 32, 0, st>>>(ix->carry, halo_dev, n, nullptr);
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
     }

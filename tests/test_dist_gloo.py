@@ -155,7 +155,7 @@ def test_balanced_kmer_ranges_tile_the_axis_and_even_out_cost():
         assert ranges[0][0] == 0 and ranges[-1][1] == T
         assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
         assert all(lo % (1 << wl) == 0 and hi > lo for lo, hi in ranges)
-        cost = [per_window[lo >> wl:hi >> wl].sum() + 180_000 * ((hi - lo) >> wl) for lo, hi in ranges]
+        cost = [per_window[lo >> wl:hi >> wl].sum() + 230_000 * ((hi - lo) >> wl) for lo, hi in ranges]
         assert max(cost) < 1.05 * (sum(cost) / n)
         equal = [per_window[nwin * r // n:nwin * (r + 1) // n].sum() for r in range(n)]
         assert max(equal) > 1.3 * (sum(equal) / n)                       # what balancing avoids

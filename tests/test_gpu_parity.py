@@ -27,13 +27,14 @@ def env():
 
 
 def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=False, mode=0,
-                  window_log2=None, pool_log2=None, flush=None, ovf_log2=None):
+                  window_log2=None, pool_log2=None, flush=None, ovf_log2=None, est=None):
     import torch
     hi = 4 ** K if hi is None else hi
     # test hooks of the library: small table windows / small k-mer buffer / flush scheme
     # (read at create time)
     for name, val in (("PYKMER_B200_WINDOW_LOG2", window_log2), ("PYKMER_B200_POOL_LOG2", pool_log2),
-                      ("PYKMER_B200_FLUSH", flush), ("PYKMER_B200_OVF_LOG2", ovf_log2)):
+                      ("PYKMER_B200_FLUSH", flush), ("PYKMER_B200_OVF_LOG2", ovf_log2),
+                      ("PYKMER_B200_EST", est)):
         if val is None:
             os.environ.pop(name, None)
         else:
@@ -45,6 +46,7 @@ def _index_stream(dev, stream, K, lo=0, hi=None, starts=None, pieces=None, host=
         os.environ.pop("PYKMER_B200_POOL_LOG2", None)
         os.environ.pop("PYKMER_B200_FLUSH", None)
         os.environ.pop("PYKMER_B200_OVF_LOG2", None)
+        os.environ.pop("PYKMER_B200_EST", None)
     with ix:
         if starts is not None:
             ix.set_records(starts)
@@ -515,6 +517,30 @@ def test_byte_windows_settle_carries_exactly(env, K, wlog, ovf_log2, pieces):
     assert hist == oh and all(st[k] == ost[k] for k in ("vals_sum", "vals_count", "vals_min", "vals_max"))
     ref, _, st2, _ = _index_stream(env["dev"], s, K, hi=hi, mode=PART, window_log2=min(wlog, 24), flush="l2")
     assert np.array_equal(ref, table) and st2 == st
+
+
+@pytest.mark.parametrize("K,wlog", [(11, 16), (13, 20), (13, 24), (15, 24), (17, 26)])
+@pytest.mark.parametrize("est", ["4:12:0", "2:12:0", "4:12:1", "4:12:2", "0:12:0"])
+@pytest.mark.parametrize("pieces", [None, [300_001, 1_200_000]])
+def test_estimated_pass1_and_its_exact_fallback(env, K, wlog, est, pieces):
+    """PARTITION mode sizes its segments from a sampled pass 1 (one tile in 2^shift); pass 2 then
+    does the bookkeeping.  Normal case, the two ways the estimate can fall short (over budget:
+    test 1, a window overflowing its room: test 2 -- the exact kernels queued behind redo the feed)
+    and the always-exact path all give the oracle's table, statistics, num_kmers and record flags."""
+    rng = np.random.default_rng(77 + K)
+    recs = [_random_stream(rng, int(n)) for n in (700_000, 3, 400_000, 900_000)]
+    sep = np.frombuffer(b">", dtype=np.uint8)
+    s = np.concatenate([np.concatenate([r, sep]) for r in recs])
+    starts = np.cumsum([0] + [len(r) + 1 for r in recs[:-1]]).astype(np.uint64)
+    hi = None if K <= 13 else 1 << 28
+    want, num, flags_want = env["oracle"].index_stream(s, K, range_hi=hi, rec_starts=starts) if hi else \
+        env["oracle"].index_stream(s, K, rec_starts=starts)
+    table, hist, st, flags = _index_stream(env["dev"], s, K, hi=hi, starts=starts, mode=PART, window_log2=wlog,
+                                           est=est, pieces=pieces)
+    assert st["num_kmers"] == num
+    assert np.array_equal(table, want)
+    assert hist == env["oracle"].table_stats(want)[0]
+    assert list(flags) == list(flags_want)
 
 
 def test_partition_mode_feed_after_finalize_and_reset(env):
