@@ -85,23 +85,76 @@ def load_stream(scale: float, rank: int, world: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (every
+    ~2 ms -- the timed regions here last tens of milliseconds, too short for `nvidia-smi -lms`),
+    `nvidia-smi` as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.thread, self.stop_flag, self.sm, self.mx, self.reasons = None, False, [], [], set()
+        self.timed = False                                   # samples are kept only while this is set
+
+    def _poll(self, nv, handle):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+            except Exception:
+                break
+            if self.timed:
+                self.sm.append(float(mhz))
+                for name, bit in names:
+                    if bits & bit:
+                        self.reasons.add(name)
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: match the CUDA device by PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            handle = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    h = nv.nvmlDeviceGetHandleByIndex(i)
+                    if int(nv.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        handle = h
+                        break
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))]
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.timed = True
         except OSError:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx[0] if self.mx else None, "reasons": ["no samples"]}
+            return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx[0], "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "how": "NVML, polled every ~2 ms inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -127,7 +180,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 def ncu_traffic(kernel: str):
@@ -237,9 +290,9 @@ def run_reference_merger(args):
 
 # ------------------------------------------------------------------------------ GPU arm
 
-def timed_steps(torch, dist, world, warmup, steps, body):
+def timed_steps(torch, dist, world, warmup, steps, body, sampler=None):
     """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events on the
-    launching stream, max over ranks."""
+    launching stream, max over ranks.  `sampler` keeps clock samples of the timed steps only."""
     for _ in range(warmup):
         body()
     torch.cuda.synchronize()
@@ -247,11 +300,15 @@ def timed_steps(torch, dist, world, warmup, steps, body):
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.timed = True
     ev0.record()
     for _ in range(steps):
         body()
     ev1.record()
     torch.cuda.synchronize()
+    if sampler is not None and sampler.thread is not None:
+        sampler.timed = False
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
@@ -326,7 +383,7 @@ def run_indexer_seqshard(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     l0 = scanner.launch_count() + counter.launch_count()
     sampler.start()
-    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step_device)
+    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step_device, sampler)
     clocks = sampler.stop()
     launches = (scanner.launch_count() + counter.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     ms_step = ms / args.steps
@@ -448,7 +505,7 @@ def run_indexer(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     launches0 = ix.launch_count()
     sampler.start()
-    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step_device)
+    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step_device, sampler)
     clocks = sampler.stop()
     launches_all = ix.launch_count() - launches0
     launches = launches_all * args.steps // (args.steps + args.warmup)
@@ -493,7 +550,8 @@ def run_indexer(args, rank, local_rank, world):
     dom_ms, dom_launches = prof[dom]
     achieved = alg_by_class[dom] / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_" + dom) if K == 15 else None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(("k_window_count8" if (K >= 17 and dom == "window_count") else "k_" + dom))
+                if (K in (15, 17) and not args.emulate_shard) else None,
                 "peak_source": peak_src,
                 "kernel_ms_total": dom_ms, "kernel_launches": dom_launches,
                 "algorithmic_bytes": alg_by_class[dom],
@@ -616,7 +674,7 @@ def run_merger(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step)
+    ms = timed_steps(torch, dist, world, args.warmup, args.steps, step, sampler)
     clocks = sampler.stop()
     ms_step = ms / args.steps
     bytes_bits = N * T / 8
@@ -671,6 +729,9 @@ def run_merger(args, rank, local_rank, world):
                     "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": None,
                     "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json)" + (f" x {world} GPUs" if world > 1 else "")
                                    + "; int8 ops, nominal dense 4500 per GPU",
+                    "frac_of_nominal_int8": ach / (4500.0 * world),
+                    "traffic_note": "ncu capture of this kernel at K=13, N=255 (profiles/r01_ncu_summary.txt): "
+                                    "dram read 2.14 GB = N * 4^13 / 8 exactly -- every bitmask word is read once",
                     "hbm_GBps": value, "hbm_frac": value / (hbm_peak * world)}
         else:
             popc = N * (N + 1) / 2 * T / 32
