@@ -269,32 +269,43 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanPa
         flag_records_warp(p, t.g, t.cv, cm, rcache);
         const uint32_t nq = s_qn[warp];
         for (uint32_t base = 0; base < nq; base += 32 * U) {
-            unsigned long long e[U];
-            uint32_t seen[U];
+            unsigned long long off[U];
+            uint32_t c[U], seen[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {                 // first round: independent operations
                 const uint32_t i = base + u * 32 + lane;
-                e[u] = i < nq ? q[i] : ~0ull;
-                if (e[u] == ~0ull) continue;
-                const unsigned long long off = e[u] & ((1ull << 60) - 1ull);
-                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off & ~3ull));
-                const uint32_t c = (uint32_t)(e[u] >> 60) + 1u;
-                seen[u] = SPARSE ? atomicCAS(wp, 0u, c << (8u * ((uint32_t)off & 3u))) : __ldcg(wp);
+                const unsigned long long e = i < nq ? q[i] : ~0ull;
+                off[u] = e == ~0ull ? ~0ull - (unsigned)lane : e & ((1ull << 60) - 1ull);   // dead lanes: unique
+                c[u] = e == ~0ull ? 0u : (uint32_t)(e >> 60) + 1u;
+                // microsatellites put the same two or three k-mers into every lane: one update per
+                // distinct offset of the batch (cheap screen first, MATCH.ANY only when it fires)
+                const uint32_t h = (uint32_t)off[u] ^ (uint32_t)(off[u] >> 32);
+                const uint32_t h1 = __shfl_up_sync(0xFFFFFFFFu, h, 1), h2 = __shfl_up_sync(0xFFFFFFFFu, h, 2),
+                               h3 = __shfl_up_sync(0xFFFFFFFFu, h, 3);
+                const bool dup = (lane >= 1 && h1 == h) || (lane >= 2 && h2 == h) || (lane >= 3 && h3 == h);
+                if (__any_sync(0xFFFFFFFFu, dup)) {
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, off[u]);
+                    if (peers != (1u << lane)) {
+                        const uint32_t sum = __reduce_add_sync(peers, c[u]);
+                        c[u] = lane == (__ffs((int)peers) - 1) ? min(sum, 255u) : 0u;
+                    }
+                }
+                if (!c[u]) continue;
+                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off[u] & ~3ull));
+                seen[u] = SPARSE ? atomicCAS(wp, 0u, c[u] << (8u * ((uint32_t)off[u] & 3u))) : __ldcg(wp);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {                 // second round: settle against what was seen
-                if (e[u] == ~0ull) continue;
-                const unsigned long long off = e[u] & ((1ull << 60) - 1ull);
-                const uint32_t c = (uint32_t)(e[u] >> 60) + 1u;
-                if (SPARSE && seen[u] == 0u) { ht.move(0u, c); continue; }
-                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off & ~3ull));
-                const uint32_t sh = 8u * ((uint32_t)off & 3u);
+                if (!c[u]) continue;
+                if (SPARSE && seen[u] == 0u) { ht.move(0u, c[u]); continue; }
+                uint32_t *wp = reinterpret_cast<uint32_t *>(p.table + (off[u] & ~3ull));
+                const uint32_t sh = 8u * ((uint32_t)off[u] & 3u);
                 uint32_t old = seen[u];
                 for (;;) {                                // table[idx] = min(255, table[idx] + c), indexer.py:239,262;
                                                           // counters only grow, so a read of 255 is final
                     const uint32_t b = (old >> sh) & 0xFFu;
                     if (b == 255u) break;
-                    const uint32_t nb = min(255u, b + c);
+                    const uint32_t nb = min(255u, b + c[u]);
                     const uint32_t assumed = old;
                     old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (nb << sh));
                     if (old == assumed) { ht.move(b, nb); break; }
@@ -714,8 +725,10 @@ struct OvfTable {
 };
 
 __device__ __forceinline__ void ovf_add(const OvfTable &t, uint32_t lane_idx, long long delta) {
+    if (*reinterpret_cast<volatile uint32_t *>(t.meta + 2)) return;   // already bound for the exact recount
     uint32_t h = (lane_idx * 0x9E3779B1u) >> 7;
-    for (uint32_t probe = 0; probe <= t.mask; probe++, h++) {
+    const uint32_t max_probe = min(t.mask, 255u);          // a long probe chain counts as a full table
+    for (uint32_t probe = 0; probe <= max_probe; probe++, h++) {
         const uint32_t slot = h & t.mask;
         uint32_t k = __ldcg(t.keys + slot);
         if (k == 0xFFFFFFFFu) {

@@ -134,12 +134,18 @@ PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t span, uint32_t cc, uin
     uint32_t counted = 0, pend = 0;
     if (WIDE) {
         const uint32_t r2 = pk_rcw(pc2);
+        // pk_rc_at slices r0:r1:r2 at bit 66 + 2j - 2K: shift the 96-bit value once per group by the
+        // K-dependent part (4..32 bits for K = 17..31), so that the per-window shifts are the constants 2j
+        const int sh0 = 66 - 2 * K;
+        const uint64_t rp_lo = ((((uint64_t)r1 << 32) | r2) >> sh0) | ((uint64_t)r0 << (64 - sh0));
+        const uint64_t rp_hi = (uint64_t)r0 >> sh0;
+        const uint64_t kmask = pk_kmer_mask(K);
         uint64_t prev = ~0ull;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             if (!((Wm >> (15 - j)) & 1u)) continue;
             const uint64_t f = pk_fwd_at(pc2, pc1, cc, j, K);
-            const uint64_t r = pk_rc_at(r2, r1, r0, j, K);
+            const uint64_t r = (j ? (rp_lo >> (2 * j)) | (rp_hi << (64 - 2 * j)) : rp_lo) & kmask;
             const uint64_t off = (f < r ? f : r) - lo;            // indexer.py:341
             if (!FULL && off >= span) continue;                   // another shard's k-mer
             counted |= 1u << (15 - j);
