@@ -1326,9 +1326,6 @@ struct pk_indexer {
     uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
     bool flush_smem = false;                   // second-level shared-memory flush (else L2 counters)
     bool count8 = false;                       // byte windows: the L2 window holds 8-bit lanes (k_window_count8)
-    bool overlap = false;                      // 32-bit windows: two half-size counter arrays, commit(b) beside count(b+1)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t cnt_done[2] = {nullptr, nullptr}, com_done[2] = {nullptr, nullptr};
     size_t scratch_bytes = 0;
     OvfTable ovf = {nullptr, nullptr, nullptr, nullptr, 0};
     bool sub_smem_set = false;
@@ -1453,63 +1450,8 @@ static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table
     return rc;
 }
 
-// 32-bit windows, overlapped: the L2 budget holds TWO counter arrays of half the size; while the
-// commit of window b streams one of them out on aux_stream (bandwidth), the count of window b+1
-// fills the other on `st` (L2 atomic units).
-static int indexer_flush_overlap(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
-    const size_t win = (size_t)1 << ix->win_log2;
-    cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.blockDim = dim3(256);
-    cfg.attrs = attr;
-    cfg.numAttrs = window_launch_attr(ix, attr);
-    const int rows = ix->sm_count * 4;
-    if (with_stats)
-        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
-    unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
-    const uint32_t *src = ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool;
-    cudaStream_t aux = ix->aux_stream;
-    PK_CUDA(cudaEventRecord(ix->cnt_done[0], st));          // aux starts after everything queued on st so far
-    PK_CUDA(cudaStreamWaitEvent(aux, ix->cnt_done[0], 0));
-    for (uint32_t b = 0; b < ix->nbuckets; b++) {
-        const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
-        uint32_t *half = ix->scratch + ((size_t)(b & 1u) << ix->win_log2);
-        if (b >= 2) PK_CUDA(cudaStreamWaitEvent(st, ix->com_done[b & 1u], 0));   // the half is clean again
-        if (ix->nseg) {
-            prof_scope ps(ix, st, PROF_WINDOW_COUNT);
-            cfg.stream = st;
-            cfg.gridDim = dim3(ix->sm_count * 8);
-            PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_count, src, (const uint32_t *)seg_off(ix, 0),
-                                       (const uint32_t *)seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, half));
-            ix->launches++;
-        }
-        PK_CUDA(cudaEventRecord(ix->cnt_done[b & 1u], st));
-        PK_CUDA(cudaStreamWaitEvent(aux, ix->cnt_done[b & 1u], 0));
-        uint8_t *tw = ix->table + (size_t)b * win;
-        const int cgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows, (n / 4 + 255) / 256));
-        {
-            prof_scope ps(ix, aux, PROF_WINDOW_COMMIT);
-            cfg.stream = aux;
-            cfg.gridDim = dim3(cgrid);
-            if (ix->table_valid) PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<true>, half, tw, n, bins));
-            else                 PK_CUDA(cudaLaunchKernelEx(&cfg, k_window_commit<false>, half, tw, n, bins));
-        }
-        ix->launches++;
-        PK_CUDA(cudaEventRecord(ix->com_done[b & 1u], aux));
-        if (table_host) {                                   // ship this window while the next ones are counted
-            PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->com_done[b & 1u], 0));
-            PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
-        }
-    }
-    PK_CUDA(cudaStreamWaitEvent(st, ix->com_done[0], 0));
-    PK_CUDA(cudaStreamWaitEvent(st, ix->com_done[1], 0));
-    return indexer_flush_finish(ix, st, with_stats, table_host);
-}
-
 static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
     if (ix->count8 && !ix->table_valid) return indexer_flush_inplace(ix, st, table_host);
-    if (ix->overlap && !ix->count8) return indexer_flush_overlap(ix, st, with_stats, table_host);
     if (ix->count8 && !ix->scratch) {
         // a later flush onto a table that already holds counts (k-mer buffer overflow, feeding after
         // finalize): count into a zeroed scratch window, then add it in with byte saturation
@@ -1880,11 +1822,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     const char *fe = getenv("PYKMER_B200_FLUSH");
     ix->flush_smem = fe && strcmp(fe, "smem") == 0;
     ix->count8 = fe ? strcmp(fe, "byte") == 0 : kmer_len >= 17;
-    {
-        const char *oe = getenv("PYKMER_B200_OVERLAP");
-        ix->overlap = !ix->count8 && !ix->flush_smem && oe && atoi(oe) != 0;
-    }
-    uint32_t win_log2 = ix->count8 ? 26 : (ix->overlap ? 23 : 24);
+    uint32_t win_log2 = ix->count8 ? 26 : 24;
     if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
         const int v = atoi(env);
         if (v >= 4 && v <= (ix->count8 ? 26 : 24)) win_log2 = (uint32_t)v;
@@ -1951,15 +1889,8 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
                 step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
                 step(cudaMalloc(&ix->sub, (size_t)3 * 64 * kSubs * sizeof(uint32_t)));
             } else if (!ix->count8) {                       // byte windows count in the table itself
-                ix->scratch_bytes = (sizeof(uint32_t) << win_log2) * (ix->overlap ? 2 : 1);
+                ix->scratch_bytes = sizeof(uint32_t) << win_log2;
                 step(cudaMalloc(&ix->scratch, ix->scratch_bytes));
-                if (ix->overlap) {
-                    step(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
-                    for (int i = 0; i < 2; i++) {
-                        step(cudaEventCreateWithFlags(&ix->cnt_done[i], cudaEventDisableTiming));
-                        step(cudaEventCreateWithFlags(&ix->com_done[i], cudaEventDisableTiming));
-                    }
-                }
             }
             if (ix->count8) {
                 uint32_t ovf_log2 = 16;
@@ -2046,11 +1977,6 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
         if (ix->consumed[i]) cudaEventDestroy(ix->consumed[i]);
     }
     if (ix->joined) cudaEventDestroy(ix->joined);
-    for (int i = 0; i < 2; i++) {
-        if (ix->cnt_done[i]) cudaEventDestroy(ix->cnt_done[i]);
-        if (ix->com_done[i]) cudaEventDestroy(ix->com_done[i]);
-    }
-    if (ix->aux_stream) { cudaStreamSynchronize(ix->aux_stream); cudaStreamDestroy(ix->aux_stream); }
     for (cudaEvent_t e : ix->prof_events) cudaEventDestroy(e);
     if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->work_stream) cudaStreamDestroy(ix->work_stream);
