@@ -207,6 +207,25 @@ int pk_pair_counts_device(const uint8_t *s_dev, const uint8_t *o_dev, size_t n, 
 int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t n, int min_count,
                   int max_count, int device, uint64_t *matrix_host);
 
+/* ------------------------------------------------------------------ host ingest
+ * Host-only helpers of the FASTA reader (pykmer_b200/fasta.py); no CUDA call, usable without
+ * a GPU.  They take over the two passes over the text that dominate the CLI's wall time:
+ * gunzipping a .bgz input (read_fasta, indexer.py:108-115 -- BGZF members are independent, so
+ * they inflate in parallel) and stripping + joining sequence lines (parse_fasta,
+ * indexer.py:55-95) when the lines hold no inner white space.
+ *
+ * pk_bgzf_inflate: inflate as many WHOLE BGZF members of comp[0, comp_len) as fit into
+ * out[0, out_cap) on `threads` threads (0 = all cores); CRC and length of every member are
+ * checked.  *consumed = compressed bytes used (a prefix of whole members; a truncated last
+ * member is left for the next call), *produced = bytes written.
+ * pk_fasta_clean: dst = src minus '\n' and '\r'; *n_out = bytes kept.  flags bit 0: src holds
+ * other strip()-able white space (blank, tab, \v, \f, 0x1c-0x1f), bit 1: a byte >= 0x80 -- with
+ * either set dst is not written and the caller goes line by line / rejects the input. */
+int pk_bgzf_inflate(const uint8_t *comp, size_t comp_len, uint8_t *out, size_t out_cap,
+                    size_t *consumed, size_t *produced, int threads);
+int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_out, uint32_t *flags,
+                   int threads);
+
 /* Deterministic synthetic count table (benchmark input):
  * entries [lo, hi) of sample `sample`, bit-identical to pykmer_b200/synth.py. */
 int pk_synth_table_device(uint8_t *dst_dev, int sample, uint64_t lo, uint64_t hi,

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpykmer_b200.so")
-SOURCES = ["api.cu", "indexer.cu", "merger.cu", "gram_i8.cu"]
+SOURCES = ["api.cu", "indexer.cu", "merger.cu", "gram_i8.cu", "ingest.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math", "-shared",
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd += ["-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lz", "-lpthread"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)

@@ -124,6 +124,60 @@ def bgzf_chunks(path: str, chunk_bytes: int = 64 << 20, threads: Optional[int] =
                 yield out
 
 
+_NATIVE = []
+
+
+def _native_lib():
+    """libpykmer_b200.so's host-side ingest helpers, or None when the library is not built."""
+    if not _NATIVE:
+        try:
+            from . import _native
+            _NATIVE.append(_native)
+        except (ImportError, OSError):
+            _NATIVE.append(None)
+    return _NATIVE[0]
+
+
+def _addr(buf, offset: int = 0) -> int:
+    """Address of byte `offset` of a bytearray / numpy array (kept alive by the caller)."""
+    arr = buf if isinstance(buf, np.ndarray) else np.frombuffer(buf, dtype=np.uint8)
+    return arr.ctypes.data + offset
+
+
+def bgzf_read_into(path: str, out: np.ndarray, threads: int = 0) -> int:
+    """Inflate a whole BGZF file into `out` (uint8, large enough) on all cores through
+    pk_bgzf_inflate; returns the number of bytes produced.  OSError on damage / truncation,
+    ValueError if the contents do not fit."""
+    import ctypes
+    nat = _native_lib()
+    if nat is None:
+        raise ImportError("pykmer_b200.fasta.bgzf_read_into needs libpykmer_b200.so")
+    assert out.dtype == np.uint8 and out.flags.c_contiguous and out.flags.writeable
+    fill, comp, eof = 0, b"", False
+    with open(path, "rb") as fh:
+        while not (eof and not comp):
+            if not eof and len(comp) < (8 << 20):
+                blk = fh.read(32 << 20)
+                eof = not blk
+                comp += blk
+            used, made = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            cbuf = np.frombuffer(comp, dtype=np.uint8)
+            try:
+                nat.check(nat.lib.pk_bgzf_inflate(cbuf.ctypes.data if comp else None, len(comp),
+                                                  out.ctypes.data + fill, out.size - fill,
+                                                  ctypes.byref(used), ctypes.byref(made), threads))
+            except ValueError as exc:                      # PK_ERR_ARG: not BGZF / CRC / length
+                raise OSError(f"{path}: {exc}") from None
+            comp = comp[used.value:]
+            fill += made.value
+            if used.value == 0 and (eof or len(comp) >= (8 << 20)):
+                if comp and out.size - fill < (1 << 16):
+                    raise ValueError(f"{path}: more than the expected {out.size} bytes")
+                if comp:
+                    raise OSError(f"{path}: truncated BGZF block at end of file")
+    return fill
+
+
 class FastaStream:
     """Incremental FASTA -> stream converter.
 
@@ -132,9 +186,17 @@ class FastaStream:
     record's entry exists as soon as its header has been read.
     """
 
-    def __init__(self, path: str, chunk_bytes: int = 64 << 20):
+    def __init__(self, path: str, chunk_bytes: int = 64 << 20, threads: Optional[int] = None,
+                 native: Optional[bool] = None):
         self.path = path
         self.chunk_bytes = chunk_bytes
+        self.threads = threads or 0              # 0 = every core
+        # native = the two passes over the text (BGZF inflate, newline stripping) run in
+        # libpykmer_b200.so on all cores (csrc/ingest.cpp); False = this module's own Python
+        # path, which is also what every unusual block of text falls back to.
+        self.native = _native_lib() is not None if native is None else bool(native)
+        if self.native and _native_lib() is None:
+            raise ImportError("pykmer_b200.fasta: native ingest asked for, libpykmer_b200.so is missing")
         self.names: List[str] = []
         self.starts: List[int] = []
         self.lengths: List[int] = []
@@ -251,7 +313,156 @@ class FastaStream:
                 break
         th.join()
 
-    def pieces(self) -> Iterator[np.ndarray]:
+    # -- native path ------------------------------------------------------------------
+    def _native_text_chunks(self) -> Iterator[Tuple[bytearray, int, bool]]:
+        """(text, n, last): text[:n] is the next run of whole lines (it ends at a line terminator
+        unless last).  BGZF members are inflated on all cores straight into the buffer."""
+        import ctypes
+        nat = _native_lib()
+        bgzf = self.path.endswith((".gz", ".bgz")) and is_bgzf(self.path)
+        tail = b""
+        comp = b""
+        eof = False
+        with (open(self.path, "rb") if bgzf else open_binary(self.path)) as fh:
+            while True:
+                # a BGZF member inflates to at most 64 KiB: keep room for one beyond the tail
+                text = bytearray(len(tail) + (max(self.chunk_bytes, 1 << 16) if bgzf else self.chunk_bytes))
+                text[:len(tail)] = tail
+                fill = len(tail)
+                if bgzf:
+                    while True:
+                        if not eof and len(comp) < (8 << 20):
+                            blk = fh.read(max(1 << 20, self.chunk_bytes // 3))
+                            eof = not blk
+                            comp += blk
+                        used, made = ctypes.c_size_t(0), ctypes.c_size_t(0)
+                        cbuf = np.frombuffer(comp, dtype=np.uint8)
+                        nat.check(nat.lib.pk_bgzf_inflate(cbuf.ctypes.data if comp else None, len(comp),
+                                                          _addr(text, fill), len(text) - fill,
+                                                          ctypes.byref(used), ctypes.byref(made), self.threads))
+                        comp = comp[used.value:]
+                        fill += made.value
+                        if eof and not comp:
+                            break
+                        if used.value == 0:
+                            if len(text) - fill < (1 << 16):
+                                break                      # the buffer is full
+                            if eof:                        # room, no more input, yet no whole member
+                                raise OSError(f"{self.path}: truncated BGZF block at end of file")
+                    done = eof and not comp
+                else:
+                    got = fh.readinto(memoryview(text)[fill:])
+                    fill += got or 0
+                    done = not got
+                if done:
+                    yield text, fill, True
+                    return
+                cut = max(text.rfind(b"\n", 0, fill), text.rfind(b"\r", 0, fill))
+                if cut < 0:                                # no whole line yet: grow the tail
+                    tail = bytes(text[:fill])
+                    continue
+                tail = bytes(text[cut + 1:fill])
+                yield text, cut + 1, False
+
+    def _clean_into(self, text: bytearray, a: int, b: int, dst: np.ndarray, opos: int) -> int:
+        """Lines text[a:b] between two line-initial headers -> dst[opos:]; returns the new opos."""
+        import ctypes
+        if b <= a:
+            return opos
+        nat = _native_lib()
+        kept, flags = ctypes.c_size_t(0), ctypes.c_uint32(0)
+        nat.check(nat.lib.pk_fasta_clean(_addr(text, a), b - a, _addr(dst, opos), ctypes.byref(kept),
+                                         ctypes.byref(flags), self.threads))
+        if flags.value == 0:
+            if not self._open:                             # text before the first header (indexer.py:82)
+                return opos
+            n = kept.value
+            self.lengths[-1] += n
+            self._pos += n
+            return opos + n
+        # inner white space (maybe a header behind leading blanks) or non-ASCII bytes: this
+        # module's line-by-line path, which keeps the record table itself
+        out: List[bytes] = []
+        self._sequence_block(bytes(text[a:b]), out)
+        blob = b"".join(out)
+        dst[opos:opos + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        return opos + len(blob)
+
+    def _pieces_native(self, buffers=None) -> Iterator[np.ndarray]:
+        turn = 0
+        for text, n, last in self._prefetch(self._native_text_chunks()):
+            need = n + 16
+            dst = None
+            if buffers is not None:
+                dst = buffers[turn % len(buffers)]
+                turn += 1
+                if dst.size < need:                        # a line longer than the chunk: own array
+                    dst = None
+            if dst is None:
+                dst = np.empty(need, dtype=np.uint8)
+            opos = 0
+            cur = 0
+            p = text.find(b">", 0, n)
+            while p >= 0:
+                if p == 0 or text[p - 1] in (10, 13):
+                    opos = self._clean_into(text, cur, p, dst, opos)
+                    e1, e2 = text.find(b"\n", p, n), text.find(b"\r", p, n)
+                    end = min(x for x in (e1, e2, n) if x >= 0)
+                    if self._open:                         # close the previous record
+                        dst[opos] = SEPARATOR
+                        opos += 1
+                        self._pos += 1
+                    self.names.append(bytes(text[p + 1:end]).decode("utf-8").rstrip())
+                    self.starts.append(self._pos)
+                    self.lengths.append(0)
+                    self._open = True
+                    cur = end
+                    p = text.find(b">", end, n)
+                else:
+                    p = text.find(b">", p + 1, n)          # a '>' inside a sequence line: an invalid base
+            opos = self._clean_into(text, cur, n, dst, opos)
+            if last and self._open:
+                dst[opos] = SEPARATOR
+                opos += 1
+                self._pos += 1
+                self._open = False
+            if opos:
+                yield dst[:opos]
+
+    @staticmethod
+    def _prefetch(gen, depth: int = 2):
+        """Run a generator on a helper thread so that producing overlaps consuming."""
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=depth)
+        end = object()
+
+        def work():
+            try:
+                for item in gen:
+                    q.put(item)
+                q.put(end)
+            except BaseException as exc:                   # re-raised in the consumer
+                q.put(exc)
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        while True:
+            item = q.get()
+            if item is end:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+        th.join()
+
+    def pieces(self, buffers=None) -> Iterator[np.ndarray]:
+        """The cleaned stream piece by piece.  buffers: optional ring of uint8 numpy arrays (e.g.
+        views of pinned memory) of at least chunk_bytes + chunk_bytes/8 bytes each that the pieces
+        are written into in turn -- a piece is then only valid until its buffer comes round again."""
+        if self.native:
+            yield from self._pieces_native(buffers)
+            return
         tail = b""
         if True:
             for blk in self._prefetched_chunks():

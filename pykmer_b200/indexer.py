@@ -23,15 +23,23 @@ from .tools import Header
 
 
 def _write_table(path: str, table: np.ndarray, block: int = 64 << 20) -> str:
-    """Write the table over the (sparse) tmp file and return its sha256."""
-    h = hashlib.sha256()
+    """Write the table over the (sparse) tmp file and return its sha256 (the hash runs on a
+    second thread beside the writes; both release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
     mv = memoryview(table)
-    with open(path, "r+b") as fh:
+
+    def digest() -> str:
+        h = hashlib.sha256()
         for off in range(0, len(mv), block):
-            blk = mv[off:off + block]
-            fh.write(blk)
-            h.update(blk)
-    return h.hexdigest()
+            h.update(mv[off:off + block])
+        return h.hexdigest()
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        job = pool.submit(digest)
+        with open(path, "r+b") as fh:
+            for off in range(0, len(mv), block):
+                fh.write(mv[off:off + block])
+        return job.result()
 
 
 def create_fasta_index(project_name: str, sample_name: Optional[str], input_file: str,
@@ -54,26 +62,27 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
     header.init_index_tmp_file(overwrite=overwrite)
     t_start = time.perf_counter()
 
+    # off the critical path: the sha256 of the input file (tools.py:279) and the pinned buffer
+    # the table lands in are produced by helper threads while the genome is read and indexed
+    from concurrent.futures import ThreadPoolExecutor
+    from .tools import gen_checksum
+    helpers = ThreadPoolExecutor(max_workers=2)
+    input_sum = helpers.submit(gen_checksum, header.input_file_path)
+    out_buf = helpers.submit(dev.pinned_empty, header.data_size)
+
     fs = FastaStream(input_file, chunk_bytes=chunk_bytes)
     with dev.Indexer(kmer_len, device=device) as ix:
-        ring = [None, None]
-        turn = 0
-        bases = 0
-        for piece in fs.pieces():
-            n = int(piece.size)
-            if ring[turn] is None or ring[turn].numel() < n:
-                ix.sync()
-                ring[turn] = dev.pinned_empty(max(n, chunk_bytes + (chunk_bytes >> 3)))
-            elif turn == 0:
-                ix.sync()                 # both buffers may still be read by queued copies
-            buf = ring[turn]
-            buf.numpy()[:n] = piece
+        # the reader writes its pieces straight into two pinned buffers in turn; a piece is fed
+        # (pinned -> device, asynchronous) and the handle drained before its buffer comes round again
+        cap = chunk_bytes + (chunk_bytes >> 3) + (1 << 17)
+        ring = [dev.pinned_empty(cap) for _ in range(2)]
+        views = [r.numpy() for r in ring]
+        for piece in fs.pieces(buffers=views):
             ix.set_records(fs.starts)
-            ix.feed_host(buf[:n])
-            turn ^= 1
-            bases = sum(fs.lengths)
-            header.timer.update(bases)
-        out = dev.pinned_empty(header.data_size)
+            ix.feed_host(piece)
+            ix.sync()                     # the buffer may be rewritten from here on
+            header.timer.update(sum(fs.lengths))
+        out = out_buf.result()
         hist, st = ix.finalize(table_out=out)      # table windows stream out as they are committed
         flags = ix.record_flags() if fs.starts else np.zeros(0, dtype=np.uint8)
         table = out.numpy()
@@ -88,7 +97,8 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
     t_gpu = time.perf_counter()
     checksum = _write_table(header.index_tmp_file, table)
     t_write = time.perf_counter()
-    header.write_metadata_index_tmp_file(output_checksum=checksum)
+    header.write_metadata_index_tmp_file(output_checksum=checksum, input_checksum=input_sum.result())
+    helpers.shutdown()
     os.rename(header.index_tmp_file, header.index_file)          # indexer.py:412
     t_end = time.perf_counter()
     header.wall_seconds = {"ingest_and_gpu": t_gpu - t_start, "write_and_sha256_table": t_write - t_gpu,

@@ -254,9 +254,11 @@ class Header(HeaderVars):
         """The uint8[4^K] table of a .kin / .kin.bgz file."""
         path = index_file or self.index_file
         if path.endswith("." + self.COMP_EXT):
-            from .fasta import bgzf_chunks, is_bgzf
-            if is_bgzf(path):                       # independent blocks: inflate on all host cores
-                arr = np.frombuffer(b"".join(bgzf_chunks(path)), dtype=np.uint8)
+            from .fasta import bgzf_read_into, is_bgzf
+            if is_bgzf(path):                       # independent blocks: inflate on all host cores,
+                arr = np.empty(self.data_size, dtype=np.uint8)      # straight into the table
+                got = bgzf_read_into(path, arr)
+                assert got == self.data_size, f"{path}: {got} bytes, expected {self.data_size}"
             else:                                   # plain gzip stream, as the reference reads it
                 with gzip.open(path, "rb") as fz:
                     arr = np.frombuffer(fz.read(), dtype=np.uint8)
@@ -292,10 +294,11 @@ class Header(HeaderVars):
             self.update_stats(fhd)
 
     # -- metadata (tools.py:273-291, 366-401) ----------------------------------------------
-    def update_metadata(self, index_file: str, output_checksum: Optional[str] = None) -> None:
+    def update_metadata(self, index_file: str, output_checksum: Optional[str] = None,
+                        input_checksum: Optional[str] = None) -> None:
         self.input_file_size = os.path.getsize(self.input_file_path)
         self.input_file_ctime = os.path.getctime(self.input_file_path)
-        self.input_file_cheksum = gen_checksum(self.input_file_path)
+        self.input_file_cheksum = input_checksum or gen_checksum(self.input_file_path)
         self.output_file_size = os.path.getsize(index_file)
         self.output_file_ctime = os.path.getctime(index_file)
         self.output_file_cheksum = output_checksum or gen_checksum(index_file)
@@ -308,10 +311,10 @@ class Header(HeaderVars):
         self.creation_speed = self.timer.speed_ela
 
     def write_metadata_file(self, index_file: str, output_checksum: Optional[str] = None,
-                            recompute_stats: bool = False) -> None:
+                            recompute_stats: bool = False, input_checksum: Optional[str] = None) -> None:
         assert self.num_kmers          # tools.py:367-368: an input without k-mers is an error
         assert self.chromosomes
-        self.update_metadata(index_file, output_checksum)
+        self.update_metadata(index_file, output_checksum, input_checksum)
         if recompute_stats or self.hist is None:
             for fhd in self.open_file(index_file):
                 self.update_stats(fhd)
@@ -321,8 +324,9 @@ class Header(HeaderVars):
     def write_metadata_index_file(self) -> None:
         self.write_metadata_file(self.index_file)
 
-    def write_metadata_index_tmp_file(self, output_checksum: Optional[str] = None) -> None:
-        self.write_metadata_file(self.index_tmp_file, output_checksum)
+    def write_metadata_index_tmp_file(self, output_checksum: Optional[str] = None,
+                                      input_checksum: Optional[str] = None) -> None:
+        self.write_metadata_file(self.index_tmp_file, output_checksum, input_checksum=input_checksum)
 
     def read_metadata(self) -> None:
         with open(self.metadata_file, "rt") as fh:

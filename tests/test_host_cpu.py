@@ -45,10 +45,11 @@ def test_c_abi_exports_every_declared_symbol():
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "inputs", "*"))),
                          ids=lambda p: os.path.basename(p))
 @pytest.mark.parametrize("chunk", [64 << 20, 4096, 61, 5])
-def test_fasta_reader_matches_reference_text_rules(path, chunk):
+@pytest.mark.parametrize("native", [True, False], ids=["native", "python"])
+def test_fasta_reader_matches_reference_text_rules(path, chunk, native):
     recs = list(oracle.parse_records(path))
     want, starts, lengths, names = oracle.records_to_stream(recs)
-    fs = fasta.FastaStream(path, chunk_bytes=chunk)
+    fs = fasta.FastaStream(path, chunk_bytes=chunk, native=native)
     got = fs.read_all()
     assert fs.names == names and fs.lengths == lengths and fs.starts == starts.tolist()
     assert np.array_equal(got, want)
@@ -64,18 +65,76 @@ def test_fasta_reader_edge_cases(tmp_path, text):
     open(p, "wb").write(text)
     recs = list(oracle.parse_records(p))
     want, starts, lengths, names = oracle.records_to_stream(recs)
-    for chunk in (1 << 20, 3):
-        fs = fasta.FastaStream(p, chunk_bytes=chunk)
+    for chunk, native in ((1 << 20, True), (3, True), (1 << 20, False), (3, False)):
+        fs = fasta.FastaStream(p, chunk_bytes=chunk, native=native)
         got = fs.read_all()
         assert fs.names == names and fs.lengths == lengths and fs.starts == starts.tolist()
         assert np.array_equal(got, want)
 
 
-def test_fasta_reader_rejects_non_ascii_sequence(tmp_path):
+@pytest.mark.parametrize("native", [True, False], ids=["native", "python"])
+def test_fasta_reader_rejects_non_ascii_sequence(tmp_path, native):
     p = str(tmp_path / "bad.fa")
     open(p, "wb").write(b">a\nAC\xc3\xa9GT\n")
     with pytest.raises(ValueError):
-        fasta.FastaStream(p).read_all()
+        fasta.FastaStream(p, native=native).read_all()
+
+
+def test_native_ingest_equals_python_ingest_on_messy_bgzf(tmp_path):
+    """csrc/ingest.cpp (parallel BGZF inflate + newline stripping) against this module's own
+    Python path: CRLF / lone CR / blank lines / tabs / hidden headers / '>' inside sequence, several
+    thread counts and chunk sizes, pieces written into a caller's buffer ring."""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
+    lines = [b"junk before the first header", b""]
+    for r in range(40):
+        lines.append(b">rec%d some description " % r)
+        for _ in range(int(rng.integers(0, 400))):
+            body = acgt[rng.integers(0, len(acgt), size=int(rng.integers(0, 90)))].tobytes()
+            roll = rng.random()
+            if roll < 0.02:
+                body = b"  " + body + b"\t"
+            elif roll < 0.03:
+                body = body[:5] + b">" + body[5:]
+            elif roll < 0.035:
+                body = b" >hidden%d" % r
+            lines.append(body)
+    eols = [b"\n", b"\r\n", b"\r"]
+    text = b"".join(l + eols[int(rng.integers(0, 3))] for l in lines)
+    path = str(tmp_path / "messy.fa.bgz")
+    open(path, "wb").write(synth.bgzf_compress(text, level=1))
+    ref = fasta.FastaStream(path, native=False)
+    want = ref.read_all()
+    assert len(ref.names) > 40                             # hidden headers were found
+    for chunk, threads in ((64 << 20, 0), (1 << 16, 3), (7001, 1)):
+        fs = fasta.FastaStream(path, chunk_bytes=chunk, threads=threads, native=True)
+        ring = [np.empty(max(chunk, 1 << 16) * 2 + 64, dtype=np.uint8) for _ in range(2)]
+        got = np.concatenate([p.copy() for p in fs.pieces(buffers=ring)])
+        assert np.array_equal(got, want)
+        assert fs.names == ref.names and fs.starts == ref.starts and fs.lengths == ref.lengths
+    plain = str(tmp_path / "messy.fa")
+    open(plain, "wb").write(text)
+    assert np.array_equal(fasta.FastaStream(plain, chunk_bytes=5000, native=True).read_all(), want)
+    gz = str(tmp_path / "messy.fa.gz")                     # ordinary gzip: not BGZF
+    open(gz, "wb").write(gzip.compress(text))
+    assert np.array_equal(fasta.FastaStream(gz, native=True).read_all(), want)
+
+
+def test_native_bgzf_inflate_rejects_damage(tmp_path):
+    raw = b">a\n" + b"ACGT" * 100_000 + b"\n"
+    blob = bytearray(synth.bgzf_compress(raw, level=1))
+    good = str(tmp_path / "ok.fa.bgz")
+    open(good, "wb").write(bytes(blob))
+    assert fasta.FastaStream(good, native=True).read_all().size == 400_001
+    blob[len(blob) // 2] ^= 0x55                           # flip bits inside a deflate stream
+    bad = str(tmp_path / "bad.fa.bgz")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises((OSError, ValueError)):
+        fasta.FastaStream(bad, native=True).read_all()
+    cut = str(tmp_path / "cut.fa.bgz")
+    open(cut, "wb").write(synth.bgzf_compress(raw, level=1)[:-40])
+    with pytest.raises(OSError):
+        fasta.FastaStream(cut, native=True).read_all()
 
 
 def test_bgzf_writer_is_readable_as_gzip(tmp_path):
