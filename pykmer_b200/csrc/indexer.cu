@@ -1326,6 +1326,8 @@ struct pk_indexer {
     uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
     bool flush_smem = false;                   // second-level shared-memory flush (else L2 counters)
     bool count8 = false;                       // byte windows: the L2 window holds 8-bit lanes (k_window_count8)
+    int cnt8_blocks_per_sm = 4;                // grid of k_window_count8: K=17 step 21.1 / 18.7 / 20.1 / 20.3 ms at 2 / 4 / 8 / 16
+    int cnt_blocks_per_sm = 12;                // grid of k_window_count: K=15 step 9.86 / 9.77 / 9.43 / 9.45 ms at 6 / 8 / 12 / 16
     size_t scratch_bytes = 0;
     OvfTable ovf = {nullptr, nullptr, nullptr, nullptr, 0};
     bool sub_smem_set = false;
@@ -1433,7 +1435,7 @@ static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table
         ix->launches++;
         if (ix->nseg) {
             prof_scope ps(ix, st, PROF_WINDOW_COUNT);
-            k_window_count8<true><<<ix->sm_count * 8, 256, 0, st>>>(
+            k_window_count8<true><<<ix->sm_count * ix->cnt8_blocks_per_sm, 256, 0, st>>>(
                 src, seg_off(ix, 0), seg_cnt(ix, 0), ix->nseg, ix->nbuckets, b, reinterpret_cast<uint32_t *>(tw),
                 nvec * 4, ix->ovf, ix->counters + 1);
             ix->launches++;
@@ -1471,7 +1473,7 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
     if (with_stats)
         PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
-    const int grid = ix->sm_count * 8;
+    const int grid = ix->sm_count * (ix->count8 ? ix->cnt8_blocks_per_sm : ix->cnt_blocks_per_sm);
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
         if (ix->nseg) {
@@ -1822,6 +1824,14 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
     const char *fe = getenv("PYKMER_B200_FLUSH");
     ix->flush_smem = fe && strcmp(fe, "smem") == 0;
     ix->count8 = fe ? strcmp(fe, "byte") == 0 : kmer_len >= 17;
+    if (const char *ge = getenv("PYKMER_B200_CNT8_GRID")) {
+        const int v = atoi(ge);
+        if (v >= 1 && v <= 32) ix->cnt8_blocks_per_sm = v;
+    }
+    if (const char *ge = getenv("PYKMER_B200_CNT_GRID")) {
+        const int v = atoi(ge);
+        if (v >= 1 && v <= 32) ix->cnt_blocks_per_sm = v;
+    }
     uint32_t win_log2 = ix->count8 ? 26 : 24;
     if (const char *env = getenv("PYKMER_B200_WINDOW_LOG2")) {
         const int v = atoi(env);
