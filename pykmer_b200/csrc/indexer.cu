@@ -1321,12 +1321,13 @@ struct pk_indexer {
     size_t est_min = (size_t)1 << 24;          // ... for feeds of at least this many bases
     uint32_t est_test = 0;                     // test hook: 1 = as if over budget, 2 = reserve too little room
     uint32_t *scratch = nullptr;               // one window of 32-bit counters
-    unsigned long long *bins_part = nullptr;   // [4 * sm_count][256] partial histograms
+    unsigned long long *bins_part = nullptr;   // [8 * sm_count][256] partial histograms
     uint32_t *pool2 = nullptr;                 // smem flush: entries regrouped by sub-bucket
     uint32_t *sub = nullptr;                   // smem flush: 3 x [64 * 512] counts, offsets, cursors
     bool flush_smem = false;                   // second-level shared-memory flush (else L2 counters)
     bool count8 = false;                       // byte windows: the L2 window holds 8-bit lanes (k_window_count8)
     int cnt8_blocks_per_sm = 4;                // grid of k_window_count8: K=17 step 21.1 / 18.7 / 20.1 / 20.3 ms at 2 / 4 / 8 / 16
+    int commit_blocks_per_sm = 4, zero_blocks_per_sm = 4;   // k_window_commit (K=15: 1.68 / 1.47 / 1.56 ms at 2 / 4 / 8) and k_window_zero grids
     int cnt_blocks_per_sm = 12;                // grid of k_window_count: K=15 step 9.86 / 9.77 / 9.43 / 9.45 ms at 6 / 8 / 12 / 16
     size_t scratch_bytes = 0;
     OvfTable ovf = {nullptr, nullptr, nullptr, nullptr, 0};
@@ -1429,7 +1430,9 @@ static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table
         uint8_t *tw = ix->table + (size_t)b * win;
         {
             prof_scope ps(ix, st, PROF_WINDOW_COMMIT);
-            const int zgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * 4, (nvec + 255) / 256));
+            // 15 us per 64 MiB whatever the grid (2..16 blocks per SM) and also with cudaMemsetAsync:
+            // the previous window's dirty lines leave L2 for DRAM at the same time
+            const int zgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * ix->zero_blocks_per_sm, (nvec + 255) / 256));
             k_window_zero<<<zgrid, 256, 0, st>>>(reinterpret_cast<uint4 *>(tw), nvec);
         }
         ix->launches++;
@@ -1469,9 +1472,9 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = window_launch_attr(ix, attr);
-    const int rows = ix->sm_count * 4;                      // commit grid = rows of partial bins
+    const int rows = ix->sm_count * ix->commit_blocks_per_sm;   // commit grid = rows of partial bins
     if (with_stats)
-        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
+        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)8 * ix->sm_count * 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
     const int grid = ix->sm_count * (ix->count8 ? ix->cnt8_blocks_per_sm : ix->cnt_blocks_per_sm);
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
@@ -1516,7 +1519,7 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
 
 // common end of a flush: join the table copies, reduce the histogram, recycle the buffers
 static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
-    const int rows = ix->sm_count * 4;
+    const int rows = ix->sm_count * 8;                      // every row of bins_part (unused ones are zero)
     if (table_host) {
         PK_CUDA(cudaEventRecord(ix->committed[0], ix->copy_stream));
         PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
@@ -1556,7 +1559,7 @@ static int indexer_flush_smem(pk_indexer *ix, cudaStream_t st, bool with_stats, 
     const size_t win = (size_t)1 << ix->win_log2;
     const int rows = ix->sm_count * 4;                      // >= kSubs rows of partial bins
     if (with_stats)
-        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)rows * 256 * sizeof(unsigned long long), st));
+        PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)8 * ix->sm_count * 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
     const uint32_t *src = ix->pool_ext ? ix->pool_ext : ix->pool;
     constexpr uint32_t kGroup = 64;                         // windows regrouped per pass over the pool
@@ -1828,6 +1831,14 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         const int v = atoi(ge);
         if (v >= 1 && v <= 32) ix->cnt8_blocks_per_sm = v;
     }
+    if (const char *ge = getenv("PYKMER_B200_COMMIT_GRID")) {
+        const int v = atoi(ge);
+        if (v >= 1 && v <= 8) ix->commit_blocks_per_sm = v;
+    }
+    if (const char *ge = getenv("PYKMER_B200_ZERO_GRID")) {
+        const int v = atoi(ge);
+        if (v >= 1 && v <= 32) ix->zero_blocks_per_sm = v;
+    }
     if (const char *ge = getenv("PYKMER_B200_CNT_GRID")) {
         const int v = atoi(ge);
         if (v >= 1 && v <= 32) ix->cnt_blocks_per_sm = v;
@@ -1894,7 +1905,7 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
         step(cudaMalloc(&ix->seg, seg_bytes));
         step(cudaMalloc(&ix->cursor, 256));
         if (mode == PK_MODE_PARTITION) {
-            step(cudaMalloc(&ix->bins_part, (size_t)4 * ix->sm_count * 256 * sizeof(unsigned long long)));
+            step(cudaMalloc(&ix->bins_part, (size_t)8 * ix->sm_count * 256 * sizeof(unsigned long long)));
             if (ix->flush_smem) {
                 step(cudaMalloc(&ix->pool2, cap * sizeof(uint32_t)));
                 step(cudaMalloc(&ix->sub, (size_t)3 * 64 * kSubs * sizeof(uint32_t)));
