@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256) k_feed_settle(uint32_t *__restrict__ cnt,
 // window by window, and written out as contiguous runs into the segments pass 1 sized.
 // entry = (run length - 1) << kEntShift | offset inside the window.
 template <bool WIDE, bool FULL>
-__global__ void __launch_bounds__(kScanThreads, WIDE ? 2 : 4) k_scan_scatter(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanParams p) {
     if (p.run_if && *p.run_if == 0u) return;
     if (p.seg_cap && p.ctl[1] != 0u) return;               // over budget already: straight to the exact path
     extern __shared__ uint32_t sm[];
