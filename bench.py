@@ -561,6 +561,20 @@ def run_indexer(args, rank, local_rank, world):
                 "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
                 "kernel_ms_by_class": {c: round(v[0], 4) for c, v in prof.items()},
                 "mode": {1: "direct", 2: "partition"}.get(mode, str(mode)), "windows": windows}
+    if dom in ("window_count", "scan_count_direct") and big:
+        # the counting kernels are atomic-bound, not byte-bound: the second denominator is the random
+        # atomic rate measured on this chip (tools/microbench*.cu, profiles/r01_microbench_b200.txt,
+        # profiles/r01c_microbench2_b200.txt) for the operation the kernel issues
+        op, peak_ops = (("red.add.u32, L2-resident 64 MiB window", 191.07e9) if (dom == "window_count" and K < 17) else
+                        ("atom.add.u32 with return on packed bytes, L2-resident 64 MiB window", 128.0e9)
+                        if dom == "window_count" else ("byte compare-and-swap, DRAM-resident table", 19.46e9))
+        rate = n_k_local / (dom_ms * 1e-3)
+        roofline["atomic"] = {"op": op, "achieved_per_s": rate, "peak_per_s": peak_ops, "frac": rate / peak_ops,
+                              "peak_source": "measured on this pool's B200 (tools/microbench.cu, microbench2.cu)"}
+        if dom == "window_count":
+            roofline["note"] = ("frac > 1 against HBM is the design: SURVEY 8d credits every counted k-mer with 64 B of "
+                                "DRAM traffic (sector read + write-back), which counting in an L2-resident window "
+                                "avoids; see traffic (ncu dram bytes per launch) and the atomic fraction")
 
     # end to end through the C ABI with HOST buffers: pinned stream in, table + stats out
     e2e = None
