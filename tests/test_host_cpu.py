@@ -251,3 +251,29 @@ def test_bgzf_module_roundtrip_and_kin_bgz_reader(tmp_path):
     assert not fasta.is_bgzf(out) and np.array_equal(h.read_table(), table)
     assert bgzf.decompress_file(bgzf.compress_file(kin, dst=str(tmp_path / "x.bgz")), str(tmp_path / "x.kin"))
     assert open(tmp_path / "x.kin", "rb").read() == table.tobytes()
+
+
+def test_bgz_table_roundtrip_through_native_reader(tmp_path):
+    """.kin -> bgzf.compress_file -> Header.read_table (pk_bgzf_inflate straight into the table array)
+    and the block-parallel Python reader give the bytes back; a table of the wrong size is refused."""
+    from pykmer_b200 import bgzf
+    K = 9
+    rng = np.random.default_rng(3)
+    table = (rng.random(4 ** K) < 0.2).astype(np.uint8) * rng.integers(1, 256, size=4 ** K).astype(np.uint8)
+    fa = str(tmp_path / "s.fa")
+    open(fa, "w").close()
+    kin = fa + f".{K:02d}.kin"
+    table.tofile(kin)
+    bgz = bgzf.compress_file(kin, level=1)
+    assert bgz == kin + ".bgz" and fasta.is_bgzf(bgz)
+    h = Header("p", input_file=fa, kmer_len=K)
+    assert np.array_equal(h.read_table(bgz), table)
+    assert np.array_equal(h.read_table(kin), table)
+    assert bgzf.read_all(bgz) == table.tobytes()
+    out = np.empty(table.size + 100, dtype=np.uint8)
+    assert fasta.bgzf_read_into(bgz, out, threads=2) == table.size and np.array_equal(out[:table.size], table)
+    with pytest.raises(ValueError):
+        fasta.bgzf_read_into(bgz, np.empty(table.size - 70_000, dtype=np.uint8))
+    wrong = Header("p", input_file=fa, kmer_len=K + 2)
+    with pytest.raises((AssertionError, ValueError)):
+        wrong.read_table(bgz)
