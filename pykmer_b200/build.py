@@ -55,23 +55,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-MICROBENCH_SRC = os.path.join(os.path.dirname(HERE), "tools", "microbench.cu")
-MICROBENCH_BIN = os.path.join(os.path.dirname(HERE), "tools", "microbench")
+TOOLS = os.path.join(os.path.dirname(HERE), "tools")
+MICROBENCHES = ("microbench", "microbench2")
 
 
 def build_microbench(force: bool = False) -> str:
-    """tools/microbench: raw atomic / popcount / streaming rates of the box (not product code)."""
-    if not force and os.path.exists(MICROBENCH_BIN) and \
-            os.path.getmtime(MICROBENCH_BIN) >= os.path.getmtime(MICROBENCH_SRC):
-        return MICROBENCH_BIN
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-           "-o", MICROBENCH_BIN, MICROBENCH_SRC]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout)
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
-    return MICROBENCH_BIN
+    """tools/microbench, tools/microbench2: raw atomic / popcount / streaming rates of the box
+    (measurement tools, not product code)."""
+    out = ""
+    for name in MICROBENCHES:
+        src, out = os.path.join(TOOLS, name + ".cu"), os.path.join(TOOLS, name)
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+            continue
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+               "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-o", out, src]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout)
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+    return out
 
 
 if __name__ == "__main__":

@@ -246,9 +246,31 @@ class Header(HeaderVars):
             fh.seek(self.max_size - 1)
             fh.write(b"\0")
 
+    def init_index_file(self, overwrite: bool = False, mode: str = "r+b") -> None:
+        """tools.py:344-346 (the reference's own call passes self twice and cannot run)."""
+        self._init_clean(overwrite=overwrite)
+        self.init_file(self.index_file_root, mode=mode)
+
     def init_index_tmp_file(self, overwrite: bool = False, mode: str = "r+b") -> None:
         self._init_clean(overwrite=overwrite)
         self.init_file(self.index_tmp_file, mode=mode)
+
+    # -- memmap views (tools.py:240-243, 353-363): host access to the raw table ----------
+    def _get_mmap(self, fhd, offset: int = 0, mode: str = "r+") -> Iterator[np.memmap]:
+        view = np.memmap(fhd, dtype=np.uint8, mode=mode, offset=offset, shape=(self.data_size,))
+        yield view
+        del view
+
+    def get_array_from_fhd(self, fhd, mode: str = "r+") -> Iterator[np.memmap]:
+        yield from self._get_mmap(fhd, offset=0, mode=mode)
+
+    def get_array_from_index_file(self, fhd_mode: str = "r+b", mm_mode: str = "r+") -> Iterator[np.memmap]:
+        for fhd in self.open_index_file(mode=fhd_mode):
+            yield from self.get_array_from_fhd(fhd, mode=mm_mode)
+
+    def get_array_from_index_tmp_file(self, fhd_mode: str = "r+b", mm_mode: str = "r+") -> Iterator[np.memmap]:
+        for fhd in self.open_index_tmp_file(mode=fhd_mode):
+            yield from self.get_array_from_fhd(fhd, mode=mm_mode)
 
     def read_table(self, index_file: Optional[str] = None) -> np.ndarray:
         """The uint8[4^K] table of a .kin / .kin.bgz file."""
@@ -357,6 +379,9 @@ class Header(HeaderVars):
     def check_data_index(self) -> None:
         self.check_data_file(self.index_file)
 
+    def check_data_index_tmp(self) -> None:
+        self.check_data_file(self.index_tmp_file)
+
     # -- distance (tools.py:439-493), computed on the GPU ------------------------------------
     def calculate_distance(self, other: "Header", min_count: int = HeaderVars.DEFAULT_MIN_COUNT,
                            max_count: int = HeaderVars.DEFAULT_MAX_COUNT,
@@ -366,6 +391,18 @@ class Header(HeaderVars):
         from . import device
         assert self.data_size == other.data_size
         return device.pair_counts(self.read_table(), other.read_table(), min_count, max_count)
+
+    def calculate_distance2(self, other: "Header", min_count: int = HeaderVars.DEFAULT_MIN_COUNT,
+                            max_count: int = HeaderVars.DEFAULT_MAX_COUNT) -> Tuple[int, int, int]:
+        """The reference's entry-by-entry restatement of calculate_distance (tools.py:495-512,
+        unused there).  Same three sums, so it is the same kernel here."""
+        return self.calculate_distance(other, min_count=min_count, max_count=max_count)
+
+    def __iter__(self) -> Iterator[int]:
+        """The table's bytes as ints, .bgz inflated on the way (tools.py:527-533)."""
+        for fhd in self.open_index_file(mode="rb"):
+            for blk in iter(lambda: fhd.read(max(self._buffer_size, 1 << 16)), b""):
+                yield from blk
 
     def to_dict(self, lean: bool = False) -> Dict[str, Any]:
         keys = self.HEADER_FIXED + self.HEADER_DATA

@@ -372,6 +372,11 @@ def test_merger_cli_writes_reference_files(env, tmp_path):
     # one pair through the mirror of merger.calculate_distance
     assert merger.calculate_distance(kins[0], kins[1], 2, 10) == \
         env["oracle"].pair_counts(samples["tables"][0], samples["tables"][1], 2, 10)
+    # and through Header.calculate_distance2 (tools.py:495-512) 
+    from pykmer_b200.tools import Header
+    h0, h1 = Header("p", index_file=kins[0]), Header("p", index_file=kins[1])
+    assert h0.calculate_distance2(h1, 2, 10) == h0.calculate_distance(h1, 2, 10) == \
+        env["oracle"].pair_counts(samples["tables"][0], samples["tables"][1], 2, 10)
 
 
 def test_synth_table_kernel_matches_numpy(env):

@@ -196,6 +196,29 @@ def test_init_tmp_file_is_sparse_and_overwrite_rule(tmp_path):
     assert not os.path.exists(h.index_file_root)
 
 
+def test_header_memmap_views_and_byte_iterator(tmp_path):
+    """tools.py:240-243,344-363,527-533: init_index_file, the memmap accessors and __iter__
+    (which inflates a .kin.bgz on the way, tools.py:296-302)."""
+    from pykmer_b200 import bgzf
+    K = 5
+    f = str(tmp_path / "y.fa")
+    h = Header("p", input_file=f, kmer_len=K)
+    h.init_index_file(overwrite=True)
+    assert os.path.getsize(h.index_file_root) == 4 ** K
+    table = synth.synth_table(1, K)
+    for arr in h.get_array_from_index_file():
+        assert arr.shape == (4 ** K,) and arr.dtype == np.uint8 and not arr.any()
+        arr[:] = table
+        arr.flush()
+    assert np.array_equal(np.fromfile(h.index_file_root, dtype=np.uint8), table)
+    assert list(h) == table.tolist()
+    h.init_file(h.index_tmp_file)
+    for arr in h.get_array_from_index_tmp_file(fhd_mode="rb", mm_mode="r"):
+        assert arr.size == 4 ** K and not arr.any()
+    bgzf.compress_file(h.index_file_root, level=6)
+    assert h.index_file.endswith(".kin.bgz") and list(h) == table.tolist()
+
+
 def test_timer_and_checksum(tmp_path):
     t = Timer()
     t.update(1000)
