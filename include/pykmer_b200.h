@@ -225,6 +225,15 @@ int pk_bgzf_inflate(const uint8_t *comp, size_t comp_len, uint8_t *out, size_t o
                     size_t *consumed, size_t *produced, int threads);
 int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_out, uint32_t *flags,
                    int threads);
+/* pk_bgzf_deflate: the output side -- what the documented workflow does with the external
+ * `bgzip -l 9` after every indexer run (README.md:26,261-269; data/README.md:24) and what the
+ * merger reads back (tools.py:296-302).  src[0, n) becomes ceil(n / 0xFF00) independent BGZF
+ * members, deflated on `threads` threads (0 = all cores) and written back to back into
+ * out[0, *produced); out_cap >= ceil(n / 0xFF00) * 65536.  No EOF member is appended (the
+ * caller writes it once per file).  member_sizes (may be NULL) receives each member's
+ * compressed size: the material of a .gzi index (gzireader.py:12-19). */
+int pk_bgzf_deflate(const uint8_t *src, size_t n, uint8_t *out, size_t out_cap, size_t *produced,
+                    uint32_t *member_sizes, int level, int threads);
 
 /* Deterministic synthetic count table (benchmark input):
  * entries [lo, hi) of sample `sample`, bit-identical to pykmer_b200/synth.py. */

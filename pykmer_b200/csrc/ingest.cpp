@@ -201,3 +201,73 @@ PK_API int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_
     run(compact);
     return PK_OK;
 }
+
+// ---------------------------------------------------------------------------------- writer
+// The output side: the documented workflow runs `bgzip -l 9` over every
+// .kin (README.md:26,261-269; data/README.md:24) and the merger then reads the .kin.bgz.  A BGZF
+// file is a chain of independent gzip members of at most 0xFF00 input bytes, so the members of
+// one batch are deflated on all cores into fixed 64 KiB slots and then closed up in order.
+//
+// src[0, n) -> whole members in out[0, *produced) (no EOF member: the caller appends it once,
+// at the end of the file).  out_cap >= ceil(n / 0xFF00) * 65536.  member_sizes, when not NULL,
+// receives the compressed size of each of the ceil(n / 0xFF00) members -- what a .gzi index
+// (gzireader.py:12-19: pairs of compressed / uncompressed block offsets) is made of.
+PK_API int pk_bgzf_deflate(const uint8_t *src, size_t n, uint8_t *out, size_t out_cap, size_t *produced,
+                           uint32_t *member_sizes, int level, int threads) {
+    constexpr size_t kIn = 0xFF00, kSlot = 65536, kHead = 18, kTail = 8;
+    PK_REQUIRE(produced != nullptr, "pk_bgzf_deflate: NULL output");
+    PK_REQUIRE(n == 0 || (src != nullptr && out != nullptr), "pk_bgzf_deflate: NULL buffer");
+    PK_REQUIRE(level >= 0 && level <= 9, "pk_bgzf_deflate: level %d outside 0..9", level);
+    *produced = 0;
+    const size_t nblk = (n + kIn - 1) / kIn;
+    if (nblk == 0) return PK_OK;
+    PK_REQUIRE(out_cap / kSlot >= nblk, "pk_bgzf_deflate: destination holds %zu bytes, %zu members need %zu",
+               out_cap, nblk, nblk * kSlot);
+    std::vector<uint32_t> sizes(nblk, 0);
+    const int nt = thread_count(threads, nblk);
+    std::atomic<size_t> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad.store(1); return; }
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nblk || bad.load()) break;
+            const uint8_t *in = src + i * kIn;
+            const size_t len = i + 1 == nblk ? n - i * kIn : kIn;
+            uint8_t *slot = out + i * kSlot;
+            deflateReset(&zs);
+            zs.next_in = const_cast<Bytef *>(in);
+            zs.avail_in = (uInt)len;
+            zs.next_out = slot + kHead;
+            zs.avail_out = (uInt)(kSlot - kHead - kTail);
+            if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad.store(2); break; }
+            const size_t payload = kSlot - kHead - kTail - zs.avail_out;
+            const size_t total = kHead + payload + kTail;
+            static const uint8_t head[16] = {0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 'B', 'C', 2, 0};
+            memcpy(slot, head, 16);
+            slot[16] = (uint8_t)((total - 1) & 0xFF);
+            slot[17] = (uint8_t)((total - 1) >> 8);
+            const uint32_t crc = (uint32_t)crc32(0L, in, (uInt)len), isize = (uint32_t)len;
+            memcpy(slot + kHead + payload, &crc, 4);                 // little endian hosts only
+            memcpy(slot + kHead + payload + 4, &isize, 4);
+            sizes[i] = (uint32_t)total;
+        }
+        deflateEnd(&zs);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (bad.load())
+        return pk_set_error(PK_ERR_ARG, "pk_bgzf_deflate: zlib %s", bad.load() == 1 ? "could not start" : "overran a 64 KiB member");
+    size_t opos = 0;                                                 // close the gaps, in order
+    for (size_t i = 0; i < nblk; i++) {
+        if (opos != i * kSlot) memmove(out + opos, out + i * kSlot, sizes[i]);
+        opos += sizes[i];
+        if (member_sizes) member_sizes[i] = sizes[i];
+    }
+    *produced = opos;
+    return PK_OK;
+}

@@ -300,3 +300,74 @@ def test_bgz_table_roundtrip_through_native_reader(tmp_path):
     wrong = Header("p", input_file=fa, kmer_len=K + 2)
     with pytest.raises((AssertionError, ValueError)):
         wrong.read_table(bgz)
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_bgzf_writer_native_and_python_paths(tmp_path, native):
+    """pk_bgzf_deflate (all cores, csrc/ingest.cpp) and the zlib thread pool write files that gzip
+    (the reference's reader, tools.py:296-302) gives back byte for byte; sizes around the 0xFF00
+    member boundary, several batches, every level the workflow uses (bgzip -l 9, README.md:26)."""
+    from pykmer_b200 import bgzf
+    rng = np.random.default_rng(7)
+    for n, level, batch in ((0, 6, 4), (1, 9, 4), (0xFF00 - 1, 1, 4), (0xFF00, 6, 4), (0xFF00 + 1, 9, 4),
+                            (5 * 0xFF00 + 123, 9, 2), (300_000, 0, 3)):
+        raw = (rng.integers(0, 256, n, dtype=np.uint8) * (rng.random(n) < 0.2)).astype(np.uint8).tobytes()
+        src = str(tmp_path / f"t{n}.kin")
+        open(src, "wb").write(raw)
+        out = bgzf.compress_file(src, level=level, batch=batch, index=True, native=native, threads=3)
+        blob = open(out, "rb").read()
+        assert blob.endswith(bgzf.EOF_BLOCK) and gzip.decompress(blob) == raw
+        assert bgzf.read_all(out) == raw
+        # the index: one entry per data member, first implied; it agrees with the headers
+        assert bgzf.read_index(out + ".gzi") == (bgzf.scan_index(out) or [(0, 0)])
+        assert len(bgzf.read_index(out + ".gzi")) == max(1, -(-n // 0xFF00))
+
+
+def test_bgzf_native_writer_equals_python_writer(tmp_path):
+    from pykmer_b200 import bgzf
+    table = synth.synth_table(4, 9)
+    src = str(tmp_path / "s.09.kin")
+    table.tofile(src)
+    a = bgzf.compress_file(src, dst=src + ".a.bgz", level=9, native=True)
+    b = bgzf.compress_file(src, dst=src + ".b.bgz", level=9, native=False)
+    assert open(a, "rb").read() == open(b, "rb").read()          # same zlib, same members
+
+
+def test_gzi_index_layout_and_range_reads(tmp_path, capsys):
+    """.gzi layout (gzireader.py:12-19): uint64 count, then (compressed, uncompressed) offset pairs
+    of every member after the first; read_range inflates only the members a slice needs."""
+    import struct
+    from pykmer_b200 import bgzf
+    K = 9
+    table = synth.synth_table(5, K)
+    src = str(tmp_path / f"s.fa.{K:02d}.kin")
+    table.tofile(src)
+    out = bgzf.compress_file(src, level=6, index=True)
+    blob = open(out + ".gzi", "rb").read()
+    (count,) = struct.unpack_from("<Q", blob)
+    nblk = -(-table.size // 0xFF00)
+    assert count == nblk - 1 and len(blob) == 8 + 16 * count
+    pairs = np.frombuffer(blob, dtype="<u8", offset=8).reshape(-1, 2)
+    assert np.array_equal(pairs[:, 1], np.arange(1, nblk, dtype=np.uint64) * 0xFF00)
+    comp = open(out, "rb").read()
+    for c, _ in pairs:                                           # every offset is a member header
+        assert comp[int(c):int(c) + 4] == b"\x1f\x8b\x08\x04"
+    os.remove(out + ".gzi")
+    assert bgzf.build_index(out) == out + ".gzi" and open(out + ".gzi", "rb").read() == blob
+    for lo, hi in ((0, 0), (0, 1), (0, table.size), (0xFF00 - 1, 0xFF00 + 1), (0xFF00, 2 * 0xFF00),
+                   (123_456, 200_000), (table.size - 5, table.size), (table.size // 4, table.size // 2)):
+        assert np.array_equal(bgzf.read_range(out, lo, hi), table[lo:hi]), (lo, hi)
+    os.remove(out + ".gzi")                                      # falls back to the member headers
+    assert np.array_equal(bgzf.read_range(out, 70_000, 140_000), table[70_000:140_000])
+    with pytest.raises(OSError):
+        bgzf.read_range(out, table.size - 5, table.size + 5)
+    bgzf.build_index(out)
+    bgzf.print_index(out + ".gzi")
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == f"number_entries: {count:15,d}" and lines[1] == f"filesize      : {len(comp):15,d}"
+    assert lines[2] == f"pos: {0:15,d} compressed_offset {int(pairs[0, 0]):15,d} uncompressed_offset {0xFF00:15,d}"
+    assert len(lines) == count + 4
+    with open(out + ".gzi", "wb") as fh:
+        fh.write(blob[:-3])
+    with pytest.raises(OSError):
+        bgzf.read_index(out + ".gzi")
