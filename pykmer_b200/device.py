@@ -24,6 +24,24 @@ def pinned_empty(nbytes: int) -> torch.Tensor:
     return torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
 
 
+def device_scope(device: int):
+    """`with device_scope(d):` -- allocations and launches inside go to GPU d."""
+    return torch.cuda.device(device)
+
+
+def zeros(shape, dtype=torch.int32) -> torch.Tensor:
+    return torch.zeros(shape, dtype=dtype, device="cuda")
+
+
+def upload(t: torch.Tensor, non_blocking: bool = False) -> torch.Tensor:
+    """CPU tensor (ideally pinned) -> current GPU; a CUDA tensor passes through."""
+    return t if t.is_cuda else t.to("cuda", non_blocking=non_blocking)
+
+
+def stream_sync() -> None:
+    torch.cuda.current_stream().synchronize()
+
+
 def to_device_u8(arr, device: Optional[int] = None) -> torch.Tensor:
     """uint8 numpy array / tensor -> contiguous CUDA tensor (torch does the copy)."""
     if isinstance(arr, torch.Tensor):

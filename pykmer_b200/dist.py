@@ -26,6 +26,38 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def init_from_env() -> Tuple[int, int, int]:
+    """-> (rank, world, local device).  Under torchrun (WORLD_SIZE > 1) joins the job's process
+    group -- NCCL, one rank per GPU; PYKMER_B200_DIST_BACKEND=gloo lets the CPU tests and a
+    single-GPU box run several ranks -- and selects this rank's GPU; otherwise (0, 1, current)."""
+    import os
+    n = int(os.environ.get("WORLD_SIZE", "1"))
+    ndev = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    local = int(os.environ.get("LOCAL_RANK", "0")) % max(ndev, 1)
+    if ndev:
+        torch.cuda.set_device(local)
+    if n > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(os.environ.get("PYKMER_B200_DIST_BACKEND", "nccl"))
+    rank, n = world()
+    return rank, n, local
+
+
+def raise_together(error: Optional[BaseException], src: int = 0, group=None) -> None:
+    """Rank `src` reports whether its host-side step (opening files, parsing text) failed; every
+    rank then raises -- nobody is left waiting in a collective for a rank that has gone."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if error is not None:
+            raise error
+        return
+    box = [None if error is None else f"{type(error).__name__}: {error}"]
+    dist.broadcast_object_list(box, src=src, group=group)
+    if error is not None:
+        raise error
+    if box[0] is not None:
+        raise RuntimeError(f"rank {src} failed: {box[0]}")
+
+
 def shard_range(total: int, rank: int, nranks: int, align: int = ALIGN) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of the k-mer axis owned by `rank`; slices tile [0, total)."""
     def cut(r: int) -> int:
@@ -72,7 +104,12 @@ def reduce_flags(flags: np.ndarray, group=None) -> np.ndarray:
 def reduce_gram(G: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the partial Gram matrices of the k-mer-axis shards, in place."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+        if G.is_cuda and dist.get_backend(group) != "nccl":       # gloo: through host memory
+            g = G.cpu()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            G.copy_(g)
+        else:
+            dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
     return G
 
 

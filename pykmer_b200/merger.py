@@ -126,13 +126,18 @@ def merge(project_name: str, indexes: List[Path], min_count: int = DEFAULT_MIN_C
     assert all(i.exists() for i in indexes)
     entries = _check_inputs(indexes, buffer_size)
 
+    from . import dist as pdist
+    rank, world = pdist.world()
     matrix = merge_tables([e["header"] for e in entries], min_count, max_count, device=device)
-    n = len(entries)
-    for k, l in ((k, l) for k in range(n - 1) for l in range(k + 1, n)):
-        t_k, t_l, shared = (int(v) for v in matrix[k, l])
-        print(f"   matrix Total #{k:3d} {t_k:15,d} Total #{l:3d} {t_l:15,d} Shared {shared:15,d}")
-
-    _save(outfile, project_name, min_count, max_count, entries, matrix)
+    if rank == 0:                                             # every rank holds the matrix; one writes
+        n = len(entries)
+        for k, l in ((k, l) for k in range(n - 1) for l in range(k + 1, n)):
+            t_k, t_l, shared = (int(v) for v in matrix[k, l])
+            print(f"   matrix Total #{k:3d} {t_k:15,d} Total #{l:3d} {t_l:15,d} Shared {shared:15,d}")
+        _save(outfile, project_name, min_count, max_count, entries, matrix)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
     return entries, matrix
 
 
@@ -140,27 +145,50 @@ def merge_tables(headers: List[Header], min_count: int, max_count: int, device: 
                  slab_bytes: int = 256 << 20) -> np.ndarray:
     """Read each sample's table once (the file named by its JSON, .bgz preferred:
     tools.py:185-196), threshold + pack it on the GPU, then one Gram pass.
-    -> (N, N, 3) uint64."""
+    -> (N, N, 3) uint64.
+
+    Inside a torch.distributed job (torchrun merger.py ...) rank r takes slice r of the k-mer
+    axis of every sample -- the sums of tools.py:480-482 are sums over that axis, so the partial
+    Gram matrices simply add up (one all-reduce of N x N int64) -- and reads only
+    that slice of each file (Header.read_table_slice)."""
     import torch
     from . import device as dev          # needs the CUDA library; no fallback
+    from . import dist as pdist
 
     N = len(headers)
     T = headers[0].data_size
-    words = (T + 31) // 32
-    stride = (words + 3) & ~3
-    with torch.cuda.device(device):
-        bits = torch.zeros((N, stride), dtype=torch.int32, device="cuda")
-        stage = dev.pinned_empty(min(T, slab_bytes))
-        for s, h in enumerate(headers):
-            table = h.read_table()
-            assert table.size == T
-            for off in range(0, T, slab_bytes):
-                n = min(slab_bytes, T - off)
-                torch.cuda.current_stream().synchronize()      # stage is reused
+    rank, world = pdist.world()
+    lo, hi = pdist.shard_range(T, rank, world) if world > 1 else (0, T)
+    n_own = hi - lo
+    words = (n_own + 31) // 32
+    stride = max(4, (words + 3) & ~3)
+    with dev.device_scope(device):
+        bits = dev.zeros((N, stride), torch.int32)
+        stage = dev.pinned_empty(max(1, min(n_own, slab_bytes)))
+        def read(h: Header) -> np.ndarray:
+            assert h.data_size == T
+            return h.read_table() if world == 1 else h.read_table_slice(lo, hi)
+
+        # the next sample is read / inflated on a helper thread while this one crosses PCIe
+        from concurrent.futures import ThreadPoolExecutor
+        reader = ThreadPoolExecutor(max_workers=1)
+        ahead = reader.submit(read, headers[0]) if n_own else None
+        for s in range(N if n_own else 0):
+            table = ahead.result()
+            ahead = reader.submit(read, headers[s + 1]) if s + 1 < N else None
+            assert table.size == n_own
+            for off in range(0, n_own, slab_bytes):
+                n = min(slab_bytes, n_own - off)
+                dev.stream_sync()                              # stage is reused
                 stage.numpy()[:n] = table[off:off + n]
-                d = stage[:n].to("cuda", non_blocking=True)
+                d = dev.upload(stage[:n], non_blocking=True)
                 dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
-        G = dev.gram(bits, words=words)
+        reader.shutdown()
+        if n_own:
+            G = dev.gram(bits, words=words)
+        else:                                                  # tiny table, more ranks than slices
+            G = dev.zeros((N, N), torch.int64)
+        pdist.reduce_gram(G)
         Gh = G.cpu().numpy()
     return dev.matrix_from_gram(Gh)
 
@@ -171,8 +199,13 @@ def main(argv: Optional[List[str]] = None) -> None:
     if len(indexes) <= 1:
         print("needs at least 2 files")
         sys.exit(1)
+    import os
+    device = 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:            # torchrun merger.py ...: one rank per GPU
+        from . import dist as pdist
+        device = pdist.init_from_env()[2]
     merge(args.Project_Name, indexes, min_count=args.min_count, max_count=args.max_count,
-          buffer_size=args.buffer_size, block_size=args.block_size, threads=args.threads)
+          buffer_size=args.buffer_size, block_size=args.block_size, threads=args.threads, device=device)
 
 
 if __name__ == "__main__":

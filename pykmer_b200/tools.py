@@ -289,6 +289,26 @@ class Header(HeaderVars):
         assert arr.size == self.data_size, f"{path}: {arr.size} bytes, expected {self.data_size}"
         return arr
 
+    def read_table_slice(self, lo: int, hi: int, index_file: Optional[str] = None) -> np.ndarray:
+        """Entries [lo, hi) of the table -- the share of the k-mer axis one rank of a multi-GPU
+        merge works on.  A BGZF file gives up a slice by inflating only the members that hold it
+        (bgzf.read_range, with the file's .gzi when there is one); a raw .kin is read at an offset."""
+        path = index_file or self.index_file
+        assert 0 <= lo <= hi <= self.data_size
+        if path.endswith("." + self.COMP_EXT):
+            from .fasta import is_bgzf
+            if is_bgzf(path):
+                from .bgzf import read_range
+                arr = read_range(path, lo, hi)
+            else:
+                arr = self.read_table(path)[lo:hi]
+        else:
+            assert os.path.getsize(path) == self.data_size, \
+                f"{path}: {os.path.getsize(path)} bytes, expected {self.data_size}"
+            arr = np.fromfile(path, dtype=np.uint8, count=hi - lo, offset=lo)
+        assert arr.size == hi - lo, f"{path}: {arr.size} bytes in [{lo}, {hi})"
+        return arr
+
     # -- statistics (tools.py:246-263), computed on the GPU ---------------------------------
     def set_stats(self, hist: List[int], vals_sum: int, vals_count: int, vals_min: int,
                   vals_max: int) -> None:

@@ -159,3 +159,84 @@ def test_balanced_kmer_ranges_tile_the_axis_and_even_out_cost():
         assert max(cost) < 1.05 * (sum(cost) / n)
         equal = [per_window[nwin * r // n:nwin * (r + 1) // n].sum() for r in range(n)]
         assert max(equal) > 1.3 * (sum(equal) / n)                       # what balancing avoids
+
+
+# ---------------------------------------------------------------------------------------------
+# The drop-in CLIs as world_size-N jobs (torchrun indexer.py / merger.py): host logic only -- the
+# device layer is tests/fake_device.py (CPU oracle behind the same names), the collectives are
+# gloo.  Outputs are compared with what the reference's own indexer.py / merger.py wrote
+# (tests/golden).  The same jobs run with the real library in tests/test_gpu_parity.py.
+
+import hashlib
+import json
+import shutil
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import multirank  # noqa: E402
+
+GOLD = multirank.GOLD
+
+
+def _sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("case,nranks", [("rand200k.fa.bgz.11", 2), ("tiny_mixed.fa.07", 2),
+                                         ("tiny_mixed.fa.03", 2), ("saturating.fa.gz.07", 3)])
+def test_indexer_cli_as_a_multi_rank_job_writes_reference_files(tmp_path, case, nranks):
+    fname, kk = case.rsplit(".", 1)
+    K = int(kk)
+    gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
+    src = str(tmp_path / fname)
+    shutil.copy(os.path.join(GOLD, "inputs", fname), src)
+    res = multirank.run_cli(tmp_path, "indexer", [src, "sample", K], nranks=nranks)
+    assert all(rc == 0 for rc, _ in res), "\n".join(out for _, out in res)
+    kin = f"{src}.{K:02d}.kin"
+    assert os.path.exists(kin) and not os.path.exists(kin + ".tmp")
+    assert os.path.getsize(kin) == 4 ** K
+    meta = json.load(open(kin + ".json"))
+    assert sorted(meta.keys()) == gold["all_keys"]
+    for k, v in gold.items():
+        if k == "all_keys":
+            continue
+        got = os.path.basename(meta[k]) if k == "project_name" else meta[k]
+        assert got == v, k
+    assert _sha(kin) == gold["output_file_cheksum"] == meta["output_file_cheksum"]
+
+
+def test_indexer_multi_rank_job_stops_on_every_rank_when_the_reader_fails(tmp_path):
+    bad = str(tmp_path / "bad.fa")
+    open(bad, "wb").write(b">a\nACGTACGTAC\xc3\xa9GTACGT\n")           # non-ASCII inside sequence
+    res = multirank.run_cli(tmp_path, "indexer", [bad, "s", 5], nranks=2, timeout=120)
+    assert all(rc not in (0, None) for rc, _ in res), res
+    assert "timed out" not in "".join(out for _, out in res)
+    assert "ValueError" in res[0][1] and "rank 0 failed" in res[1][1]
+    empty = str(tmp_path / "empty.fa")                                   # no k-mer at all: tools.py:367-368
+    open(empty, "wb").write(b">a\nNNNNNNNN\n")
+    res = multirank.run_cli(tmp_path, "indexer", [empty, "s", 5], nranks=2, timeout=120)
+    assert all(rc not in (0, None) for rc, _ in res) and "AssertionError" in res[0][1]
+
+
+@pytest.mark.parametrize("nranks,bgzf_packed", [(2, False), (2, True), (3, True)])
+def test_merger_cli_as_a_multi_rank_job_writes_reference_files(tmp_path, nranks, bgzf_packed):
+    kins, _ = multirank.golden_merger_inputs(tmp_path, bgzf_packed=bgzf_packed)
+    lo, hi = 2, 10
+    gold = np.load(os.path.join(GOLD, "merger", f"matrix_K07_{lo:03d}-{hi:03d}.npz"))["matrix"]
+    gmeta = json.load(open(os.path.join(GOLD, "merger", f"matrix_K07_{lo:03d}-{hi:03d}.json")))
+    proj = str(tmp_path / "proj")
+    argv = [proj] + list(reversed(kins)) + [f"--min-count={lo}", f"--max-count={hi}"]
+    res = multirank.run_cli(tmp_path, "merger", argv, nranks=nranks)
+    assert all(rc == 0 for rc, _ in res), "\n".join(out for _, out in res)
+    kma = f"{proj}.{lo:03d}-{hi:03d}.kma"
+    m = np.load(kma)["matrix"]
+    off = ~np.eye(m.shape[0], dtype=bool)
+    assert m.dtype == np.uint64 and m.shape == gold.shape and np.array_equal(m[off], gold[off])
+    desc = json.load(open(kma + ".json"))
+    assert sorted(desc.keys()) == gmeta["top_keys"]
+    assert [os.path.basename(d["index_file"]) for d in desc["data"]] == gmeta["order"]
+    assert res[0][1].count("matrix Total") == m.shape[0] * (m.shape[0] - 1) // 2
+    assert "matrix Total" not in res[1][1]                      # one rank reports and writes
+    res = multirank.run_cli(tmp_path, "merger", argv, nranks=nranks)       # refuses to overwrite (merger.py:99)
+    assert all(rc not in (0, None) for rc, _ in res) and "AssertionError" in res[0][1]

@@ -832,3 +832,45 @@ def test_fused_exchange_routing_on_one_gpu(env, K, wlog, nranks):
         os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
     assert total == num and np.array_equal(flags, oflags)
     assert np.array_equal(np.concatenate(tables), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# The CLIs as multi-rank jobs with the real library: two ranks (gloo rendezvous, both on cuda:0)
+# each own half of the canonical k-mer axis.  The host protocol alone is covered on the CPU in
+# tests/test_dist_gloo.py; here the range-restricted handles and the sliced merge do the work.
+
+@pytest.mark.parametrize("case", ["rand200k.fa.bgz.13", "saturating.fa.gz.11", "tiny_mixed.fa.03"])
+def test_indexer_cli_two_ranks_on_one_gpu(env, case, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import multirank
+    fname, kk = case.rsplit(".", 1)
+    K = int(kk)
+    gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
+    src = str(tmp_path / fname)
+    shutil.copy(os.path.join(GOLD, "inputs", fname), src)
+    res = multirank.run_cli(tmp_path, "indexer", [src, "sample", K], nranks=2, fake=False)
+    assert all(rc == 0 for rc, _ in res), "\n".join(out for _, out in res)
+    kin = f"{src}.{K:02d}.kin"
+    meta = json.load(open(kin + ".json"))
+    for k, v in gold.items():
+        if k in ("all_keys", "project_name"):
+            continue
+        assert meta[k] == v, k
+    assert gen_sha(kin) == gold["output_file_cheksum"] == meta["output_file_cheksum"]
+
+
+def test_merger_cli_two_ranks_on_one_gpu(env, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import multirank
+    kins, _ = multirank.golden_merger_inputs(tmp_path, bgzf_packed=True)
+    lo, hi = 1, 50
+    gold = np.load(os.path.join(GOLD, "merger", f"matrix_K07_{lo:03d}-{hi:03d}.npz"))["matrix"]
+    proj = str(tmp_path / "proj")
+    res = multirank.run_cli(tmp_path, "merger", [proj] + kins + [f"--min-count={lo}", f"--max-count={hi}"],
+                            nranks=2, fake=False)
+    assert all(rc == 0 for rc, _ in res), "\n".join(out for _, out in res)
+    m = np.load(f"{proj}.{lo:03d}-{hi:03d}.kma")["matrix"]
+    off = ~np.eye(m.shape[0], dtype=bool)
+    assert m.dtype == np.uint64 and np.array_equal(m[off], gold[off])
