@@ -732,18 +732,20 @@ def run_merger(args, rank, local_rank, world):
 
     if rank == 0:
         name, unit = METRIC["merger"]
-        if algo == "i8":
-            # dense contraction on the tensor pipe: 2 * N^2 * 4^K int8 ops (true N, no padding credit)
+        if algo in ("i8", "f4"):
+            # dense contraction on the tensor pipe: 2 * N^2 * 4^K ops (true N, no padding credit);
+            # int8 runs at twice, FP4 (opt-in experiment, gram_f4.cu) at four times the bf16 rate
+            mult, nominal, kname = (2.0, 4500.0, "k_gram_i8") if algo == "i8" else (4.0, 9000.0, "k_gram_f4")
             ops = 2.0 * N * N * T
-            peak_t = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) \
-                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 2.0 * 1590.0
+            peak_t = mult * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else mult * 1590.0
             ach = ops / (ms_step * 1e-3) / 1e12
             peak_t *= world                                   # whole-job rate against the whole job's pipes
-            roof = {"bound": "tensor", "kernel": "k_gram_i8", "achieved": ach, "peak": peak_t,
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_t,
                     "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": None,
-                    "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json)" + (f" x {world} GPUs" if world > 1 else "")
-                                   + "; int8 ops, nominal dense 4500 per GPU",
-                    "frac_of_nominal_int8": ach / (4500.0 * world),
+                    "peak_source": f"{mult:.0f} x measured bf16 burst (MEASURED_PEAKS.json)" + (f" x {world} GPUs" if world > 1 else "")
+                                   + f"; nominal dense {nominal:.0f} per GPU",
+                    "frac_of_nominal_int8" if algo == "i8" else "frac_of_nominal_fp4": ach / (nominal * world),
                     "traffic_note": "ncu capture of this kernel at K=13, N=255 (profiles/r01_ncu_summary.txt): "
                                     "dram read 2.14 GB = N * 4^13 / 8 exactly -- every bitmask word is read once",
                     "hbm_GBps": value, "hbm_frac": value / (hbm_peak * world)}
@@ -756,7 +758,8 @@ def run_merger(args, rank, local_rank, world):
             "metric": name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8 x u8 -> s32 (tcgen05 kind::i8) -> int64" if algo == "i8" else "u32 popcount -> int64",
+            "dtype": {"i8": "u8 x u8 -> s32 (tcgen05 kind::i8) -> int64",
+                      "f4": "e2m1 x e2m1 -> f32 (tcgen05 kind::mxf4, exact integers < 2^24) -> int64"}.get(algo, "u32 popcount -> int64"),
             "data": "synthetic",
             "config": {"workload": f"merger K={K}, N={N} synthetic samples, --max-count={args.max_count}; "
                                    f"Gram stage over {bytes_bits / 1e9:.2f} GB of presence bitmask",

@@ -24,43 +24,14 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "tcgen05_util.h"
 
 namespace {
 
+using namespace pk_umma;
+
 // per-config constants live in GramCfg<NP>: K=32 steps (= bitmask words) per pipeline stage,
 // producer warps, stage ring depth
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes,
-// LBO = bytes between the two 16-byte K chunks, SBO = bytes between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
-    return d;                                             // layout_type 0 = no swizzle
-}
 
 // instruction descriptor, kind::i8: D = S32, A = B = unsigned 8 bit, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -76,22 +47,6 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xFFFFFFFF;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-
 // 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
     return (nib * 0x00204081u) & 0x01010101u;
@@ -288,17 +243,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
                 if (c0 >= nsamples) break;
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NP + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-                      "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-                      "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-                      "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-                      "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr, v);
                 if (lane_has_row && row < nsamples) {
 #pragma unroll
                     for (int c = 0; c < 32; c++)

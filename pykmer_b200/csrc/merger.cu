@@ -277,6 +277,8 @@ PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, 
     // default: 7x faster at N = 50, profiles/) and AND + popcount on the ALUs (any N).
     const char *algo = getenv("PYKMER_B200_GRAM");
     const bool want_popc = algo && strcmp(algo, "popc") == 0;
+    if (algo && strcmp(algo, "f4") == 0 && nsamples <= 256)       // opt-in experiment, see gram_f4.cu
+        return pk_gram_f4_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
     if (!want_popc && nsamples <= 256)
         return pk_gram_i8_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
     const int npanels = (nsamples + kPanel - 1) / kPanel;

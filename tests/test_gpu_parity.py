@@ -278,9 +278,16 @@ def test_threshold_pack_vs_oracle(env, n, lohi):
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), want)
 
 
-@pytest.fixture(params=["i8", "popc"])
+F4_ENABLED = os.environ.get("PYKMER_B200_TEST_F4") == "1"
+F4_SKIP = "gram_f4.cu is an opt-in experiment until it has been validated on the B200 (PYKMER_B200_TEST_F4=1)"
+
+
+@pytest.fixture(params=["i8", "popc", "f4"])
 def gram_algo(request):
-    """Both exact Gram implementations: tcgen05 kind::i8 tensor cores and AND + popcount."""
+    """The exact Gram implementations: tcgen05 kind::i8 tensor cores, AND + popcount, and the
+    opt-in FP4 experiment (kind::mxf4)."""
+    if request.param == "f4" and not F4_ENABLED:
+        pytest.skip(F4_SKIP)
     os.environ["PYKMER_B200_GRAM"] = request.param
     yield request.param
     os.environ.pop("PYKMER_B200_GRAM", None)
@@ -305,6 +312,26 @@ def test_gram_vs_oracle(env, gram_algo, N, words):
     assert np.array_equal(G, want)
     G2 = env["dev"].gram(d, words=words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
     assert np.array_equal(G2.cpu().numpy(), 2 * want)
+
+
+@pytest.mark.skipif(not F4_ENABLED, reason=F4_SKIP)
+@pytest.mark.parametrize("N", [3, 130])
+def test_gram_f4_every_partial_sum_is_exact(env, N):
+    """All-ones masks, 2^19 words per CTA: the FP32 accumulators walk through every multiple of 64
+    up to 2^24 -- the largest value a CTA may reach -- so any lost low bit shows up in G."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    words = sms << 19
+    d = torch.full((N, words), -1, dtype=torch.int32, device="cuda")
+    d[N - 1, 1::2] = 0x55555555                                   # one sample with half the bits
+    os.environ["PYKMER_B200_GRAM"] = "f4"
+    try:
+        G = env["dev"].gram(d, words=words).cpu().numpy()
+    finally:
+        os.environ.pop("PYKMER_B200_GRAM", None)
+    want = np.full((N, N), 32 * words, dtype=np.int64)
+    want[N - 1, :] = want[:, N - 1] = 16 * words + 16 * (words // 2)
+    assert np.array_equal(G, want)
 
 
 MERGER_CASES = sorted(glob.glob(os.path.join(GOLD, "merger", "matrix_*.npz")))
