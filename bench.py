@@ -668,7 +668,8 @@ def run_merger(args, rank, local_rank, world):
     n = hi - lo
     words = n // 32
     stride = (words + 3) & ~3
-    bits = torch.zeros((N, stride), dtype=torch.int32, device="cuda")
+    tiled = dev.use_tiled_masks(N)        # default for <= 256 samples: tiled masks + the FP4 Gram kernel
+    bits = dev.tiled_masks(words, N) if tiled else torch.zeros((N, stride), dtype=torch.int32, device="cuda")
     raw = torch.empty(n, dtype=torch.uint8, device="cuda")
     G = torch.zeros((N, N), dtype=torch.int64, device="cuda")
     # pack stage timed separately (per sample: generate, then threshold + pack)
@@ -677,13 +678,19 @@ def run_merger(args, rank, local_rank, world):
     for s in range(N):
         dev.synth_table(s, lo, hi, out=raw)
         ev[0].record()
-        dev.threshold_pack(raw, 1, args.max_count, out=bits[s])
+        if tiled:
+            dev.threshold_pack_tiled(raw, 1, args.max_count, bits, s, N)
+        else:
+            dev.threshold_pack(raw, 1, args.max_count, out=bits[s])
         ev[1].record()
         torch.cuda.synchronize()
         pack_ms += ev[0].elapsed_time(ev[1])
 
     def step():
-        dev.gram(bits, words=words, out=G, accumulate=False)
+        if tiled:
+            dev.gram_tiled(bits, N, words, out=G, accumulate=False)
+        else:
+            dev.gram(bits, words=words, out=G, accumulate=False)
         pdist.reduce_gram(G)                                  # N x N int64 partials, NCCL all-reduce
 
     sampler = ClockSampler(local_rank)
@@ -694,7 +701,7 @@ def run_merger(args, rank, local_rank, world):
     bytes_bits = N * T / 8
     value = bytes_bits / (ms_step * 1e-3) / 1e9
     hbm_peak, peak_src = measured_peak()
-    algo = os.environ.get("PYKMER_B200_GRAM", "i8" if N <= 256 else "popc")
+    algo = "f4" if tiled else os.environ.get("PYKMER_B200_GRAM", "i8" if N <= 256 else "popc")
     Gh = G.cpu().numpy()
 
     # end to end through the C ABI with HOST tables (pk_merge_host): pinned copy in, pack, Gram
@@ -735,7 +742,8 @@ def run_merger(args, rank, local_rank, world):
         if algo in ("i8", "f4"):
             # dense contraction on the tensor pipe: 2 * N^2 * 4^K ops (true N, no padding credit);
             # int8 runs at twice, FP4 (opt-in experiment, gram_f4.cu) at four times the bf16 rate
-            mult, nominal, kname = (2.0, 4500.0, "k_gram_i8") if algo == "i8" else (4.0, 9000.0, "k_gram_f4")
+            mult, nominal, kname = (2.0, 4500.0, "k_gram_i8") if algo == "i8" else \
+                (4.0, 9000.0, "k_gram_f4" + (" (tiled masks)" if tiled else " (row-major masks)"))
             ops = 2.0 * N * N * T
             peak_t = mult * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) \
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else mult * 1590.0
@@ -746,8 +754,9 @@ def run_merger(args, rank, local_rank, world):
                     "peak_source": f"{mult:.0f} x measured bf16 burst (MEASURED_PEAKS.json)" + (f" x {world} GPUs" if world > 1 else "")
                                    + f"; nominal dense {nominal:.0f} per GPU",
                     "frac_of_nominal_int8" if algo == "i8" else "frac_of_nominal_fp4": ach / (nominal * world),
-                    "traffic_note": "ncu capture of this kernel at K=13, N=255 (profiles/r01_ncu_summary.txt): "
-                                    "dram read 2.14 GB = N * 4^13 / 8 exactly -- every bitmask word is read once",
+                    "traffic_note": ("ncu capture of k_gram_i8 at K=13, N=255 (profiles/r01_ncu_summary.txt): "
+                                     "dram read 2.14 GB = N * 4^13 / 8 exactly -- every bitmask word is read once"
+                                     if algo == "i8" else "no ncu capture of k_gram_f4 yet; it reads every mask word once by construction"),
                     "hbm_GBps": value, "hbm_frac": value / (hbm_peak * world)}
         else:
             popc = N * (N + 1) / 2 * T / 32
@@ -765,6 +774,7 @@ def run_merger(args, rank, local_rank, world):
                                    f"Gram stage over {bytes_bits / 1e9:.2f} GB of presence bitmask",
                        "parallelism": f"kmer-axis x{world}" if world > 1 else "single GPU",
                        "l2": f"bitmask {bytes_bits / 1e9:.2f} GB >> 126 MB L2", "algo": algo,
+                       "mask_layout": "tiled [1024 k-mers][sample][32 words]" if tiled else "row-major",
                        "pack_ms_total": pack_ms, "pack_GBps": N * n * 1.125 / (pack_ms * 1e-3) / 1e9,
                        "trace_G": int(np.trace(Gh)), "G01": int(Gh[0, 1])},
             "clocks": clocks, "roofline": roof, "e2e": e2e, "gpu_launches": args.steps,

@@ -196,6 +196,23 @@ int pk_threshold_pack_device(const uint8_t *table_dev, size_t n, int min_count, 
  * overwrites gram_dev, 1 adds to it (k-mer-axis slabs / shards). */
 int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
                    int64_t *gram_dev, int accumulate, pk_stream stream);
+/* Tiled masks -- the layout the tensor-core Gram kernel streams best (up to PK_TILED_MAX_SAMPLES
+ * samples).  With row-major masks every sample is its own stream and a CTA gathers 128 bytes from
+ * each of them per step: DRAM sees ~38,000 interleaved streams and delivers ~1.1 TB/s.  Here the
+ * words of ALL samples for the same 1024 k-mers lie side by side,
+ *     word g of sample r  ->  bits_tiled_dev[(g / 32) * nrows * 32 + r * 32 + g % 32],
+ * so the gather is one sequential stream.  The buffer holds ceil(words / 32) * nrows * 32 words and
+ * must be zeroed before packing (the padding of the last tile is read).
+ * pk_threshold_pack_tiled_device packs n entries of sample `row` whose first entry is k-mer
+ * 32 * first_word of that sample (slabs of a table may be packed by separate calls).
+ * pk_gram_tiled_device is pk_gram_device on such a buffer (tcgen05 kind::mxf4, see gram_f4.cu);
+ * `words` = words per sample. */
+#define PK_TILED_MAX_SAMPLES 256
+int pk_threshold_pack_tiled_device(const uint8_t *table_dev, size_t n, size_t first_word, int min_count,
+                                   int max_count, uint32_t *bits_tiled_dev, int row, int nrows,
+                                   pk_stream stream);
+int pk_gram_tiled_device(const uint32_t *bits_tiled_dev, int nsamples, size_t words, int64_t *gram_dev,
+                         int accumulate, pk_stream stream);
 /* One pair, straight from two device tables: out_host = {Total_s, Total_o, Shared}
  * -- the return value of Header.calculate_distance (tools.py:493).  Synchronises. */
 int pk_pair_counts_device(const uint8_t *s_dev, const uint8_t *o_dev, size_t n, int min_count,

@@ -15,10 +15,10 @@ int pk_set_error(int code, const char *fmt, ...);
 // tensor cores (tcgen05 kind::i8); nsamples <= 256.
 int pk_gram_i8_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
                       int64_t *gram_dev, int device, cudaStream_t st);
-// gram_f4.cu: the same contraction on the block-scaled FP4 path (tcgen05 kind::mxf4), opt-in
-// experiment (PYKMER_B200_GRAM=f4); nsamples <= 256.
+// gram_f4.cu: the same contraction on the block-scaled FP4 path (tcgen05 kind::mxf4); nsamples <= 256.
+// tile_rows = 0: bits[row][word]; tile_rows = R: the tiled layout bits[word / 32][R][32].
 int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
-                      int64_t *gram_dev, int device, cudaStream_t st);
+                      int64_t *gram_dev, int device, cudaStream_t st, int tile_rows);
 
 #define PK_CUDA(call)                                                                   \
     do {                                                                                \

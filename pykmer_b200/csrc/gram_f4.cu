@@ -71,10 +71,18 @@ struct F4Cfg {
     static constexpr int kProducerWarps = 8;
     static constexpr int kProducerThreads = kProducerWarps * 32;
     static constexpr int kThreads = kProducerThreads + 32;            // + the MMA-issuing warp
-    static constexpr int kGroups = NP == 256 ? 1 : 8;     // producer groups filling stages in parallel
-    static constexpr int kKB = NP == 64 ? 8 : 4;          // K=64 steps per stage (2 mask words per row each)
+    // What bounds the producers is the gather of the mask words -- every row is its own stream,
+    // so a warp's load touches 32 different lines -- and that gather runs at about one line MISS
+    // per 8 cycles per SM however many loads are in flight (measured: 4 bytes per cycle per SM
+    // with 32 bytes used per miss, tools/gram_sweep.py).  So a thread always takes a whole 128-byte
+    // line of its row: for <= 128 rows a stage covers 16 K=64 steps (32 words = one line per row), for
+    // 256 rows -- where such a stage would be 128 KB -- a thread reads a line into registers and feeds
+    // four 4-step stages from it.
+    static constexpr int kGroups = NP == 64 ? 4 : (NP == 128 ? 2 : 1);   // groups fill different stages; <= kStages
+    static constexpr int kKB = NP == 256 ? 4 : 16;        // K=64 steps per stage (2 mask words per row each)
     static constexpr int kWords = 2 * kKB;                // mask words per row per stage
-    static constexpr int kStages = NP == 256 ? 5 : 8;
+    static constexpr int kLineStages = 32 / kWords;       // stages one 128-byte line of a row feeds
+    static constexpr int kStages = NP == 64 ? 4 : (NP == 128 ? 3 : 5);
     static constexpr int kTileBytes = NP * 32;            // one K=64 step of all NP rows (32 bytes per row)
     static constexpr int kStageBytes = kKB * kTileBytes;
     static constexpr int kAccN = NP == 256 ? 128 : NP;    // columns of one accumulator
@@ -83,12 +91,19 @@ struct F4Cfg {
     static constexpr int kTmemCols = NP == 256 ? 512 : (NP == 128 ? 256 : 128);
     static constexpr int kPad = 4096;                     // the M=128 descriptor of a 64-row tile overruns
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kPad + 256 + 1024;
+    static_assert(kGroups <= kStages && kSmem <= 227 * 1024, "a group may not lap the ring; shared memory budget");
 };
 
 template <int NP, int AHEAD>
 __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32_t *__restrict__ bits, int nsamples,
                                                         size_t words, size_t stride_words,
-                                                        unsigned long long *__restrict__ gram) {
+                                                        unsigned long long *__restrict__ gram, int diag, int tile_rows) {
+    // tile_rows: 0 = bits[row][word] with a row stride; R > 0 = the tiled layout
+    // bits[word / 32][R rows][32 words] (include/pykmer_b200.h) -- the lines of all rows for the same
+    // 1024 k-mers lie side by side, so a CTA's gather is one sequential stream instead of one per row.
+    // diag (PYKMER_B200_GRAM_DIAG, timing experiments only -- the result is then meaningless):
+    // bit 0 = producers skip the global loads, bit 1 = the issuer skips the MMAs, bit 2 = producers
+    // skip the shared-memory stores
     using C = F4Cfg<NP>;
     constexpr int kKB = C::kKB, kWords = C::kWords;
     constexpr int kProducerThreads = C::kProducerThreads;
@@ -105,7 +120,8 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
 
     // this CTA's slab of words, in whole stages of kWords words
     const size_t total_stages = (words + kWords - 1) / kWords;
-    const size_t per_cta = (total_stages + gridDim.x - 1) / gridDim.x;
+    size_t per_cta = (total_stages + gridDim.x - 1) / gridDim.x;
+    per_cta = (per_cta + C::kLineStages - 1) / C::kLineStages * C::kLineStages;     // slabs start on a line
     const size_t st0 = min(total_stages, (size_t)blockIdx.x * per_cta);
     const size_t st1 = min(total_stages, st0 + per_cta);
     const size_t nst = st1 - st0;
@@ -155,6 +171,10 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
         const int group = threadIdx.x / kGroupThreads, tg = threadIdx.x % kGroupThreads;
         const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
         uint32_t wv[kAhead][kRowsPerThread][kWords];
+        auto row_ptr = [&](int row, size_t w0) -> const uint32_t * {       // w0: a multiple of kWords
+            if (tile_rows) return bits + (w0 >> 5) * ((size_t)tile_rows * 32) + (size_t)row * 32 + (w0 & 31);
+            return bits + (size_t)row * stride_words + w0;
+        };
 
         auto fetch = [&](uint32_t (&dst)[kRowsPerThread][kWords], size_t it) {
             const size_t w0 = (st0 + it) * kWords;
@@ -163,8 +183,9 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
                 const int row = tg + rr * kGroupThreads;
 #pragma unroll
                 for (int k = 0; k < kWords; k++) dst[rr][k] = 0;
+                if (diag & 1) continue;
                 if (row < nsamples && it < nst) {
-                    const uint32_t *src = bits + (size_t)row * stride_words + w0;
+                    const uint32_t *src = row_ptr(row, w0);
                     if (vec_ok && w0 + kWords <= words) {
 #pragma unroll
                         for (int k = 0; k < kWords; k += 4) {
@@ -188,6 +209,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
             for (int rr = 0; rr < kRowsPerThread; rr++) {
                 const int row = tg + rr * kGroupThreads;
                 uint8_t *dst = stage + (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
+                if (diag & 4) continue;
 #pragma unroll
                 for (int k = 0; k < kKB; k++) {            // K=64 step k: words 2k, 2k+1 -> chunks 0, 1
                     *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kTileBytes) = expand_word_f4(src[rr][2 * k]);
@@ -199,15 +221,61 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
             mbar_arrive(smem_u32(&full_bar[s]));
         };
 
+        if constexpr (C::kLineStages == 1) {
 #pragma unroll
-        for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)group + (size_t)p * kGroups);
-        for (size_t it = group; it < nst; it += (size_t)kAhead * kGroups) {
+            for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)group + (size_t)p * kGroups);
+            for (size_t it = group; it < nst; it += (size_t)kAhead * kGroups) {
 #pragma unroll
-            for (int p = 0; p < kAhead; p++) {
-                const size_t cur = it + (size_t)p * kGroups;
-                if (cur < nst) {
-                    produce(wv[p], cur);
-                    fetch(wv[p], cur + (size_t)kAhead * kGroups);
+                for (int p = 0; p < kAhead; p++) {
+                    const size_t cur = it + (size_t)p * kGroups;
+                    if (cur < nst) {
+                        produce(wv[p], cur);
+                        fetch(wv[p], cur + (size_t)kAhead * kGroups);
+                    }
+                }
+            }
+        } else {
+            // one row per thread, one group: line L of the row = stages kLineStages * L ..
+            static_assert(C::kLineStages == 1 || (kGroups == 1 && kRowsPerThread == 1), "line mode: one row per thread");
+            constexpr int kLS = C::kLineStages;
+            uint32_t line[2][kLS][1][kWords];
+            auto fetch_line = [&](uint32_t (&dst)[kLS][1][kWords], size_t ln) {
+                const size_t w0 = (st0 + ln * kLS) * kWords;
+                const int row = tg;
+#pragma unroll
+                for (int j = 0; j < kLS; j++)
+#pragma unroll
+                    for (int k = 0; k < kWords; k++) dst[j][0][k] = 0;
+                if ((diag & 1) || row >= nsamples || ln * kLS >= nst) return;
+                const uint32_t *src = row_ptr(row, w0);
+                if (vec_ok && w0 + kLS * kWords <= words) {
+#pragma unroll
+                    for (int j = 0; j < kLS; j++)
+#pragma unroll
+                        for (int k = 0; k < kWords; k += 4) {
+                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + j * kWords + k));
+                            dst[j][0][k] = q.x; dst[j][0][k + 1] = q.y; dst[j][0][k + 2] = q.z; dst[j][0][k + 3] = q.w;
+                        }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kLS; j++)
+#pragma unroll
+                        for (int k = 0; k < kWords; k++)
+                            if (w0 + j * kWords + k < words) dst[j][0][k] = __ldg(src + j * kWords + k);
+                }
+            };
+            fetch_line(line[0], 0);
+            fetch_line(line[1], 1);
+            for (size_t ln = 0; ln * kLS < nst; ln += 2) {
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const size_t s0 = (ln + b) * kLS;
+                    if (s0 < nst) {
+#pragma unroll
+                        for (int j = 0; j < kLS; j++)
+                            if (s0 + j < nst) produce(line[b][j], s0 + j);
+                        fetch_line(line[b], ln + b + 2);
+                    }
                 }
             }
         }
@@ -227,6 +295,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
                 for (int kb = 0; kb < kKB; kb++) {
                     const uint64_t lo = dstage + (uint64_t)((kb * C::kTileBytes) >> 4);   // rows 0..127
                     const uint32_t acc = (it | kb) ? 1u : 0u;
+                    if (diag & 2) continue;
                     if (C::kAccs == 1) {
                         mma_f4(tmem_base, lo, lo, idesc, acc, sf, sf);
                     } else {
@@ -286,16 +355,23 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
 
 template <int NP, int AHEAD>
 int launch_gram_f4(const uint32_t *bits, int nsamples, size_t words, size_t stride_words,
-                   unsigned long long *gram, int device, cudaStream_t st) {
+                   unsigned long long *gram, int device, cudaStream_t st, int tile_rows) {
     using C = F4Cfg<NP>;
     PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const size_t total_stages = (words + C::kWords - 1) / C::kWords;
     // a CTA's FP32 accumulators must stay exact integers: at most 2^24 k-mers = 2^19 words each
-    const size_t min_ctas = (words + ((1ull << 19) - 1)) >> 19;
+    // (slabs are rounded up to whole lines and stages inside the kernel: keep 64 words of margin)
+    const size_t slab_max = (1ull << 19) - 64;
+    const size_t min_ctas = (words + slab_max - 1) / slab_max;
     size_t grid = (size_t)pk_sm_count(device);
     grid = std::max(grid, min_ctas);
     grid = std::max<size_t>(1, std::min(grid, total_stages));
-    k_gram_f4<NP, AHEAD><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram);
+    int diag = 0;
+    if (const char *env = getenv("PYKMER_B200_GRAM_DIAG")) diag = atoi(env);
+    if (tile_rows && (words & 31))
+        return pk_set_error(PK_ERR_ARG, "gram_f4: the tiled layout needs a multiple of 32 words, got %zu", words);
+    k_gram_f4<NP, AHEAD><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram,
+                                                                        diag, tile_rows);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -304,10 +380,10 @@ int launch_gram_f4(const uint32_t *bits, int nsamples, size_t words, size_t stri
 
 // gram (int64, nsamples x nsamples, already zeroed or holding a partial sum) += B * B^T
 int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
-                      int64_t *gram_dev, int device, cudaStream_t st) {
+                      int64_t *gram_dev, int device, cudaStream_t st, int tile_rows) {
     unsigned long long *g = reinterpret_cast<unsigned long long *>(gram_dev);
-    if (nsamples <= 64) return launch_gram_f4<64, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
-    if (nsamples <= 128) return launch_gram_f4<128, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
-    if (nsamples <= 256) return launch_gram_f4<256, 2>(bits_dev, nsamples, words, stride_words, g, device, st);
+    if (nsamples <= 64) return launch_gram_f4<64, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
+    if (nsamples <= 128) return launch_gram_f4<128, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
+    if (nsamples <= 256) return launch_gram_f4<256, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
     return pk_set_error(PK_ERR_ARG, "pk_gram_f4_launch: %d samples exceed one tensor-core tile (256)", nsamples);
 }

@@ -25,9 +25,12 @@ __device__ __forceinline__ uint32_t valid_nibble(uint32_t w, uint32_t lo4, uint3
     return ((m & 0x08040201u) * 0x01010101u) >> 24;      // byte b -> bit b
 }
 
+// nrows = 0: word wi goes to bits[wi].  nrows = R: the tiled layout -- word g = first_word + wi of
+// sample `row` goes to bits[(g / 32) * R * 32 + row * 32 + g % 32].
 __global__ void __launch_bounds__(256) k_threshold_pack(const uint8_t *__restrict__ table, size_t n,
                                                         uint32_t lo, uint32_t hi,
-                                                        uint32_t *__restrict__ bits) {
+                                                        uint32_t *__restrict__ bits, size_t first_word,
+                                                        uint32_t row, uint32_t nrows) {
     const uint32_t lo4 = lo * 0x01010101u, hi4 = hi * 0x01010101u;
     const size_t words = (n + 31) / 32;
     const size_t full_words = n / 32;
@@ -47,7 +50,12 @@ __global__ void __launch_bounds__(256) k_threshold_pack(const uint8_t *__restric
                 if (c >= lo && c <= hi) out |= 1u << (i & 31);
             }
         }
-        bits[wi] = out;
+        if (nrows) {
+            const size_t g = first_word + wi;
+            bits[((g >> 5) * nrows + row) * 32 + (g & 31)] = out;
+        } else {
+            bits[wi] = out;
+        }
     }
 }
 
@@ -257,9 +265,45 @@ PK_API int pk_threshold_pack_device(const uint8_t *table_dev, size_t n, int min_
     PK_CUDA(cudaGetDevice(&device));
     const size_t words = (n + 31) / 32;
     k_threshold_pack<<<grid_for(words, 256, device, 8), 256, 0, (cudaStream_t)stream>>>(
-        table_dev, n, (uint32_t)min_count, (uint32_t)max_count, bits_dev);
+        table_dev, n, (uint32_t)min_count, (uint32_t)max_count, bits_dev, 0, 0u, 0u);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
+}
+
+PK_API int pk_threshold_pack_tiled_device(const uint8_t *table_dev, size_t n, size_t first_word, int min_count,
+                                          int max_count, uint32_t *bits_tiled_dev, int row, int nrows,
+                                          pk_stream stream) {
+    PK_REQUIRE(table_dev != nullptr && bits_tiled_dev != nullptr, "pk_threshold_pack_tiled_device: NULL pointer");
+    PK_REQUIRE(min_count >= 1 && max_count <= 255, "pk_threshold_pack_tiled_device: thresholds [%d, %d] outside 1..255",
+               min_count, max_count);                                           // merger.py:90-91
+    PK_REQUIRE(((uintptr_t)table_dev & 15u) == 0, "pk_threshold_pack_tiled_device: table_dev must be 16-byte aligned");
+    PK_REQUIRE(nrows >= 1 && row >= 0 && row < nrows, "pk_threshold_pack_tiled_device: row %d of %d", row, nrows);
+    if (n == 0) return PK_OK;
+    int device = 0;
+    PK_CUDA(cudaGetDevice(&device));
+    const size_t words = (n + 31) / 32;
+    k_threshold_pack<<<grid_for(words, 256, device, 8), 256, 0, (cudaStream_t)stream>>>(
+        table_dev, n, (uint32_t)min_count, (uint32_t)max_count, bits_tiled_dev, first_word, (uint32_t)row,
+        (uint32_t)nrows);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+PK_API int pk_gram_tiled_device(const uint32_t *bits_tiled_dev, int nsamples, size_t words, int64_t *gram_dev,
+                                int accumulate, pk_stream stream) {
+    PK_REQUIRE(bits_tiled_dev != nullptr && gram_dev != nullptr, "pk_gram_tiled_device: NULL pointer");
+    PK_REQUIRE(nsamples >= 1 && nsamples <= PK_TILED_MAX_SAMPLES,
+               "pk_gram_tiled_device: %d samples, the tiled masks serve 1..%d (more: pk_gram_device)", nsamples,
+               PK_TILED_MAX_SAMPLES);
+    PK_REQUIRE(((uintptr_t)bits_tiled_dev & 15u) == 0, "pk_gram_tiled_device: bits must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0;
+    PK_CUDA(cudaGetDevice(&device));
+    if (!accumulate)
+        PK_CUDA(cudaMemsetAsync(gram_dev, 0, (size_t)nsamples * nsamples * sizeof(int64_t), st));
+    if (words == 0) return PK_OK;
+    const size_t padded = (words + 31) & ~(size_t)31;             // whole tiles; the padding words are zero
+    return pk_gram_f4_launch(bits_tiled_dev, nsamples, padded, padded, gram_dev, device, st, nsamples);
 }
 
 PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
@@ -277,8 +321,11 @@ PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, 
     // default: 7x faster at N = 50, profiles/) and AND + popcount on the ALUs (any N).
     const char *algo = getenv("PYKMER_B200_GRAM");
     const bool want_popc = algo && strcmp(algo, "popc") == 0;
-    if (algo && strcmp(algo, "f4") == 0 && nsamples <= 256)       // opt-in experiment, see gram_f4.cu
-        return pk_gram_f4_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
+    if (algo && strcmp(algo, "f4") == 0 && nsamples <= 256) {     // FP4 path on row-major masks (sweeps)
+        const char *tiled = getenv("PYKMER_B200_GRAM_TILED");    // the caller laid the words out in tiles
+        return pk_gram_f4_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st,
+                                 tiled && atoi(tiled) ? nsamples : 0);
+    }
     if (!want_popc && nsamples <= 256)
         return pk_gram_i8_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
     const int npanels = (nsamples + kPanel - 1) / kPanel;
@@ -337,6 +384,10 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
 
     const size_t words = (n + 31) / 32;
     const size_t stride_words = (words + 3) & ~(size_t)3;
+    // <= 256 samples: tiled masks + the FP4 Gram kernel (gram_f4.cu); PYKMER_B200_GRAM=i8|popc|f4 keeps
+    // the row-major masks and the kernel named
+    const bool tiled = nsamples <= PK_TILED_MAX_SAMPLES && getenv("PYKMER_B200_GRAM") == nullptr;
+    const size_t mask_words = tiled ? ((words + 31) / 32) * 32 * (size_t)nsamples : (size_t)nsamples * stride_words;
     const size_t chunk = std::min<size_t>(n, 64u << 20);          // bytes per staged copy, multiple of 32
     uint8_t *stage[2] = {nullptr, nullptr};
     uint32_t *bits = nullptr;
@@ -346,8 +397,9 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
     std::vector<int64_t> G((size_t)nsamples * nsamples);
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    step(cudaMalloc(&bits, (size_t)nsamples * stride_words * sizeof(uint32_t)));
+    step(cudaMalloc(&bits, mask_words * sizeof(uint32_t)));
     step(cudaMalloc(&gram, G.size() * sizeof(int64_t)));
+    if (tiled && e == cudaSuccess) step(cudaMemset(bits, 0, mask_words * sizeof(uint32_t)));   // tile padding
     step(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
     step(cudaStreamCreateWithFlags(&work_st, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
@@ -365,14 +417,17 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
             step(cudaEventRecord(copied[buf], copy_st));
             step(cudaStreamWaitEvent(work_st, copied[buf], 0));
             if (e == cudaSuccess)
-                rc = pk_threshold_pack_device(stage[buf], len, min_count, max_count,
-                                              bits + (size_t)s * stride_words + off / 32, work_st);
+                rc = tiled ? pk_threshold_pack_tiled_device(stage[buf], len, off / 32, min_count, max_count, bits, s,
+                                                            nsamples, work_st)
+                           : pk_threshold_pack_device(stage[buf], len, min_count, max_count,
+                                                      bits + (size_t)s * stride_words + off / 32, work_st);
             step(cudaEventRecord(consumed[buf], work_st));
             buf ^= 1;
         }
     }
     if (e == cudaSuccess && rc == PK_OK)
-        rc = pk_gram_device(bits, nsamples, words, stride_words, gram, 0, work_st);
+        rc = tiled ? pk_gram_tiled_device(bits, nsamples, words, gram, 0, work_st)
+                   : pk_gram_device(bits, nsamples, words, stride_words, gram, 0, work_st);
     if (e == cudaSuccess && rc == PK_OK)
         step(cudaMemcpyAsync(G.data(), gram, G.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, work_st));
     if (e == cudaSuccess && rc == PK_OK) step(cudaStreamSynchronize(work_st));

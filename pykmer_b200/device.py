@@ -328,6 +328,54 @@ def gram(bits: torch.Tensor, words: Optional[int] = None, out: Optional[torch.Te
     return out
 
 
+TILED_MAX_SAMPLES = 256
+
+
+def tiled_mask_words(words: int, nrows: int) -> int:
+    """int32 words of a tiled mask buffer for `nrows` samples of `words` words each."""
+    return ((words + 31) // 32) * nrows * 32
+
+
+def tiled_masks(words: int, nrows: int) -> torch.Tensor:
+    """Zeroed tiled mask buffer (include/pykmer_b200.h: word g of sample r at
+    [(g // 32) * nrows * 32 + r * 32 + g % 32])."""
+    return torch.zeros(max(4, tiled_mask_words(words, nrows)), dtype=torch.int32, device="cuda")
+
+
+def threshold_pack_tiled(table: torch.Tensor, min_count: int, max_count: int, out: torch.Tensor,
+                         row: int, nrows: int, first_word: int = 0, stream=None) -> torch.Tensor:
+    """uint8 CUDA table slab of sample `row` -> its words of the tiled mask buffer `out`."""
+    assert table.is_cuda and table.dtype == torch.uint8 and table.is_contiguous()
+    assert out.is_cuda and out.element_size() == 4 and out.is_contiguous()
+    words = (table.numel() + 31) // 32
+    assert out.numel() >= tiled_mask_words(first_word + words, nrows)
+    with torch.cuda.device(table.device):
+        nat.check(lib.pk_threshold_pack_tiled_device(table.data_ptr(), table.numel(), first_word, min_count,
+                                                     max_count, out.data_ptr(), row, nrows, _stream_ptr(stream)))
+    return out
+
+
+def gram_tiled(bits: torch.Tensor, nsamples: int, words: int, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False, stream=None) -> torch.Tensor:
+    """tiled mask buffer -> (N, N) int64 CUDA Gram matrix (N <= TILED_MAX_SAMPLES)."""
+    assert bits.is_cuda and bits.element_size() == 4 and bits.is_contiguous()
+    assert bits.numel() >= tiled_mask_words(words, nsamples)
+    if out is None:
+        out = torch.zeros((nsamples, nsamples), dtype=torch.int64, device=bits.device)
+        accumulate = False
+    with torch.cuda.device(bits.device):
+        nat.check(lib.pk_gram_tiled_device(bits.data_ptr(), nsamples, words, out.data_ptr(),
+                                           1 if accumulate else 0, _stream_ptr(stream)))
+    return out
+
+
+def use_tiled_masks(nsamples: int) -> bool:
+    """The merger's default for <= 256 samples; PYKMER_B200_GRAM=i8|popc|f4 selects a kernel on
+    row-major masks instead."""
+    import os
+    return nsamples <= TILED_MAX_SAMPLES and os.environ.get("PYKMER_B200_GRAM") is None
+
+
 def matrix_from_gram(G: np.ndarray) -> np.ndarray:
     """(N, N, 3) uint64: [k, l] = (G[k,k], G[l,l], G[k,l])  (merger.py:175-176)."""
     G = np.asarray(G)

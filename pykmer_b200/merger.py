@@ -162,9 +162,11 @@ def merge_tables(headers: List[Header], min_count: int, max_count: int, device: 
     n_own = hi - lo
     words = (n_own + 31) // 32
     stride = max(4, (words + 3) & ~3)
+    tiled = dev.use_tiled_masks(N)       # <= 256 samples: tiled masks + the FP4 tensor-core Gram kernel
     with dev.device_scope(device):
-        bits = dev.zeros((N, stride), torch.int32)
+        bits = dev.tiled_masks(words, N) if tiled else dev.zeros((N, stride), torch.int32)
         stage = dev.pinned_empty(max(1, min(n_own, slab_bytes)))
+
         def read(h: Header) -> np.ndarray:
             assert h.data_size == T
             return h.read_table() if world == 1 else h.read_table_slice(lo, hi)
@@ -182,10 +184,13 @@ def merge_tables(headers: List[Header], min_count: int, max_count: int, device: 
                 dev.stream_sync()                              # stage is reused
                 stage.numpy()[:n] = table[off:off + n]
                 d = dev.upload(stage[:n], non_blocking=True)
-                dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
+                if tiled:
+                    dev.threshold_pack_tiled(d, min_count, max_count, bits, s, N, first_word=off // 32)
+                else:
+                    dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
         reader.shutdown()
         if n_own:
-            G = dev.gram(bits, words=words)
+            G = dev.gram_tiled(bits, N, words) if tiled else dev.gram(bits, words=words)
         else:                                                  # tiny table, more ranks than slices
             G = dev.zeros((N, N), torch.int64)
         pdist.reduce_gram(G)

@@ -74,6 +74,10 @@ class Indexer:
         return dst
 
 
+def use_tiled_masks(nsamples):
+    return False
+
+
 def threshold_pack(table, min_count, max_count, out=None, stream=None):
     words = torch.from_numpy(oracle.threshold_pack(table.numpy(), min_count, max_count).view(np.int32))
     out.view(-1)[:words.numel()] = words

@@ -278,14 +278,14 @@ def test_threshold_pack_vs_oracle(env, n, lohi):
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), want)
 
 
-F4_ENABLED = os.environ.get("PYKMER_B200_TEST_F4") == "1"
-F4_SKIP = "gram_f4.cu is an opt-in experiment until it has been validated on the B200 (PYKMER_B200_TEST_F4=1)"
+F4_ENABLED = os.environ.get("PYKMER_B200_TEST_F4", "1") == "1"
+F4_SKIP = "FP4 Gram tests switched off (PYKMER_B200_TEST_F4=0)"
 
 
 @pytest.fixture(params=["i8", "popc", "f4"])
 def gram_algo(request):
-    """The exact Gram implementations: tcgen05 kind::i8 tensor cores, AND + popcount, and the
-    opt-in FP4 experiment (kind::mxf4)."""
+    """The exact Gram implementations on row-major masks: tcgen05 kind::i8 tensor cores, AND +
+    popcount, tcgen05 kind::mxf4 (FP4; on tiled masks it is the merger's default, tested below)."""
     if request.param == "f4" and not F4_ENABLED:
         pytest.skip(F4_SKIP)
     os.environ["PYKMER_B200_GRAM"] = request.param
@@ -332,6 +332,45 @@ def test_gram_f4_every_partial_sum_is_exact(env, N):
     want = np.full((N, N), 32 * words, dtype=np.int64)
     want[N - 1, :] = want[:, N - 1] = 16 * words + 16 * (words // 2)
     assert np.array_equal(G, want)
+
+
+@pytest.mark.parametrize("N,n", [(1, 5), (2, 100), (3, 1024), (7, 33_000), (50, 70_001), (64, 40_000),
+                                 (65, 50_000), (128, 98_304), (200, 77_777), (256, 40_000), (50, 3_000_001)])
+def test_tiled_masks_pack_and_gram_vs_oracle(env, N, n):
+    """The merger's default path for <= 256 samples: tables -> tiled masks (packed in two slabs) ->
+    FP4 Gram.  Layout and matrix against the oracle, table lengths that are not whole words / tiles."""
+    import torch
+    dev, oracle = env["dev"], env["oracle"]
+    rng = np.random.default_rng(N * 7919 + n)
+    tables = (rng.integers(0, 12, size=(N, n), dtype=np.uint8) * (rng.random((N, n)) < 0.4)).astype(np.uint8)
+    lo, hi = 2, 9
+    words = (n + 31) // 32
+    bits = dev.tiled_masks(words, N)
+    cut = (n // 2) // 1024 * 1024                                 # slabs start on whole words
+    for s in range(N):
+        t = torch.from_numpy(tables[s]).cuda()
+        if cut:
+            dev.threshold_pack_tiled(t[:cut].contiguous(), lo, hi, bits, s, N)
+            dev.threshold_pack_tiled(t[cut:].contiguous(), lo, hi, bits, s, N, first_word=cut // 32)
+        else:
+            dev.threshold_pack_tiled(t, lo, hi, bits, s, N)
+    rows = np.stack([oracle.threshold_pack(tables[s], lo, hi) for s in range(N)])
+    tiles = (words + 31) // 32
+    got = bits.cpu().numpy().view(np.uint32)[:tiles * N * 32].reshape(tiles, N, 32)
+    want_tiled = np.zeros((N, tiles * 32), dtype=np.uint32)
+    want_tiled[:, :words] = rows
+    assert np.array_equal(got, want_tiled.reshape(N, tiles, 32).transpose(1, 0, 2))
+    G = dev.gram_tiled(bits, N, words).cpu().numpy()
+    if N * words > 2_000_000:
+        B = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little").astype(np.float64)
+        want = (B @ B.T).astype(np.int64)
+    else:
+        want = oracle.gram_from_bits(rows)
+    assert np.array_equal(G, want)
+    G2 = dev.gram_tiled(bits, N, words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
+    assert np.array_equal(G2.cpu().numpy(), 2 * want)
+    with pytest.raises(ValueError):                                # more than one tensor-core tile of samples
+        dev.gram_tiled(dev.tiled_masks(1, 257), 257, 1)
 
 
 MERGER_CASES = sorted(glob.glob(os.path.join(GOLD, "merger", "matrix_*.npz")))
