@@ -15,12 +15,20 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 15
 T = 4 ** K
 words = T // 32
-bits = torch.zeros((N, words), dtype=torch.int32, device="cuda")
 raw = torch.empty(T, dtype=torch.uint8, device="cuda")
-for s in range(N):
-    dev.synth_table(s, 0, T, out=raw)
-    dev.threshold_pack(raw, 1, 50, out=bits[s])
-G = dev.gram(bits)
-G = dev.gram(bits)
+if dev.use_tiled_masks(N):                      # the merger's default for <= 256 samples
+    bits = dev.tiled_masks(words, N)
+    for s in range(N):
+        dev.synth_table(s, 0, T, out=raw)
+        dev.threshold_pack_tiled(raw, 1, 50, bits, s, N)
+    G = dev.gram_tiled(bits, N, words)
+    G = dev.gram_tiled(bits, N, words)
+else:
+    bits = torch.zeros((N, words), dtype=torch.int32, device="cuda")
+    for s in range(N):
+        dev.synth_table(s, 0, T, out=raw)
+        dev.threshold_pack(raw, 1, 50, out=bits[s])
+    G = dev.gram(bits)
+    G = dev.gram(bits)
 torch.cuda.synchronize()
 print("N", N, "K", K, "trace", int(G.diagonal().sum()), "G01", int(G[0, 1]))
