@@ -44,7 +44,7 @@ def main():
     bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (256, WORDS + PAD), dtype=torch.int32, device="cuda", generator=g)
     print(f"row stride = {WORDS} + {PAD} words", flush=True)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for n in (50, 64, 100, 128, 200, 255):
+    for n in [int(v) for v in os.environ.get("SWEEP_NS", "50,64,100,128,200,255").split(",")]:
         ref_ms, ref = timed(bits, n, {"PYKMER_B200_GRAM": "i8"})
         steps = WORDS / 2 / sms
         print(f"N={n:3d} i8            {ref_ms:7.3f} ms   {ref_ms * 1.965e6 / (2 * steps):6.1f} clk per K=32 step", flush=True)
@@ -53,7 +53,7 @@ def main():
         for layout, src in (("rows ", bits), ("tiled", tiled)):
             for diag in (0, 2):
                 ms, G = timed(src, n, {"PYKMER_B200_GRAM": "f4", "PYKMER_B200_GRAM_DIAG": str(diag),
-                                       "PYKMER_B200_GRAM_TILED": "1" if layout == "tiled" else "0"})
+                                       "PYKMER_B200_GRAM_TILED": "0" if layout == "rows " else "1"})
                 ok = "" if diag else (" exact" if torch.equal(G, ref) else " MISMATCH")
                 print(f"N={n:3d} f4 {layout} diag={diag} {ms:7.3f} ms   {ms * 1.965e6 / steps:6.1f} clk per K=64 step{ok}",
                       flush=True)
