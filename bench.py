@@ -96,6 +96,7 @@ class ClockSampler:
         self.rows, self.proc, self.idx = [], None, gpu_index
         self.thread, self.stop_flag, self.sm, self.mx, self.reasons = None, False, [], [], set()
         self.timed = False                                   # samples are kept only while this is set
+        self.near, self.near_reasons = [], set()             # ... and, apart, those of the warm-up steps
 
     def _poll(self, nv, handle):
         names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
@@ -108,11 +109,11 @@ class ClockSampler:
                 bits = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
             except Exception:
                 break
-            if self.timed:
-                self.sm.append(float(mhz))
-                for name, bit in names:
-                    if bits & bit:
-                        self.reasons.add(name)
+            sm, reasons = (self.sm, self.reasons) if self.timed else (self.near, self.near_reasons)
+            sm.append(float(mhz))
+            for name, bit in names:
+                if bits & bit:
+                    reasons.add(name)
             time.sleep(0.002)
 
     def start(self):
@@ -151,6 +152,14 @@ class ClockSampler:
         if self.thread is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
+            if not self.sm and self.near:
+                # a timed region of a few milliseconds can fall between two polls: report the samples
+                # of the warm-up steps of the same kernel that ran immediately before it, and say so
+                tail = self.near[-16:]
+                return {"sm_mhz": statistics.median(tail), "sm_max_mhz": self.mx[0],
+                        "reasons": sorted(self.near_reasons), "samples": len(tail),
+                        "how": "NVML, polled every ~2 ms; the timed region was shorter than one poll, these "
+                               "are the samples of the warm-up steps immediately before it"}
             if not self.sm:
                 return {"sm_mhz": None, "sm_max_mhz": self.mx[0] if self.mx else None, "reasons": ["no samples"]}
             return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx[0], "reasons": sorted(self.reasons),
