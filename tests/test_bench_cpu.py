@@ -1,0 +1,39 @@
+"""bench.py's reference arm (--impl reference: the C port of the reference algorithm on the host
+cores) keeps the JSON contract the driver parses; rank != 0 of a multi-rank launch prints nothing."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+        "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def _run(extra, env=None):
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+    assert res.returncode == 0, res.stderr[-2000:]
+    return res.stdout.strip().splitlines()
+
+
+@pytest.mark.parametrize("extra,metric", [
+    (["--kmer", "11", "--scale", "0.004", "--cpu-sample-mbp", "2"], "indexer_bp_per_s_K11"),
+    (["--workload", "merger", "--kmer", "9", "--samples", "6"], "merger_bitmask_GB_per_s"),
+])
+def test_reference_arm_prints_one_contract_line(extra, metric):
+    lines = _run(extra)
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert KEYS <= set(line) and line["impl"] == "reference" and line["metric"] == metric
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    assert _run(["--kmer", "11", "--scale", "0.004"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
