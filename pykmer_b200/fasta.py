@@ -23,7 +23,6 @@ guessing.  Header lines may hold any UTF-8.
 from __future__ import annotations
 
 import gzip
-import io
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 from typing import BinaryIO, Iterator, List, Optional, Tuple

@@ -3,7 +3,6 @@
 (analysis aid, not product code)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import bench
 from oracle import oracle
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.125
