@@ -1,19 +1,25 @@
-// gram_f4.cu -- EXPERIMENT (opt-in: PYKMER_B200_GRAM=f4; the default stays gram_i8.cu): the merger's
-// Gram matrix G = B * B^T (merger.py:136-176 over tools.py:473-482) with the presence bits
-// expanded to 4-bit E2M1 numbers instead of bytes, on the block-scaled FP4 tensor path
-// (tcgen05.mma kind::mxf4, K = 64 per instruction, all scale factors 1.0).
+// gram_f4.cu -- the merger's Gram matrix G = B * B^T (merger.py:136-176 over tools.py:473-482) on the
+// block-scaled FP4 tensor path: the presence bits are expanded to 4-bit E2M1 numbers (tcgen05.mma
+// kind::mxf4, K = 64 per instruction, all scale factors 1.0).  The default for <= 256 samples, fed
+// with TILED masks (pk_gram_tiled_device); PYKMER_B200_GRAM=f4 runs it on row-major masks.
 //
-// Why: gram_i8.cu is bound by shared-memory traffic -- a bit becomes a byte, so a K=32 step of R
-// rows stores 32 R bytes and the MMAs read them back -- with the tensor pipe level with it at
-// R = 256.  A nibble per bit halves the bytes per k-mer on both sides and the FP4 pipe runs at
-// twice the int8 rate.
+// Why not a byte per bit (gram_i8.cu): that kernel is bound by shared-memory traffic -- a K=32 step of
+// R rows stores 32 R bytes and the MMAs read them back -- with the tensor pipe level with it at
+// R = 256.  A nibble per bit halves the bytes per k-mer on both sides and the FP4 pipe runs at twice
+// the int8 rate.  Measured (K=15): N=255 34.1 -> 17.0 ms, N=50 6.50 -> 3.69 ms.
+//
+// Why tiled masks: with bits[row][word] every row is its own stream and 148 CTAs x 256 rows keep
+// ~38,000 of them open -- a DRAM page is opened for one 128-byte line, and the gather stops at
+// 1.1 TB/s whatever the prefetch depth, load width or row stride (profiles/r01f_gram_sweep_*.txt).  With
+// bits[word / 32][row][32 words] the lines of all rows for the same 1024 k-mers lie side by side and
+// a CTA reads one sequential stream (tile_rows below).
 //
 // Exactness: a product is 0 or 1 and the FP32 accumulator of one CTA sees at most 2^24 k-mers
 // (the launch sizes the grid for that), so every partial sum is an integer FP32 holds exactly --
 // PROVIDED the tensor core adds into the full 24-bit significand.  That is a property of the
-// hardware, not of the instruction set, and it is checked, not assumed: tests/ run this kernel
-// against gram_i8 / the oracle on all-ones masks (every partial sum from 64 up to 2^24 occurs) and
-// on random ones.  Until those tests have passed on the B200 this path stays off by default.
+// hardware, not of the instruction set, and it is tested, not assumed: tests/ run this kernel
+// against gram_i8 / the oracle / the reference's golden matrices, on all-ones masks (every partial
+// sum from 64 up to 2^24 occurs: test_gram_f4_every_partial_sum_is_exact) and on random ones.
 //
 // Layout, roles and pipeline are those of gram_i8.cu.  Differences:
 //   * one 32-bit mask word -> 16 bytes (32 nibbles, 0x2 = 1.0 in E2M1) by two masks and four

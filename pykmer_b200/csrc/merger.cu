@@ -4,8 +4,9 @@
 // (tools.py:439-493: s_valid/o_valid/c_valid and the three sums) and the pair
 // loop of merge (merger.py:136-176), recast as a thresholded presence-bitmask
 // Gram matrix so every sample is read once instead of N-1 times:
-//   k_threshold_pack   uint8 table -> 1 bit per k-mer  (min <= c <= max)
-//   k_gram_popc        G[k][l] += popcount(bits[k] & bits[l]), 4x4 register tiles
+//   k_threshold_pack   uint8 table -> 1 bit per k-mer  (min <= c <= max), row-major or tiled masks
+//   (gram_f4.cu, gram_i8.cu: the Gram matrix on the tensor cores -- the default up to 256 samples)
+//   k_gram_popc        G[k][l] += popcount(bits[k] & bits[l]), 4x4 register tiles (any N)
 //   k_pair_counts      the literal three sums for one pair of tables
 //   k_synth_table      deterministic synthetic tables for the benchmark
 #include <algorithm>
@@ -317,8 +318,9 @@ PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, 
     if (!accumulate)
         PK_CUDA(cudaMemsetAsync(gram_dev, 0, (size_t)nsamples * nsamples * sizeof(int64_t), st));
     if (words == 0) return PK_OK;
-    // Two exact implementations: tcgen05 kind::i8 tensor-core contraction (N <= 256, the
-    // default: 7x faster at N = 50, profiles/) and AND + popcount on the ALUs (any N).
+    // Row-major masks: tcgen05 kind::i8 tensor-core contraction (N <= 256, the default HERE; the
+    // merger itself packs tiled masks and calls pk_gram_tiled_device), kind::mxf4 on request, and
+    // AND + popcount on the ALUs (any N).
     const char *algo = getenv("PYKMER_B200_GRAM");
     const bool want_popc = algo && strcmp(algo, "popc") == 0;
     if (algo && strcmp(algo, "f4") == 0 && nsamples <= 256) {     // FP4 path on row-major masks (sweeps)

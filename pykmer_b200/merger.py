@@ -5,7 +5,7 @@ calculate_distance :62-78, merge :80-210, main :213-239): same command line,
 validation, output names and file contents.  Where the reference scans every
 pair of files (N(N-1)/2 tasks in a multiprocessing.Pool), this module reads each
 table once, thresholds and bit-packs it on the GPU, and obtains the whole matrix
-from one Gram contraction G = B * B^T (pykmer_b200/csrc/merger.cu, gram_i8.cu):
+from one Gram contraction G = B * B^T (pykmer_b200/csrc/merger.cu, gram_f4.cu, gram_i8.cu):
 matrix[k, l] = (G[k,k], G[l,l], G[k,l]).
 
 The reference leaves the diagonal of the matrix uninitialised (merger.py:136);
