@@ -265,6 +265,17 @@ def threshold_pack(table: np.ndarray, min_count: int = 1, max_count: int = 255):
     return bits
 
 
+def tile_masks(rows: np.ndarray) -> np.ndarray:
+    """Row-major mask words (N, words) -> the tiled layout of include/pykmer_b200.h, flat:
+    word g of sample r at [(g // 32) * N * 32 + r * 32 + g % 32]; the last tile is zero-padded."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    n, words = rows.shape
+    tiles = (words + 31) // 32
+    padded = np.zeros((n, tiles * 32), dtype=np.uint32)
+    padded[:, :words] = rows
+    return np.ascontiguousarray(padded.reshape(n, tiles, 32).transpose(1, 0, 2)).reshape(-1)
+
+
 def gram_from_bits(bits: np.ndarray) -> np.ndarray:
     """G[k,l] = popcount(bits[k] & bits[l]) -- the Gram form of the pair loop."""
     N = bits.shape[0]

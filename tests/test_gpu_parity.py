@@ -355,11 +355,8 @@ def test_tiled_masks_pack_and_gram_vs_oracle(env, N, n):
         else:
             dev.threshold_pack_tiled(t, lo, hi, bits, s, N)
     rows = np.stack([oracle.threshold_pack(tables[s], lo, hi) for s in range(N)])
-    tiles = (words + 31) // 32
-    got = bits.cpu().numpy().view(np.uint32)[:tiles * N * 32].reshape(tiles, N, 32)
-    want_tiled = np.zeros((N, tiles * 32), dtype=np.uint32)
-    want_tiled[:, :words] = rows
-    assert np.array_equal(got, want_tiled.reshape(N, tiles, 32).transpose(1, 0, 2))
+    want_tiled = oracle.tile_masks(rows)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32)[:want_tiled.size], want_tiled)
     G = dev.gram_tiled(bits, N, words).cpu().numpy()
     if N * words > 2_000_000:
         B = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little").astype(np.float64)

@@ -137,3 +137,19 @@ def test_config1_syn10M(tmp_path):
     assert res["hist"] == gold["hist"]
     assert res["vals_sum"] == gold["vals_sum"] and res["vals_max"] == gold["vals_max"]
     assert hashlib.sha256(res["table"].tobytes()).hexdigest() == gold["output_file_cheksum"]
+
+
+def test_tiled_mask_layout_formula():
+    """The tiled layout the merger packs into (include/pykmer_b200.h): word g of sample r sits at
+    (g // 32) * N * 32 + r * 32 + g % 32; Gram matrices do not depend on the layout."""
+    rng = np.random.default_rng(9)
+    for n, words in ((1, 1), (3, 31), (5, 32), (7, 33), (50, 100)):
+        rows = rng.integers(0, 2 ** 32, size=(n, words), dtype=np.uint64).astype(np.uint32)
+        flat = oracle.tile_masks(rows)
+        assert flat.size == -(-words // 32) * n * 32
+        for r in range(n):
+            for g in (0, words // 2, words - 1):
+                assert flat[(g // 32) * n * 32 + r * 32 + g % 32] == rows[r, g]
+        back = flat.reshape(-1, n, 32).transpose(1, 0, 2).reshape(n, -1)
+        assert np.array_equal(back[:, :words], rows) and not back[:, words:].any()
+        assert np.array_equal(oracle.gram_from_bits(back), oracle.gram_from_bits(rows))
