@@ -370,3 +370,14 @@ def test_gzi_index_layout_and_range_reads(tmp_path, capsys):
         fh.write(blob[:-3])
     with pytest.raises(OSError):
         bgzf.read_index(out + ".gzi")
+
+
+def test_known_answer_generator_matches_the_reference_construction(tmp_path):
+    """test.py (drop-in for the reference's test.py:8-33): the K=5 file equals, text for text, the
+    input the reference itself indexed for tests/golden (allkmers_05: every 5-mer as a record)."""
+    res = subprocess.run([os.sys.executable, os.path.join(ROOT, "test.py"), "5", "3"], cwd=tmp_path,
+                         capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.split() == ["5", "3"]
+    made = gzip.open(tmp_path / "examples" / "example--05.fasta.gz").read()
+    assert made == gzip.open(os.path.join(GOLD, "inputs", "allkmers_05.fasta.gz")).read()
+    assert gzip.open(tmp_path / "examples" / "example--03.fasta.gz").read().count(b">") == 64
