@@ -162,6 +162,44 @@ def balanced_kmer_ranges(per_window: np.ndarray, nranks: int, window_log2: int, 
     return [(w0 << window_log2, min(total, w1 << window_log2)) for w0, w1 in owners]
 
 
+def analytic_kmer_ranges(total: int, nranks: int, kmers: float, align: int = 1 << 26,
+                         update_rate: float = 20e9, fill_rate: float = 7e12) -> List[Tuple[int, int]]:
+    """k-mer-axis shards [lo, hi) of about equal cost WITHOUT a planning pass, for the CLI's DIRECT
+    counting of very sparse tables (K >= 19).  cost(shard) = its share of the `kmers` table updates at
+    `update_rate` per second (measured 20 G/s) + its bytes of zero-fill at `fill_rate`
+    (measured 7.2 TB/s).  The share comes from the leading base of a canonical k-mer: min(fwd, rc)
+    starts with A, C, G, T with probability 7/16, 5/16, 3/16, 1/16 (either of two independent first
+    bases is the smaller one), uniform inside a quarter to first order -- equal ranges would leave
+    ranks 0 and 1 with 1.75x the mean.  Every rank computes the same cuts from the same three numbers;
+    cuts are multiples of `align` entries (a counting window of any mode)."""
+    if nranks <= 1 or total < nranks * align:
+        return [shard_range(total, r, nranks, align=min(align, ALIGN)) for r in range(nranks)]
+    units = total // align                                   # the axis in whole windows
+    quarter = units / 4.0
+    shares = (7 / 16, 5 / 16, 3 / 16, 1 / 16)
+    per_unit_fill = align / fill_rate
+
+    def cost_upto(u: float) -> float:                        # cost of [0, u) windows
+        k = 0.0
+        for q, share in enumerate(shares):
+            k += share * min(max(u - q * quarter, 0.0), quarter) / quarter
+        return kmers * k / update_rate + u * per_unit_fill
+
+    whole = cost_upto(float(units))
+    cuts = [0]
+    for r in range(1, nranks):
+        want, lo, hi = whole * r / nranks, cuts[-1] + 1, units - (nranks - r)
+        while lo < hi:                                        # smallest u with cost_upto(u) >= want
+            mid = (lo + hi) // 2
+            if cost_upto(float(mid)) < want:
+                lo = mid + 1
+            else:
+                hi = mid
+        cuts.append(lo)
+    cuts.append(units)
+    return [(cuts[r] * align, total if r == nranks - 1 else cuts[r + 1] * align) for r in range(nranks)]
+
+
 def slice_bounds(nbytes: int, rank: int, nranks: int, align: int = 16) -> Tuple[int, int]:
     """Byte slice [a, b) of the stream scanned by `rank` (16-byte aligned starts)."""
     def cut(r: int) -> int:

@@ -126,7 +126,15 @@ def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool
     from .tools import gen_checksum
 
     rank, world = pdist.world()
-    lo, hi = pdist.shard_range(header.data_size, rank, world)
+    if header.kmer_len >= 19:
+        # very sparse table, counted DIRECT: balance updates + zero-fill analytically (canonical k-mers
+        # crowd the low values).  The k-mer count is not known before the file is read; every rank
+        # derives the same estimate from the size of the input (about 3.5 bases per compressed byte).
+        size = os.path.getsize(header.input_file_path)
+        packed = header.input_file_path.endswith((".gz", ".bgz"))
+        lo, hi = pdist.analytic_kmer_ranges(header.data_size, world, size * (3.5 if packed else 1.0))[rank]
+    else:
+        lo, hi = pdist.shard_range(header.data_size, rank, world)
     t_start = time.perf_counter()
     error = None
     if rank == 0:

@@ -240,3 +240,37 @@ def test_merger_cli_as_a_multi_rank_job_writes_reference_files(tmp_path, nranks,
     assert "matrix Total" not in res[1][1]                      # one rank reports and writes
     res = multirank.run_cli(tmp_path, "merger", argv, nranks=nranks)       # refuses to overwrite (merger.py:99)
     assert all(rc not in (0, None) for rc, _ in res) and "AssertionError" in res[0][1]
+
+
+def test_analytic_kmer_ranges_tile_the_axis_and_balance_the_model():
+    """dist.analytic_kmer_ranges (the multi-GPU CLI at K >= 19): aligned cuts that tile the axis, every
+    shard non-empty, costs within a window of each other under the stated model, and the shares it
+    assumes (7/16, 5/16, 3/16, 1/16 by leading base) hold for canonical k-mers of random sequence."""
+    from pykmer_b200 import dist as pdist
+    T, align = 4 ** 19, 1 << 26
+    for n in (1, 2, 3, 4, 8):
+        for kmers in (0.0, 1e6, 780e6, 3e9):
+            rs = pdist.analytic_kmer_ranges(T, n, kmers)
+            assert rs[0][0] == 0 and rs[-1][1] == T and all(a[1] == b[0] for a, b in zip(rs[:-1], rs[1:]))
+            assert all(lo < hi and lo % align == 0 for lo, hi in rs)
+            if n > 1 and kmers == 780e6:
+                def cost(lo, hi):
+                    k = 0.0
+                    for q, share in enumerate((7 / 16, 5 / 16, 3 / 16, 1 / 16)):
+                        a, b = max(lo, q * T // 4), min(hi, (q + 1) * T // 4)
+                        k += share * max(b - a, 0) / (T // 4)
+                    return kmers * k / 20e9 + (hi - lo) / 7e12
+                costs = [cost(lo, hi) for lo, hi in rs]
+                window = kmers * (7 / 16) * align / (T // 4) / 20e9 + align / 7e12
+                assert max(costs) - min(costs) <= 2 * window + 1e-12
+                assert rs[0][1] - rs[0][0] < rs[-1][1] - rs[-1][0]          # crowded low end: narrower shards
+    small = pdist.analytic_kmer_ranges(4 ** 9, 4, 1e6)                       # tiny table: plain equal ranges
+    assert small[0][0] == 0 and small[-1][1] == 4 ** 9
+    # the assumed shares, on random 9-mers
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, 4, size=(200_000, 9))
+    w = 4 ** np.arange(8, -1, -1)
+    fwd, rc = codes @ w, (3 - codes[:, ::-1]) @ w
+    lead = np.minimum(fwd, rc) // 4 ** 8
+    got = np.bincount(lead, minlength=4) / lead.size
+    assert np.allclose(got, [7 / 16, 5 / 16, 3 / 16, 1 / 16], atol=0.01)
