@@ -141,6 +141,44 @@ def merge(project_name: str, indexes: List[Path], min_count: int = DEFAULT_MIN_C
     return entries, matrix
 
 
+class _SliceSource:
+    """Entries [lo, hi) of one sample's table (the file its JSON names, .bgz preferred:
+    tools.py:185-196), handed out slab by slab into the caller's buffers."""
+
+    def __init__(self, header: Header, lo: int, hi: int):
+        path = header.index_file
+        self.left = hi - lo
+        self.arr, self.fh, self.pos = None, None, 0
+        if path.endswith(PACKED):
+            whole = lo == 0 and hi == header.data_size
+            self.arr = header.read_table(path) if whole else header.read_table_slice(lo, hi, path)
+        else:
+            import os
+            assert os.path.getsize(path) == header.data_size, \
+                f"{path}: {os.path.getsize(path)} bytes, expected {header.data_size}"
+            self.fh = open(path, "rb", buffering=0)
+            self.fh.seek(lo)
+
+    def read_into(self, buf: np.ndarray) -> int:
+        n = min(buf.size, self.left)
+        if self.arr is not None:
+            buf[:n] = self.arr[self.pos:self.pos + n]
+        else:
+            view, got = memoryview(buf)[:n], 0
+            while got < n:
+                step = self.fh.readinto(view[got:])
+                assert step, "table file ended early"
+                got += step
+        self.pos += n
+        self.left -= n
+        return n
+
+    def close(self) -> None:
+        if self.fh is not None:
+            self.fh.close()
+        self.arr = None
+
+
 def merge_tables(headers: List[Header], min_count: int, max_count: int, device: int = 0,
                  slab_bytes: int = 256 << 20) -> np.ndarray:
     """Read each sample's table once (the file named by its JSON, .bgz preferred:
@@ -165,29 +203,38 @@ def merge_tables(headers: List[Header], min_count: int, max_count: int, device: 
     tiled = dev.use_tiled_masks(N)       # <= 256 samples: tiled masks + the FP4 tensor-core Gram kernel
     with dev.device_scope(device):
         bits = dev.tiled_masks(words, N) if tiled else dev.zeros((N, stride), torch.int32)
-        stage = dev.pinned_empty(max(1, min(n_own, slab_bytes)))
+        # Two pinned slabs in turn: a helper thread reads / inflates the next slab straight into one
+        # while the other crosses PCIe.  A raw .kin is read at its offset with readinto (no
+        # intermediate array); a .kin.bgz has to be inflated first (the slice only, Header.read_table_slice).
+        ring = [dev.pinned_empty(max(1, min(n_own, slab_bytes))) for _ in range(2)]
+        jobs = [(s, off) for s in range(N if n_own else 0) for off in range(0, n_own, slab_bytes)]
+        source: Dict[int, _SliceSource] = {}
 
-        def read(h: Header) -> np.ndarray:
-            assert h.data_size == T
-            return h.read_table() if world == 1 else h.read_table_slice(lo, hi)
+        def read(j: int) -> int:
+            s, off = jobs[j]
+            if off == 0:
+                assert headers[s].data_size == T
+                source[s] = _SliceSource(headers[s], lo, hi)
+            n = source[s].read_into(ring[j & 1].numpy())
+            if off + n >= n_own:
+                source.pop(s).close()
+            return n
 
-        # the next sample is read / inflated on a helper thread while this one crosses PCIe
         from concurrent.futures import ThreadPoolExecutor
         reader = ThreadPoolExecutor(max_workers=1)
-        ahead = reader.submit(read, headers[0]) if n_own else None
-        for s in range(N if n_own else 0):
-            table = ahead.result()
-            ahead = reader.submit(read, headers[s + 1]) if s + 1 < N else None
-            assert table.size == n_own
-            for off in range(0, n_own, slab_bytes):
-                n = min(slab_bytes, n_own - off)
-                dev.stream_sync()                              # stage is reused
-                stage.numpy()[:n] = table[off:off + n]
-                d = dev.upload(stage[:n], non_blocking=True)
-                if tiled:
-                    dev.threshold_pack_tiled(d, min_count, max_count, bits, s, N, first_word=off // 32)
-                else:
-                    dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
+        ahead = reader.submit(read, 0) if jobs else None
+        for j, (s, off) in enumerate(jobs):
+            n = ahead.result()
+            assert n == min(slab_bytes, n_own - off)
+            if j + 1 < len(jobs):
+                dev.stream_sync()                              # the other slab has crossed: refill it
+                ahead = reader.submit(read, j + 1)
+            d = dev.upload(ring[j & 1][:n], non_blocking=True)
+            if tiled:
+                dev.threshold_pack_tiled(d, min_count, max_count, bits, s, N, first_word=off // 32)
+            else:
+                dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
+        dev.stream_sync()
         reader.shutdown()
         if n_own:
             G = dev.gram_tiled(bits, N, words) if tiled else dev.gram(bits, words=words)

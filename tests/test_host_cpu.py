@@ -381,3 +381,26 @@ def test_known_answer_generator_matches_the_reference_construction(tmp_path):
     made = gzip.open(tmp_path / "examples" / "example--05.fasta.gz").read()
     assert made == gzip.open(os.path.join(GOLD, "inputs", "allkmers_05.fasta.gz")).read()
     assert gzip.open(tmp_path / "examples" / "example--03.fasta.gz").read().count(b">") == 64
+
+
+def test_merge_tables_streams_slabs_in_order(tmp_path, monkeypatch):
+    """merger.merge_tables host logic (slab ring, helper-thread reads, raw / BGZF / plain-gzip
+    sources) with the device layer replaced by tests/fake_device.py: several slabs per sample,
+    result equal to the oracle's pair loop."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_device
+    import multirank
+    import pykmer_b200
+    from pykmer_b200 import merger
+    monkeypatch.setitem(_sys.modules, "pykmer_b200.device", fake_device)
+    monkeypatch.setattr(pykmer_b200, "device", fake_device, raising=False)
+    for packed in (False, True):
+        sub = tmp_path / ("bgzf" if packed else "gz")
+        sub.mkdir()
+        kins, tables = multirank.golden_merger_inputs(sub, bgzf_packed=packed)
+        headers = [Header(k, index_file=k) for k in kins]
+        want = oracle.merge_matrix(np.stack(list(tables)), 2, 10)
+        for slab in (4096, 16384, 1 << 20):                      # 4 slabs, exactly one, larger than the table
+            got = merger.merge_tables(headers, 2, 10, slab_bytes=slab)
+            assert np.array_equal(got, want), (packed, slab)
