@@ -242,6 +242,11 @@ int pk_bgzf_inflate(const uint8_t *comp, size_t comp_len, uint8_t *out, size_t o
                     size_t *consumed, size_t *produced, int threads);
 int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_out, uint32_t *flags,
                    int threads);
+/* pk_fasta_find_headers: offsets of every '>' that starts a line of text[0, n) (offset 0 or right after
+ * '\n' / '\r') -- where parse_fasta opens a record (indexer.py:62-80); ascending, on `threads` threads.
+ * *count = number found, also when it exceeds cap (only the first cap are stored). */
+int pk_fasta_find_headers(const uint8_t *text, size_t n, uint64_t *pos_out, size_t cap, size_t *count,
+                          int threads);
 /* pk_bgzf_deflate: the output side -- what the documented workflow does with the external
  * `bgzip -l 9` after every indexer run (README.md:26,261-269; data/README.md:24) and what the
  * merger reads back (tools.py:296-302).  src[0, n) becomes ceil(n / 0xFF00) independent BGZF

@@ -28,7 +28,7 @@ SYMBOLS = (
     "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
     "pk_table_stats_device",
     "pk_threshold_pack_device", "pk_gram_device", "pk_threshold_pack_tiled_device", "pk_gram_tiled_device", "pk_pair_counts_device", "pk_merge_host",
-    "pk_synth_table_device", "pk_bgzf_inflate", "pk_fasta_clean", "pk_bgzf_deflate",
+    "pk_synth_table_device", "pk_bgzf_inflate", "pk_fasta_clean", "pk_bgzf_deflate", "pk_fasta_find_headers",
 )
 
 
@@ -96,6 +96,7 @@ def _load() -> ctypes.CDLL:
         "pk_bgzf_inflate": [vp, sz, vp, sz, c.POINTER(sz), c.POINTER(sz), i32],
         "pk_fasta_clean": [vp, sz, vp, c.POINTER(sz), c.POINTER(c.c_uint32), i32],
         "pk_bgzf_deflate": [vp, sz, vp, sz, c.POINTER(sz), vp, i32, i32],
+        "pk_fasta_find_headers": [vp, sz, vp, sz, c.POINTER(sz), i32],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -271,3 +271,42 @@ PK_API int pk_bgzf_deflate(const uint8_t *src, size_t n, uint8_t *out, size_t ou
     *produced = opos;
     return PK_OK;
 }
+
+// Offsets of the headers of a block of whole lines: every '>' that starts a line (offset 0, or right
+// after '\n' / '\r') -- the places where parse_fasta opens a record (indexer.py:62-80; a '>' anywhere
+// else in a line is just an invalid base).  Ascending; *count is the number found even when it
+// exceeds cap (the first cap are stored; the caller retries with more room).
+PK_API int pk_fasta_find_headers(const uint8_t *text, size_t n, uint64_t *pos_out, size_t cap, size_t *count,
+                                 int threads) {
+    PK_REQUIRE(count != nullptr, "pk_fasta_find_headers: NULL count");
+    PK_REQUIRE(n == 0 || text != nullptr, "pk_fasta_find_headers: NULL text");
+    PK_REQUIRE(cap == 0 || pos_out != nullptr, "pk_fasta_find_headers: NULL output");
+    *count = 0;
+    if (n == 0) return PK_OK;
+    const size_t grain = (size_t)4 << 20;
+    const int nt = thread_count(threads, (n + grain - 1) / grain);
+    std::vector<std::vector<uint64_t>> found((size_t)nt);
+    auto scan = [&](int t) {
+        const size_t a = n / (size_t)nt * (size_t)t, b = t == nt - 1 ? n : n / (size_t)nt * (size_t)(t + 1);
+        size_t i = a;
+        while (i < b) {
+            const uint8_t *hit = (const uint8_t *)memchr(text + i, '>', b - i);
+            if (!hit) break;
+            const size_t p = (size_t)(hit - text);
+            if (p == 0 || text[p - 1] == '\n' || text[p - 1] == '\r') found[(size_t)t].push_back(p);
+            i = p + 1;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(scan, t);
+    scan(0);
+    for (auto &th : pool) th.join();
+    size_t k = 0;
+    for (const auto &v : found)
+        for (uint64_t p : v) {
+            if (k < cap) pos_out[k] = p;
+            k++;
+        }
+    *count = k;
+    return PK_OK;
+}

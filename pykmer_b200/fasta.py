@@ -193,6 +193,8 @@ class FastaStream:
         # native = the two passes over the text (BGZF inflate, newline stripping) run in
         # libpykmer_b200.so on all cores (csrc/ingest.cpp); False = this module's own Python
         # path, which is also what every unusual block of text falls back to.
+        import queue
+        self._text_pool: "queue.SimpleQueue" = queue.SimpleQueue()   # text buffers handed back by the consumer
         self.native = _native_lib() is not None if native is None else bool(native)
         if self.native and _native_lib() is None:
             raise ImportError("pykmer_b200.fasta: native ingest asked for, libpykmer_b200.so is missing")
@@ -243,8 +245,10 @@ class FastaStream:
             if p == 0 or buf[p - 1] in (10, 13):
                 if p > cur:
                     self._sequence_block(buf[cur:p], out)
-                e1, e2 = buf.find(b"\n", p), buf.find(b"\r", p)
-                end = min(x for x in (e1, e2, n) if x >= 0)
+                end = buf.find(b"\n", p)
+                end = n if end < 0 else end
+                cr = buf.find(b"\r", p, end)
+                end = cr if cr >= 0 else end
                 self._open_record(buf[p + 1:end], out)
                 cur = end
                 p = buf.find(b">", end)
@@ -324,8 +328,16 @@ class FastaStream:
         eof = False
         with (open(self.path, "rb") if bgzf else open_binary(self.path)) as fh:
             while True:
-                # a BGZF member inflates to at most 64 KiB: keep room for one beyond the tail
-                text = bytearray(len(tail) + (max(self.chunk_bytes, 1 << 16) if bgzf else self.chunk_bytes))
+                # a BGZF member inflates to at most 64 KiB: keep room for one beyond the tail.  The
+                # buffers go round (a fresh 64 MiB bytearray is zero-filled and page-faulted in each
+                # time); nothing beyond `fill` is ever read, so stale bytes do no harm.
+                want = len(tail) + (max(self.chunk_bytes, 1 << 16) if bgzf else self.chunk_bytes)
+                text = None
+                while text is None or len(text) < want:
+                    try:
+                        text = self._text_pool.get_nowait()
+                    except Exception:
+                        text = bytearray(want + (1 << 12))
                 text[:len(tail)] = tail
                 fill = len(tail)
                 if bgzf:
@@ -356,7 +368,8 @@ class FastaStream:
                 if done:
                     yield text, fill, True
                     return
-                cut = max(text.rfind(b"\n", 0, fill), text.rfind(b"\r", 0, fill))
+                cut = text.rfind(b"\n", 0, fill)           # last line terminator: a \r counts only if it
+                cut = max(cut, text.rfind(b"\r", max(cut, 0), fill))   # comes after the last \n
                 if cut < 0:                                # no whole line yet: grow the tail
                     tail = bytes(text[:fill])
                     continue
@@ -401,32 +414,46 @@ class FastaStream:
                 dst = np.empty(need, dtype=np.uint8)
             opos = 0
             cur = 0
-            p = text.find(b">", 0, n)
-            while p >= 0:
-                if p == 0 or text[p - 1] in (10, 13):
-                    opos = self._clean_into(text, cur, p, dst, opos)
-                    e1, e2 = text.find(b"\n", p, n), text.find(b"\r", p, n)
-                    end = min(x for x in (e1, e2, n) if x >= 0)
-                    if self._open:                         # close the previous record
-                        dst[opos] = SEPARATOR
-                        opos += 1
-                        self._pos += 1
-                    self.names.append(bytes(text[p + 1:end]).decode("utf-8").rstrip())
-                    self.starts.append(self._pos)
-                    self.lengths.append(0)
-                    self._open = True
-                    cur = end
-                    p = text.find(b">", end, n)
-                else:
-                    p = text.find(b">", p + 1, n)          # a '>' inside a sequence line: an invalid base
+            for p in self._header_offsets(text, n):        # every '>' that starts a line
+                if p < cur:
+                    continue                               # inside the previous header line (lone \r quirks)
+                opos = self._clean_into(text, cur, p, dst, opos)
+                end = text.find(b"\n", p, n)               # the header line ends at the first \n or \r;
+                end = n if end < 0 else end                # look for \r only before that \n (not to
+                cr = text.find(b"\r", p, end)              # the end of a 64 MiB chunk of Unix text)
+                end = cr if cr >= 0 else end
+                if self._open:                             # close the previous record
+                    dst[opos] = SEPARATOR
+                    opos += 1
+                    self._pos += 1
+                self.names.append(bytes(text[p + 1:end]).decode("utf-8").rstrip())
+                self.starts.append(self._pos)
+                self.lengths.append(0)
+                self._open = True
+                cur = end
             opos = self._clean_into(text, cur, n, dst, opos)
             if last and self._open:
                 dst[opos] = SEPARATOR
                 opos += 1
                 self._pos += 1
                 self._open = False
+            self._text_pool.put(text)                      # the producer may fill it again
             if opos:
                 yield dst[:opos]
+
+    def _header_offsets(self, text: bytearray, n: int):
+        """Offsets in text[:n] of the '>' that start a line, ascending (pk_fasta_find_headers, all cores)."""
+        import ctypes
+        nat = _native_lib()
+        cap = 1 << 12
+        while True:
+            pos = np.empty(cap, dtype=np.uint64)
+            count = ctypes.c_size_t(0)
+            nat.check(nat.lib.pk_fasta_find_headers(_addr(text, 0), n, pos.ctypes.data, cap, ctypes.byref(count),
+                                                    self.threads))
+            if count.value <= cap:
+                return pos[:count.value].tolist()
+            cap = count.value
 
     @staticmethod
     def _prefetch(gen, depth: int = 2):
