@@ -404,3 +404,19 @@ def test_merge_tables_streams_slabs_in_order(tmp_path, monkeypatch):
         for slab in (4096, 16384, 1 << 20):                      # 4 slabs, exactly one, larger than the table
             got = merger.merge_tables(headers, 2, 10, slab_bytes=slab)
             assert np.array_equal(got, want), (packed, slab)
+
+
+def test_library_carries_the_tensor_core_instructions():
+    """The built sm_100a library really holds the 5th-generation tensor-core code paths: UTCOMMA
+    (tcgen05.mma kind::mxf4, gram_f4.cu), UTCIMMA (kind::i8, gram_i8.cu), TMEM loads / stores."""
+    import shutil as _shutil
+    tool = _shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not installed")
+    from pykmer_b200 import _native as nat
+    res = subprocess.run([tool, "-sass", "-arch", "sm_100a", nat.LIB_PATH], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-500:]
+    sass = res.stdout
+    for mnemonic in ("UTCOMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert "k_gram_f4" in sass and "k_gram_i8" in sass
