@@ -196,18 +196,24 @@ int pk_threshold_pack_device(const uint8_t *table_dev, size_t n, int min_count, 
  * overwrites gram_dev, 1 adds to it (k-mer-axis slabs / shards). */
 int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
                    int64_t *gram_dev, int accumulate, pk_stream stream);
-/* Tiled masks -- the layout the tensor-core Gram kernel streams best (up to PK_TILED_MAX_SAMPLES
- * samples).  With row-major masks every sample is its own stream and a CTA gathers 128 bytes from
- * each of them per step: DRAM sees ~38,000 interleaved streams and delivers ~1.1 TB/s.  Here the
+/* Tiled masks -- the layout the tensor-core Gram kernel streams (any number of samples up to
+ * PK_TILED_MAX_SAMPLES; more than 256 run block pair by block pair).  With row-major masks every
+ * sample is its own stream and a CTA gathers 128 bytes from each of them per step: DRAM sees
+ * ~38,000 interleaved streams and delivers ~1.1 TB/s.  Here the
  * words of ALL samples for the same 1024 k-mers lie side by side,
  *     word g of sample r  ->  bits_tiled_dev[(g / 32) * nrows * 32 + r * 32 + g % 32],
  * so the gather is one sequential stream.  The buffer holds ceil(words / 32) * nrows * 32 words and
  * must be zeroed before packing (the padding of the last tile is read).
  * pk_threshold_pack_tiled_device packs n entries of sample `row` whose first entry is k-mer
  * 32 * first_word of that sample (slabs of a table may be packed by separate calls).
- * pk_gram_tiled_device is pk_gram_device on such a buffer (tcgen05 kind::mxf4, see gram_f4.cu);
- * `words` = words per sample. */
-#define PK_TILED_MAX_SAMPLES 256
+ * pk_gram_tiled_device is pk_gram_device on such a buffer (tcgen05 kind::mxf4 with FP32 accumulators
+ * that stay exact integers, see gram_f4.cu); `words` = words per sample.
+ * pk_gram_tiled_exact: *exact = 1 if the device accumulates 0/1 FP4 products exactly up to 2^24 (checked
+ * once per device by driving one accumulator through every integer from 2^23 up; cached), 0 if not --
+ * pk_gram_tiled_device then refuses (PK_ERR_STATE) and the caller packs row-major masks for
+ * pk_gram_device's integer kernels instead (pk_merge_host does so by itself). */
+#define PK_TILED_MAX_SAMPLES 4096
+int pk_gram_tiled_exact(int device, int *exact);
 int pk_threshold_pack_tiled_device(const uint8_t *table_dev, size_t n, size_t first_word, int min_count,
                                    int max_count, uint32_t *bits_tiled_dev, int row, int nrows,
                                    pk_stream stream);

@@ -27,7 +27,7 @@ SYMBOLS = (
     "pk_indexer_import_segments", "pk_indexer_pool_ipc_handle", "pk_indexer_open_peer_pool",
     "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
     "pk_table_stats_device",
-    "pk_threshold_pack_device", "pk_gram_device", "pk_threshold_pack_tiled_device", "pk_gram_tiled_device", "pk_pair_counts_device", "pk_merge_host",
+    "pk_threshold_pack_device", "pk_gram_device", "pk_threshold_pack_tiled_device", "pk_gram_tiled_device", "pk_gram_tiled_exact", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device", "pk_bgzf_inflate", "pk_fasta_clean", "pk_bgzf_deflate", "pk_fasta_find_headers",
 )
 
@@ -90,6 +90,7 @@ def _load() -> ctypes.CDLL:
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],
         "pk_threshold_pack_tiled_device": [vp, sz, sz, i32, i32, vp, i32, i32, vp],
         "pk_gram_tiled_device": [vp, i32, sz, vp, i32, vp],
+        "pk_gram_tiled_exact": [i32, c.POINTER(i32)],
         "pk_pair_counts_device": [vp, vp, sz, i32, i32, vp, vp],
         "pk_merge_host": [c.POINTER(vp), i32, sz, i32, i32, i32, vp],
         "pk_synth_table_device": [vp, i32, u64, u64, vp],

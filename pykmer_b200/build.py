@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 TOOLS = os.path.join(os.path.dirname(HERE), "tools")
-MICROBENCHES = ("microbench", "microbench2")
+MICROBENCHES = ("microbench", "microbench2", "microbench3")
 
 
 def build_microbench(force: bool = False) -> str:

@@ -15,10 +15,12 @@ int pk_set_error(int code, const char *fmt, ...);
 // tensor cores (tcgen05 kind::i8); nsamples <= 256.
 int pk_gram_i8_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
                       int64_t *gram_dev, int device, cudaStream_t st);
-// gram_f4.cu: the same contraction on the block-scaled FP4 path (tcgen05 kind::mxf4); nsamples <= 256.
-// tile_rows = 0: bits[row][word]; tile_rows = R: the tiled layout bits[word / 32][R][32].
-int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
-                      int64_t *gram_dev, int device, cudaStream_t st, int tile_rows);
+// gram_f4.cu: the same contraction on the block-scaled FP4 path (tcgen05 kind::mxf4) over TILED masks
+// bits[word / 32][nsamples][32]; words a multiple of 32; any nsamples (more than 256: block pairs).
+int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, int64_t *gram_dev, int device,
+                      cudaStream_t st);
+// 1 / 0: FP32 accumulation of 0/1 products is / is not exact up to 2^24 on this device (checked once)
+int pk_gram_f4_exact(int device);
 
 #define PK_CUDA(call)                                                                   \
     do {                                                                                \

@@ -1,38 +1,45 @@
 // gram_f4.cu -- the merger's Gram matrix G = B * B^T (merger.py:136-176 over tools.py:473-482) on the
 // block-scaled FP4 tensor path: the presence bits are expanded to 4-bit E2M1 numbers (tcgen05.mma
-// kind::mxf4, K = 64 per instruction, all scale factors 1.0).  The default for <= 256 samples, fed
-// with TILED masks (pk_gram_tiled_device); PYKMER_B200_GRAM=f4 runs it on row-major masks.
+// kind::mxf4, K = 64 per instruction, all scale factors 1.0).  The merger's default, fed with TILED
+// masks (pk_gram_tiled_device): bits[word / 32][row][32 words], so that the 128-byte lines of all
+// rows for the same 1024 k-mers lie side by side and a CTA reads one sequential stream (with
+// row-major masks 148 CTAs x 256 rows keep ~38,000 DRAM streams open and the gather stops at
+// 1.1 TB/s whatever the prefetch depth, load width or row stride: profiles/r01f_gram_sweep_*.txt).
 //
-// Why not a byte per bit (gram_i8.cu): that kernel is bound by shared-memory traffic -- a K=32 step of
-// R rows stores 32 R bytes and the MMAs read them back -- with the tensor pipe level with it at
-// R = 256.  A nibble per bit halves the bytes per k-mer on both sides and the FP4 pipe runs at twice
-// the int8 rate.  Measured (K=15): N=255 34.1 -> 17.0 ms, N=50 6.50 -> 3.69 ms.
+// Round 2: what bounded round 1's kernel was SHARED-MEMORY bandwidth, not the tensor pipe.  With both
+// operands in shared memory a K=64 step of 256 rows stores 8 KB and its three MMAs read 24 KB back
+// (A and B of each), 256 cycles at 128 B/clk against 192 cycles of tensor pipe (measured: 300); at
+// <= 64 samples the M=128 instruction read 4 KB of A, half of it padding, + 2 KB of B per 2 KB stored
+// (64 cycles, measured 65, against 32 of tensor pipe).  So now
+//   * the A operand comes from TENSOR MEMORY: the producer thread that expands row r of a tile is
+//     the thread that owns TMEM lane r (warp w reaches lanes 32 (w % 4) ..), so it writes the same
+//     16 + 16 bytes it stores to shared memory (the B operand) into 8 TMEM columns of its lane with
+//     tcgen05.st; the MMAs then read only B from shared memory (12 KB instead of 24 KB per step at
+//     256 rows);
+//   * <= 64 samples run as a DUAL slab: lanes 0..63 carry the samples over the first half of the
+//     CTA's k-mers, lanes 64..127 the same samples over the second half, one M=128 x N=128
+//     instruction covers two K=64 steps, and the epilogue adds the two diagonal 64 x 64 blocks -- no
+//     operand row is padding;
+//   * the row blocks are arguments (any two 128-row blocks of one tiled buffer), so more than 256
+//     samples run on the tensor cores too, block pair by block pair (pk_gram_f4_launch).
 //
-// Why tiled masks: with bits[row][word] every row is its own stream and 148 CTAs x 256 rows keep
-// ~38,000 of them open -- a DRAM page is opened for one 128-byte line, and the gather stops at
-// 1.1 TB/s whatever the prefetch depth, load width or row stride (profiles/r01f_gram_sweep_*.txt).  With
-// bits[word / 32][row][32 words] the lines of all rows for the same 1024 k-mers lie side by side and
-// a CTA reads one sequential stream (tile_rows below).
+// Exactness: a product is 0 or 1 and an FP32 accumulator sees at most 2^24 k-mers (the launch sizes
+// the grid for that), so every partial sum is an integer FP32 holds exactly -- PROVIDED the tensor
+// core adds into the full 24-bit significand.  That is a property of the hardware, not of the
+// instruction set: pk_gram_f4_exact() checks it once per device before the first launch (one CTA
+// driven through every integer from 2^23 to 2^24 - 2^15, odd ones included) and the merger falls back
+// to the integer kernels if it ever fails; tests/ run this kernel against gram_i8, AND + popcount, the
+// oracle and the reference's golden matrices, at BASELINE size too (tests/test_gpu_at_scale.py).
 //
-// Exactness: a product is 0 or 1 and the FP32 accumulator of one CTA sees at most 2^24 k-mers
-// (the launch sizes the grid for that), so every partial sum is an integer FP32 holds exactly --
-// PROVIDED the tensor core adds into the full 24-bit significand.  That is a property of the
-// hardware, not of the instruction set, and it is tested, not assumed: tests/ run this kernel
-// against gram_i8 / the oracle / the reference's golden matrices, on all-ones masks (every partial
-// sum from 64 up to 2^24 occurs: test_gram_f4_every_partial_sum_is_exact) and on random ones.
-//
-// Layout, roles and pipeline are those of gram_i8.cu.  Differences:
-//   * one 32-bit mask word -> 16 bytes (32 nibbles, 0x2 = 1.0 in E2M1) by two masks and four
-//     PRMT table look-ups (2 bits -> 1 byte); WHICH nibble a k-mer lands in is irrelevant as
-//     long as A and B agree, and they are the same tile;
-//   * the scale factors (UE8M0, 0x7F = 2^0) live in TMEM; every one of them is 1.0, so 32
-//     columns are filled with 0x7F bytes once and every MMA points both operands at them --
-//     whatever the layout, it reads ones;
-//   * 129..256 samples use the symmetry: three 128 x 128 accumulators (0,0), (0,1), (1,1) instead
-//     of two 128 x 256 ones -- 384 TMEM columns, which leaves room for the scale factors -- and the
-//     epilogue mirrors (0,1) into (1,0).
+// Which nibble a k-mer lands in is irrelevant as long as A and B agree: both are written from the
+// same registers (one 32-bit mask word -> 16 bytes = 32 nibbles, 0x2 = 1.0 in E2M1, by two masks and
+// four PRMT look-ups), 16 bytes = one K chunk of the shared-memory core matrix = 4 TMEM columns.
+// The scale factors (UE8M0, 0x7F = 2^0) live in TMEM; every one of them is 1.0, so 32 columns are
+// filled with 0x7F bytes once and every MMA points both operands at them.
 #include <algorithm>
+#include <mutex>
 #include <stdlib.h>
+#include <vector>
 
 #include "common.h"
 #include "tcgen05_util.h"
@@ -47,8 +54,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f4(int m, int n) {
     return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_f4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]^T
+__device__ __forceinline__ void mma_f4_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -56,6 +64,25 @@ __device__ __forceinline__ void mma_f4(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
         : "memory");
+}
+
+// D[tmem] (+)= A[tmem: lane = row, 8 columns = 64 E2M1] * B[smem descriptor]^T
+__device__ __forceinline__ void mma_f4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+}
+
+// 8 consecutive TMEM columns of this thread's lane <- two expanded mask words
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 a, const uint4 b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
 }
 
 // 2 mask bits -> one byte of two E2M1 nibbles: 00 -> 0x00, 01 -> 0x02, 10 -> 0x20, 11 -> 0x22
@@ -72,51 +99,62 @@ __device__ __forceinline__ uint4 expand_word_f4(uint32_t w) {
     return q;
 }
 
+// One TILE = 32 mask words per row = 1024 k-mers = 16 K=64 steps; a thread owns one row of the staged
+// block and always takes a whole 128-byte line of it.
+//   NP = 256: rows = two 128-row blocks (lo, hi); three accumulators (lo,lo), (lo,hi), (hi,hi); all
+//             256 producer threads fill every stage.
+//   NP = 128: one 128-row block, one accumulator; the two halves of the producer warps (warps 0..3,
+//             warps 4..7 -- both reach all 128 TMEM lanes) take alternate tiles.
+//             DUAL: the block is [<= 64 samples over the first half of the CTA's tiles; the same samples
+//             over the second half].
+constexpr int kTileWords = 32;
+constexpr int kTileSteps = 16;                          // K=64 steps per tile
+
 template <int NP>
 struct F4Cfg {
     static constexpr int kProducerWarps = 8;
     static constexpr int kProducerThreads = kProducerWarps * 32;
     static constexpr int kThreads = kProducerThreads + 32;            // + the MMA-issuing warp
-    // What bounds the producers is the gather of the mask words -- every row is its own stream,
-    // so a warp's load touches 32 different lines -- and that gather runs at about one line MISS
-    // per 8 cycles per SM however many loads are in flight (measured: 4 bytes per cycle per SM
-    // with 32 bytes used per miss, tools/gram_sweep.py).  So a thread always takes a whole 128-byte
-    // line of its row: for <= 128 rows a stage covers 16 K=64 steps (32 words = one line per row), for
-    // 256 rows -- where such a stage would be 128 KB -- a thread reads a line into registers and feeds
-    // four 4-step stages from it.
-    static constexpr int kGroups = NP == 64 ? 4 : (NP == 128 ? 2 : 1);   // groups fill different stages; <= kStages
-    static constexpr int kKB = NP == 256 ? 4 : 16;        // K=64 steps per stage (2 mask words per row each)
-    static constexpr int kWords = 2 * kKB;                // mask words per row per stage
-    static constexpr int kLineStages = 32 / kWords;       // stages one 128-byte line of a row feeds
-    static constexpr int kStages = NP == 64 ? 4 : (NP == 128 ? 3 : 5);
-    static constexpr int kTileBytes = NP * 32;            // one K=64 step of all NP rows (32 bytes per row)
-    static constexpr int kStageBytes = kKB * kTileBytes;
-    static constexpr int kAccN = NP == 256 ? 128 : NP;    // columns of one accumulator
+    static constexpr int kGroups = NP == 256 ? 1 : 2;                 // producer groups filling different tiles
+    static constexpr int kGroupThreads = kProducerThreads / kGroups;
+    static constexpr int kKB = NP == 256 ? 2 : 4;                     // K=64 steps per stage
+    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds
+    static constexpr int kStages = NP == 256 ? 3 : 6;
+    static constexpr int kStepBytes = NP * 32;                        // one K=64 step of all NP rows
+    static constexpr int kStageBytes = kKB * kStepBytes;              // 16 KB either way
     static constexpr int kAccs = NP == 256 ? 3 : 1;
-    static constexpr int kSfCol = kAccs * kAccN;          // scale factors behind the accumulators
-    static constexpr int kTmemCols = NP == 256 ? 512 : (NP == 128 ? 256 : 128);
-    static constexpr int kPad = 4096;                     // the M=128 descriptor of a 64-row tile overruns
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kPad + 256 + 1024;
-    static_assert(kGroups <= kStages && kSmem <= 227 * 1024, "a group may not lap the ring; shared memory budget");
+    static constexpr int kSfCol = kAccs * 128;                        // scale factors behind the accumulators
+    static constexpr int kACol = kSfCol + 32;                         // ring of A operands behind them
+    static constexpr int kAStageCols = kKB * 8 * (NP / 128);          // 8 columns per step and 128-row block
+    static constexpr int kTmemCols = 512;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 256 + 1024;
+    static_assert(kACol + kStages * kAStageCols <= kTmemCols, "TMEM budget");
+    static_assert(kStages >= kGroups && kSmem <= 227 * 1024, "ring depth / shared memory budget");
 };
 
-template <int NP, int AHEAD>
-__global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32_t *__restrict__ bits, int nsamples,
-                                                        size_t words, size_t stride_words,
-                                                        unsigned long long *__restrict__ gram, int diag, int tile_rows) {
-    // tile_rows: 0 = bits[row][word] with a row stride; R > 0 = the tiled layout
-    // bits[word / 32][R rows][32 words] (include/pykmer_b200.h) -- the lines of all rows for the same
-    // 1024 k-mers lie side by side, so a CTA's gather is one sequential stream instead of one per row.
-    // diag (PYKMER_B200_GRAM_DIAG, timing experiments only -- the result is then meaningless):
-    // bit 0 = producers skip the global loads, bit 1 = the issuer skips the MMAs, bit 2 = producers
-    // skip the shared-memory stores
+struct GramArgs {
+    const uint32_t *bits;      // tiled masks: word g of row r at ((g / 32) * tile_rows + r) * 32 + g % 32
+    size_t tiles;              // tiles per row (words / 32)
+    int tile_rows;             // rows of the tiled buffer
+    int row_lo, n_lo;          // first 128-row block: rows [row_lo, row_lo + n_lo)
+    int row_hi, n_hi;          // second block (NP = 256)
+    int acc_mask;              // NP = 256: bit 0 (lo,lo), bit 1 (lo,hi), bit 2 (hi,hi) -- which blocks to compute
+    unsigned long long *gram;  // [ld][ld]
+    int ld;
+    size_t tiles_per_cta;
+    int diag;                  // PYKMER_B200_GRAM_DIAG (timing experiments only -- the result is then meaningless):
+                               // bit 0 = no global loads, bit 1 = no MMAs, bit 2 = no operand stores
+};
+
+template <int NP, bool DUAL, bool ATM>
+__global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramArgs g) {
     using C = F4Cfg<NP>;
-    constexpr int kKB = C::kKB, kWords = C::kWords;
-    constexpr int kProducerThreads = C::kProducerThreads;
+    static_assert(!DUAL || NP == 128, "the dual slab is a form of the one-block kernel");
+    constexpr int kKB = C::kKB;
     constexpr int kMmaWarp = C::kProducerWarps;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *ctrl = smem + (size_t)C::kStages * C::kStageBytes + C::kPad;
+    uint8_t *ctrl = smem + (size_t)C::kStages * C::kStageBytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);               // [kStages]
     uint64_t *empty_bar = full_bar + C::kStages;                            // [kStages]
     uint64_t *done_bar = empty_bar + C::kStages;
@@ -124,25 +162,21 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // this CTA's slab of words, in whole stages of kWords words
-    const size_t total_stages = (words + kWords - 1) / kWords;
-    size_t per_cta = (total_stages + gridDim.x - 1) / gridDim.x;
-    per_cta = (per_cta + C::kLineStages - 1) / C::kLineStages * C::kLineStages;     // slabs start on a line
-    const size_t st0 = min(total_stages, (size_t)blockIdx.x * per_cta);
-    const size_t st1 = min(total_stages, st0 + per_cta);
-    const size_t nst = st1 - st0;
+    // this CTA's tiles [t0, t1); DUAL: first half [t0, tm) on lanes 0..63, second half [tm, t1) on 64..127
+    const size_t t0 = min(g.tiles, (size_t)blockIdx.x * g.tiles_per_cta);
+    const size_t t1 = min(g.tiles, t0 + g.tiles_per_cta);
+    const size_t tm = DUAL ? t0 + (t1 - t0 + 1) / 2 : t1;
+    const size_t ntiles = tm - t0;                                          // tiles this CTA steps through
+    const size_t nst = ntiles * C::kTileStages;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; s++) {
-            mbar_init(smem_u32(&full_bar[s]), kProducerThreads / C::kGroups);
+            mbar_init(smem_u32(&full_bar[s]), C::kGroupThreads);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(done_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero the pad once: it is read (and ignored) by the over-running A descriptor
-    for (int i = threadIdx.x; i < C::kPad / 16; i += blockDim.x)
-        reinterpret_cast<uint4 *>(smem + (size_t)C::kStages * C::kStageBytes)[i] = make_uint4(0, 0, 0, 0);
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)), "n"(C::kTmemCols));
@@ -169,127 +203,93 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp < kMmaWarp) {
-        // ------------------------------------------------------------ producers (see gram_i8.cu)
-        constexpr int kGroups = C::kGroups;
-        constexpr int kGroupThreads = kProducerThreads / kGroups;
-        constexpr int kRowsPerThread = NP / kGroupThreads;
-        constexpr int kAhead = AHEAD;              // stages of global loads in flight per group
-        const int group = threadIdx.x / kGroupThreads, tg = threadIdx.x % kGroupThreads;
-        const bool vec_ok = ((stride_words & 3) == 0) && (((uintptr_t)bits & 15u) == 0);
-        uint32_t wv[kAhead][kRowsPerThread][kWords];
-        auto row_ptr = [&](int row, size_t w0) -> const uint32_t * {       // w0: a multiple of kWords
-            if (tile_rows) return bits + (w0 >> 5) * ((size_t)tile_rows * 32) + (size_t)row * 32 + (w0 & 31);
-            return bits + (size_t)row * stride_words + w0;
-        };
-
-        auto fetch = [&](uint32_t (&dst)[kRowsPerThread][kWords], size_t it) {
-            const size_t w0 = (st0 + it) * kWords;
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerThread; rr++) {
-                const int row = tg + rr * kGroupThreads;
-#pragma unroll
-                for (int k = 0; k < kWords; k++) dst[rr][k] = 0;
-                if (diag & 1) continue;
-                if (row < nsamples && it < nst) {
-                    const uint32_t *src = row_ptr(row, w0);
-                    if (vec_ok && w0 + kWords <= words) {
-#pragma unroll
-                        for (int k = 0; k < kWords; k += 4) {
-                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + k));
-                            dst[rr][k] = q.x; dst[rr][k + 1] = q.y; dst[rr][k + 2] = q.z; dst[rr][k + 3] = q.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kWords; k++)
-                            if (w0 + k < words) dst[rr][k] = __ldg(src + k);
-                    }
-                }
-            }
-        };
-        auto produce = [&](const uint32_t (&src)[kRowsPerThread][kWords], size_t it) {
-            const int s = (int)(it % C::kStages);
-            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
-            mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-            uint8_t *stage = smem + (size_t)s * C::kStageBytes;
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerThread; rr++) {
-                const int row = tg + rr * kGroupThreads;
-                uint8_t *dst = stage + (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
-                if (diag & 4) continue;
-#pragma unroll
-                for (int k = 0; k < kKB; k++) {            // K=64 step k: words 2k, 2k+1 -> chunks 0, 1
-                    *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kTileBytes) = expand_word_f4(src[rr][2 * k]);
-                    *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kTileBytes + 128) =
-                        expand_word_f4(src[rr][2 * k + 1]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&full_bar[s]));
-        };
-
-        if constexpr (C::kLineStages == 1) {
-#pragma unroll
-            for (int p = 0; p < kAhead; p++) fetch(wv[p], (size_t)group + (size_t)p * kGroups);
-            for (size_t it = group; it < nst; it += (size_t)kAhead * kGroups) {
-#pragma unroll
-                for (int p = 0; p < kAhead; p++) {
-                    const size_t cur = it + (size_t)p * kGroups;
-                    if (cur < nst) {
-                        produce(wv[p], cur);
-                        fetch(wv[p], cur + (size_t)kAhead * kGroups);
-                    }
-                }
-            }
+        // ------------------------------------------------------------ producers
+        // thread -> TMEM lane r of quarter (warp % 4); half = warp / 4 picks the block (NP = 256)
+        // or the producer group (NP = 128)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const int group = NP == 256 ? 0 : half;
+        int src_row;                                   // row of the tiled buffer this thread expands
+        bool valid;
+        size_t first_tile = t0, my_tiles = ntiles;
+        if (NP == 256) {
+            src_row = half ? g.row_hi + r : g.row_lo + r;
+            valid = r < (half ? g.n_hi : g.n_lo);
+        } else if (DUAL) {
+            src_row = g.row_lo + (r & 63);
+            valid = (r & 63) < g.n_lo;
+            if (r >= 64) { first_tile = tm; my_tiles = t1 - tm; }
         } else {
-            // one row per thread, one group: line L of the row = stages kLineStages * L ..
-            static_assert(C::kLineStages == 1 || (kGroups == 1 && kRowsPerThread == 1), "line mode: one row per thread");
-            constexpr int kLS = C::kLineStages;
-            uint32_t line[2][kLS][1][kWords];
-            auto fetch_line = [&](uint32_t (&dst)[kLS][1][kWords], size_t ln) {
-                const size_t w0 = (st0 + ln * kLS) * kWords;
-                const int row = tg;
+            src_row = g.row_lo + r;
+            valid = r < g.n_lo;
+        }
+        const int srow = NP == 256 ? half * 128 + r : r;                    // row inside the staged step
+        const uint32_t soff = (uint32_t)(srow >> 3) * 256u + (uint32_t)(srow & 7) * 16u;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)C::kACol +
+                               (NP == 256 ? (uint32_t)(half * kKB * 8) : 0u);
+        const uint4 *line_base = reinterpret_cast<const uint4 *>(g.bits) +
+                                 ((size_t)first_tile * g.tile_rows + src_row) * (kTileWords / 4);
+        const size_t line_stride = (size_t)g.tile_rows * (kTileWords / 4);   // uint4 per tile
+
+        uint32_t line[2][kTileWords];
+        auto fetch = [&](uint32_t (&dst)[kTileWords], size_t t) {
+            if (!valid || t >= my_tiles || (g.diag & 1)) {
 #pragma unroll
-                for (int j = 0; j < kLS; j++)
+                for (int k = 0; k < kTileWords; k++) dst[k] = 0;
+                return;
+            }
+            const uint4 *src = line_base + t * line_stride;
 #pragma unroll
-                    for (int k = 0; k < kWords; k++) dst[j][0][k] = 0;
-                if ((diag & 1) || row >= nsamples || ln * kLS >= nst) return;
-                const uint32_t *src = row_ptr(row, w0);
-                if (vec_ok && w0 + kLS * kWords <= words) {
+            for (int k = 0; k < kTileWords / 4; k++) {
+                const uint4 q = __ldg(src + k);
+                dst[4 * k] = q.x; dst[4 * k + 1] = q.y; dst[4 * k + 2] = q.z; dst[4 * k + 3] = q.w;
+            }
+        };
+        auto produce = [&](const uint32_t (&src)[kTileWords], size_t t) {
 #pragma unroll
-                    for (int j = 0; j < kLS; j++)
+            for (int j = 0; j < C::kTileStages; j++) {
+                const size_t it = t * C::kTileStages + j;
+                const int s = (int)(it % C::kStages);
+                const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
+                mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint8_t *dst = smem + (size_t)s * C::kStageBytes + soff;
+                const uint32_t tdst = tlane + (uint32_t)(s * C::kAStageCols);
+                if (!(g.diag & 4)) {
 #pragma unroll
-                        for (int k = 0; k < kWords; k += 4) {
-                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + j * kWords + k));
-                            dst[j][0][k] = q.x; dst[j][0][k + 1] = q.y; dst[j][0][k + 2] = q.z; dst[j][0][k + 3] = q.w;
-                        }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kLS; j++)
-#pragma unroll
-                        for (int k = 0; k < kWords; k++)
-                            if (w0 + j * kWords + k < words) dst[j][0][k] = __ldg(src + j * kWords + k);
-                }
-            };
-            fetch_line(line[0], 0);
-            fetch_line(line[1], 1);
-            for (size_t ln = 0; ln * kLS < nst; ln += 2) {
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    const size_t s0 = (ln + b) * kLS;
-                    if (s0 < nst) {
-#pragma unroll
-                        for (int j = 0; j < kLS; j++)
-                            if (s0 + j < nst) produce(line[b][j], s0 + j);
-                        fetch_line(line[b], ln + b + 2);
+                    for (int k = 0; k < kKB; k++) {        // K=64 step k of the stage: two words -> chunks 0, 1
+                        const uint4 c0 = expand_word_f4(src[(j * kKB + k) * 2]);
+                        const uint4 c1 = expand_word_f4(src[(j * kKB + k) * 2 + 1]);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes) = c0;
+                        *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes + 128) = c1;
+                        if (ATM) tmem_st8(tdst + (uint32_t)(k * 8), c0, c1);
                     }
+                }
+                if (ATM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(smem_u32(&full_bar[s]));
+            }
+        };
+
+        fetch(line[0], (size_t)group);
+        fetch(line[1], (size_t)group + C::kGroups);
+        for (size_t t = group; t < ntiles; t += 2 * C::kGroups) {
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const size_t cur = t + (size_t)b * C::kGroups;
+                if (cur < ntiles) {
+                    produce(line[b], cur);
+                    fetch(line[b], cur + 2 * C::kGroups);
                 }
             }
         }
     } else {
         // ------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc_f4(128, C::kAccN);
+        const uint32_t idesc = make_idesc_f4(128, 128);
         const uint64_t desc0 = make_desc(smem_u32(smem), 128, 256);
         const uint32_t sf = tmem_base + (uint32_t)C::kSfCol;
+        const uint32_t a0 = tmem_base + (uint32_t)C::kACol;
         for (size_t it = 0; it < nst; it++) {
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
@@ -297,18 +297,27 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint64_t dstage = desc0 + (uint64_t)((s * C::kStageBytes) >> 4);
+                const uint32_t astage = a0 + (uint32_t)(s * C::kAStageCols);
 #pragma unroll
                 for (int kb = 0; kb < kKB; kb++) {
-                    const uint64_t lo = dstage + (uint64_t)((kb * C::kTileBytes) >> 4);   // rows 0..127
+                    const uint64_t lo = dstage + (uint64_t)((kb * C::kStepBytes) >> 4);   // rows 0..127
                     const uint32_t acc = (it | kb) ? 1u : 0u;
-                    if (diag & 2) continue;
-                    if (C::kAccs == 1) {
-                        mma_f4(tmem_base, lo, lo, idesc, acc, sf, sf);
+                    if (g.diag & 2) continue;
+                    if (NP == 128) {
+                        if (ATM) mma_f4_ts(tmem_base, astage + kb * 8, lo, idesc, acc, sf, sf);
+                        else     mma_f4_ss(tmem_base, lo, lo, idesc, acc, sf, sf);
                     } else {
                         const uint64_t hi = lo + (uint64_t)((128 * 32) >> 4);            // rows 128..255
-                        mma_f4(tmem_base, lo, lo, idesc, acc, sf, sf);                   // (0,0)
-                        mma_f4(tmem_base + 128, lo, hi, idesc, acc, sf, sf);             // (0,1)
-                        mma_f4(tmem_base + 256, hi, hi, idesc, acc, sf, sf);             // (1,1)
+                        const uint32_t alo = astage + kb * 8, ahi = alo + kKB * 8;
+                        if (ATM) {
+                            if (g.acc_mask & 1) mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);         // (lo,lo)
+                            if (g.acc_mask & 2) mma_f4_ts(tmem_base + 128, alo, hi, idesc, acc, sf, sf);   // (lo,hi)
+                            if (g.acc_mask & 4) mma_f4_ts(tmem_base + 256, ahi, hi, idesc, acc, sf, sf);   // (hi,hi)
+                        } else {
+                            if (g.acc_mask & 1) mma_f4_ss(tmem_base, lo, lo, idesc, acc, sf, sf);
+                            if (g.acc_mask & 2) mma_f4_ss(tmem_base + 128, lo, hi, idesc, acc, sf, sf);
+                            if (g.acc_mask & 4) mma_f4_ss(tmem_base + 256, hi, hi, idesc, acc, sf, sf);
+                        }
                     }
                 }
                 mma_commit(smem_u32(&empty_bar[s]));      // frees the stage when the MMAs retire
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
         __syncwarp();
     }
 
-    if (warp < kMmaWarp && nst) {
+    if (warp < kMmaWarp && nst && !(g.diag & 2)) {
         // ------------------------------------------------------------ epilogue
         // warp w reads TMEM lanes 32 (w % 4) ..: row (w % 4) * 32 + lane of an accumulator; the two
         // warps that share a lane quarter take alternate 32-column chunks
@@ -327,24 +336,43 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3, half = warp >> 2;
         const int r = quarter * 32 + lane;
-#pragma unroll 1
-        for (int a = 0; a < C::kAccs; a++) {
-            const int row0 = a == 2 ? 128 : 0, col0 = a == 0 ? 0 : (C::kAccs == 1 ? 0 : 128);
-            if (row0 + quarter * 32 >= nsamples) continue;            // warp-uniform
-#pragma unroll 1
-            for (int c0 = half * 32; c0 < C::kAccN; c0 += 64) {
-                if (col0 + c0 >= nsamples) break;
+        const size_t ld = (size_t)g.ld;
+        if (NP == 128 && DUAL) {
+            // rows 0..63 x columns 0..63 and rows 64..127 x columns 64..127 are the two halves' Gram blocks
+            const int i = r & 63;
+            const int c0 = (r >= 64 ? 64 : 0) + half * 32;
+            if ((c0 & 63) < g.n_lo) {                                   // warp-uniform
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * C::kAccN + c0), v);
-                const int row = row0 + r;
-                if (row < nsamples) {
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (i < g.n_lo) {
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
-                        const int col = col0 + c0 + c;
+                        const int j = (c0 & 63) + c;
                         const unsigned long long x = __float2ull_rn(__uint_as_float(v[c]));
-                        if (col < nsamples && x) {
-                            atomicAdd(&gram[(size_t)row * nsamples + col], x);
-                            if (a == 1) atomicAdd(&gram[(size_t)col * nsamples + row], x);   // mirror of (0,1)
+                        if (j < g.n_lo && x) atomicAdd(&g.gram[(size_t)(g.row_lo + i) * ld + g.row_lo + j], x);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < C::kAccs; a++) {
+                if (NP == 256 && !((g.acc_mask >> a) & 1)) continue;
+                const int rbase = a == 2 ? g.row_hi : g.row_lo, nr = a == 2 ? g.n_hi : g.n_lo;
+                const int cbase = a == 0 ? g.row_lo : g.row_hi, nc = a == 0 ? g.n_lo : g.n_hi;
+                if (quarter * 32 >= nr) continue;                        // warp-uniform
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < 128; c0 += 64) {
+                    if (c0 >= nc) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 128 + c0), v);
+                    if (r < nr) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const unsigned long long x = __float2ull_rn(__uint_as_float(v[c]));
+                            if (c0 + c < nc && x) {
+                                atomicAdd(&g.gram[(size_t)(rbase + r) * ld + cbase + c0 + c], x);
+                                if (a == 1) atomicAdd(&g.gram[(size_t)(cbase + c0 + c) * ld + rbase + r], x);   // mirror of (lo,hi)
+                            }
                         }
                     }
                 }
@@ -359,37 +387,162 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const uint32
     }
 }
 
-template <int NP, int AHEAD>
-int launch_gram_f4(const uint32_t *bits, int nsamples, size_t words, size_t stride_words,
-                   unsigned long long *gram, int device, cudaStream_t st, int tile_rows) {
+// the A operand from tensor memory (default) or, PYKMER_B200_GRAM_A=smem, both operands from shared
+// memory as in round 1 (kept for the measurement that decided it, profiles/r02*_gram_*)
+bool a_from_tmem() {
+    static const bool v = [] {
+        const char *e = getenv("PYKMER_B200_GRAM_A");
+        return !(e && e[0] == 's');
+    }();
+    return v;
+}
+
+template <int NP, bool DUAL>
+int launch_one(GramArgs a, int device, cudaStream_t st, size_t force_grid) {
     using C = F4Cfg<NP>;
-    PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    const size_t total_stages = (words + C::kWords - 1) / C::kWords;
-    // a CTA's FP32 accumulators must stay exact integers: at most 2^24 k-mers = 2^19 words each
-    // (slabs are rounded up to whole lines and stages inside the kernel: keep 64 words of margin)
-    const size_t slab_max = (1ull << 19) - 64;
-    const size_t min_ctas = (words + slab_max - 1) / slab_max;
-    size_t grid = (size_t)pk_sm_count(device);
-    grid = std::max(grid, min_ctas);
-    grid = std::max<size_t>(1, std::min(grid, total_stages));
-    int diag = 0;
-    if (const char *env = getenv("PYKMER_B200_GRAM_DIAG")) diag = atoi(env);
-    if (tile_rows && (words & 31))
-        return pk_set_error(PK_ERR_ARG, "gram_f4: the tiled layout needs a multiple of 32 words, got %zu", words);
-    k_gram_f4<NP, AHEAD><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(bits, nsamples, words, stride_words, gram,
-                                                                        diag, tile_rows);
+    // an FP32 accumulator must stay an exact integer: at most 2^24 k-mers = 2^14 tiles each (the dual
+    // slab has one accumulator block per half)
+    const size_t cap = (size_t)(DUAL ? 2 : 1) << 14;
+    size_t grid = std::max((size_t)pk_sm_count(device), (a.tiles + cap - 1) / cap);
+    grid = std::max<size_t>(1, std::min(grid, a.tiles));
+    if (force_grid) grid = force_grid;
+    a.tiles_per_cta = (a.tiles + grid - 1) / grid;
+    if (a.tiles_per_cta > cap)
+        return pk_set_error(PK_ERR_ARG, "gram_f4: %zu tiles per CTA exceed the exact range of an FP32 accumulator", a.tiles_per_cta);
+    a.diag = 0;
+    if (const char *env = getenv("PYKMER_B200_GRAM_DIAG")) a.diag = atoi(env);
+    if (a_from_tmem()) {
+        PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, DUAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+        k_gram_f4<NP, DUAL, true><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(a);
+    } else {
+        PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, DUAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+        k_gram_f4<NP, DUAL, false><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(a);
+    }
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
+// ---- the once-per-device exactness check ------------------------------------------------------------
+// Three rows over 2^14 - 32 tiles (16,744,448 k-mers), ONE CTA, one accumulator:
+//   A  2^23 ones, then exactly one set bit per K=64 instruction      B  all ones
+//   C  2^23 ones, then one set bit (A's) every third instruction
+// (A,A) and (A,B) walk through every integer from 2^23 to 2^24 - 32768 - 1, (A,C), (C,C) through every
+// third; the closed forms below are what exact accumulation gives.
+constexpr size_t kCheckTiles = (1u << 14) - 32;
+constexpr size_t kCheckOnes = 1u << 13;                  // tiles of ones = 2^23 k-mers
+
+__global__ void k_selfcheck_fill(uint32_t *bits) {
+    // tile t, row r, word k  ->  bits[(t * 3 + r) * 32 + k]
+    const size_t n = kCheckTiles * 3 * 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = i / 96;
+        const int r = (int)((i / 32) % 3), k = (int)(i % 32);
+        uint32_t w = 0xFFFFFFFFu;
+        if (r != 1 && t >= kCheckOnes) {
+            const size_t step = (t - kCheckOnes) * 16 + (size_t)(k >> 1);      // K=64 step after the ones
+            w = (k & 1) ? 0u : 1u << (step & 31);
+            if (r == 2 && step % 3 != 0) w = 0u;
+        }
+        bits[i] = w;
+    }
+}
+
+std::mutex g_check_mutex;
+int g_exact[64];                                         // 0 = not checked, 1 = exact, -1 = NOT exact
+
+int selfcheck(int device) {
+    uint32_t *bits = nullptr;
+    unsigned long long *gram = nullptr, h[9];
+    cudaStream_t st = nullptr;
+    PK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaError_t e = cudaMalloc(&bits, kCheckTiles * 3 * 32 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&gram, sizeof h);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gram, 0, sizeof h, st);
+    int rc = PK_OK;
+    if (e == cudaSuccess) {
+        k_selfcheck_fill<<<296, 256, 0, st>>>(bits);
+        GramArgs a{};
+        a.bits = bits; a.tiles = kCheckTiles; a.tile_rows = 3; a.row_lo = 0; a.n_lo = 3; a.acc_mask = 1;
+        a.gram = gram; a.ld = 3;
+        rc = launch_one<128, false>(a, device, st, 1);
+        if (rc == PK_OK) e = cudaMemcpyAsync(h, gram, sizeof h, cudaMemcpyDeviceToHost, st);
+        if (rc == PK_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(bits); cudaFree(gram); cudaStreamDestroy(st);
+    if (rc != PK_OK) return rc;
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "gram_f4 exactness check: %s", cudaGetErrorString(e));
+    const unsigned long long ones = kCheckOnes * 1024ull, steps = (kCheckTiles - kCheckOnes) * 16ull,
+                             third = (steps + 2) / 3, all = kCheckTiles * 1024ull;
+    const unsigned long long want[9] = {ones + steps, ones + steps, ones + third,
+                                        ones + steps, all,          ones + third,
+                                        ones + third, ones + third, ones + third};
+    bool ok = true;
+    for (int i = 0; i < 9; i++) ok = ok && h[i] == want[i];
+    return ok ? 1 : -1;
+}
+
 }  // namespace
 
-// gram (int64, nsamples x nsamples, already zeroed or holding a partial sum) += B * B^T
-int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
-                      int64_t *gram_dev, int device, cudaStream_t st, int tile_rows) {
-    unsigned long long *g = reinterpret_cast<unsigned long long *>(gram_dev);
-    if (nsamples <= 64) return launch_gram_f4<64, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
-    if (nsamples <= 128) return launch_gram_f4<128, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
-    if (nsamples <= 256) return launch_gram_f4<256, 2>(bits_dev, nsamples, words, stride_words, g, device, st, tile_rows);
-    return pk_set_error(PK_ERR_ARG, "pk_gram_f4_launch: %d samples exceed one tensor-core tile (256)", nsamples);
+// 1 = FP32 accumulation of 0/1 products is exact up to 2^24 on this device (checked once, cached),
+// 0 = it is not: the callers must use the integer kernels; negative = error
+int pk_gram_f4_exact(int device) {
+    if (device < 0 || device >= 64) return pk_set_error(PK_ERR_ARG, "pk_gram_f4_exact: device %d", device);
+    std::lock_guard<std::mutex> lock(g_check_mutex);
+    if (g_exact[device] == 0) {
+        if (const char *e = getenv("PYKMER_B200_F4_EXACT")) {      // test hook: pretend the check failed / passed
+            g_exact[device] = atoi(e) ? 1 : -1;
+        } else {
+            pk_device_guard guard(device);
+            const int rc = selfcheck(device);
+            if (rc != 1 && rc != -1) return rc;
+            g_exact[device] = rc;
+        }
+    }
+    return g_exact[device] == 1 ? 1 : 0;
+}
+
+// gram (int64, nsamples x nsamples, already zeroed or holding a partial sum) += B * B^T for tiled masks
+// of `nsamples` rows and `words` (a multiple of 32) words per row.  Any nsamples: up to 256 in one
+// launch, more block pair by block pair -- pairs (2i, 2i+1) of 128-row blocks with all three
+// accumulators, then every remaining cross pair with the (lo,hi) accumulator alone.
+int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, int64_t *gram_dev, int device,
+                      cudaStream_t st) {
+    if (words & 31)
+        return pk_set_error(PK_ERR_ARG, "gram_f4: the tiled layout needs a multiple of 32 words, got %zu", words);
+    const int exact = pk_gram_f4_exact(device);
+    if (exact < 0) return exact;
+    if (!exact)
+        return pk_set_error(PK_ERR_STATE, "gram_f4: this device does not accumulate FP4 products exactly up to 2^24 "
+                            "(pk_gram_f4_exact); use the integer Gram kernels (row-major masks, pk_gram_device)");
+    GramArgs a{};
+    a.bits = bits_dev; a.tiles = words / 32; a.tile_rows = nsamples;
+    a.gram = reinterpret_cast<unsigned long long *>(gram_dev); a.ld = nsamples;
+    if (nsamples <= 64) {
+        a.row_lo = 0; a.n_lo = nsamples; a.acc_mask = 1;
+        return a.tiles >= 2 ? launch_one<128, true>(a, device, st, 0) : launch_one<128, false>(a, device, st, 0);
+    }
+    if (nsamples <= 128) {
+        a.row_lo = 0; a.n_lo = nsamples; a.acc_mask = 1;
+        return launch_one<128, false>(a, device, st, 0);
+    }
+    const int nb = (nsamples + 127) / 128;
+    auto rows = [&](int b) { return std::min(128, nsamples - b * 128); };
+    for (int b = 0; b + 1 < nb; b += 2) {                    // (2i, 2i+1): the two diagonal blocks and their cross block
+        a.row_lo = b * 128; a.n_lo = rows(b); a.row_hi = (b + 1) * 128; a.n_hi = rows(b + 1); a.acc_mask = 7;
+        const int rc = launch_one<256, false>(a, device, st, 0);
+        if (rc != PK_OK) return rc;
+    }
+    if (nb & 1) {                                            // the last block's own diagonal
+        a.row_lo = (nb - 1) * 128; a.n_lo = rows(nb - 1); a.acc_mask = 1;
+        const int rc = launch_one<128, false>(a, device, st, 0);
+        if (rc != PK_OK) return rc;
+    }
+    for (int i = 0; i < nb; i++)
+        for (int j = i + 1; j < nb; j++) {
+            if ((i & 1) == 0 && j == i + 1) continue;        // done above
+            a.row_lo = i * 128; a.n_lo = rows(i); a.row_hi = j * 128; a.n_hi = rows(j); a.acc_mask = 2;
+            const int rc = launch_one<256, false>(a, device, st, 0);
+            if (rc != PK_OK) return rc;
+        }
+    return PK_OK;
 }

@@ -290,12 +290,22 @@ PK_API int pk_threshold_pack_tiled_device(const uint8_t *table_dev, size_t n, si
     return PK_OK;
 }
 
+PK_API int pk_gram_tiled_exact(int device, int *exact) {
+    PK_REQUIRE(exact != nullptr, "pk_gram_tiled_exact: NULL output");
+    int ndev = 0;
+    PK_CUDA(cudaGetDeviceCount(&ndev));
+    PK_REQUIRE(device >= 0 && device < ndev, "pk_gram_tiled_exact: device %d of %d", device, ndev);
+    const int rc = pk_gram_f4_exact(device);
+    if (rc < 0) return rc;
+    *exact = rc;
+    return PK_OK;
+}
+
 PK_API int pk_gram_tiled_device(const uint32_t *bits_tiled_dev, int nsamples, size_t words, int64_t *gram_dev,
                                 int accumulate, pk_stream stream) {
     PK_REQUIRE(bits_tiled_dev != nullptr && gram_dev != nullptr, "pk_gram_tiled_device: NULL pointer");
     PK_REQUIRE(nsamples >= 1 && nsamples <= PK_TILED_MAX_SAMPLES,
-               "pk_gram_tiled_device: %d samples, the tiled masks serve 1..%d (more: pk_gram_device)", nsamples,
-               PK_TILED_MAX_SAMPLES);
+               "pk_gram_tiled_device: %d samples outside 1..%d", nsamples, PK_TILED_MAX_SAMPLES);
     PK_REQUIRE(((uintptr_t)bits_tiled_dev & 15u) == 0, "pk_gram_tiled_device: bits must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int device = 0;
@@ -304,7 +314,7 @@ PK_API int pk_gram_tiled_device(const uint32_t *bits_tiled_dev, int nsamples, si
         PK_CUDA(cudaMemsetAsync(gram_dev, 0, (size_t)nsamples * nsamples * sizeof(int64_t), st));
     if (words == 0) return PK_OK;
     const size_t padded = (words + 31) & ~(size_t)31;             // whole tiles; the padding words are zero
-    return pk_gram_f4_launch(bits_tiled_dev, nsamples, padded, padded, gram_dev, device, st, nsamples);
+    return pk_gram_f4_launch(bits_tiled_dev, nsamples, padded, gram_dev, device, st);
 }
 
 PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, size_t stride_words,
@@ -318,16 +328,12 @@ PK_API int pk_gram_device(const uint32_t *bits_dev, int nsamples, size_t words, 
     if (!accumulate)
         PK_CUDA(cudaMemsetAsync(gram_dev, 0, (size_t)nsamples * nsamples * sizeof(int64_t), st));
     if (words == 0) return PK_OK;
-    // Row-major masks: tcgen05 kind::i8 tensor-core contraction (N <= 256, the default HERE; the
-    // merger itself packs tiled masks and calls pk_gram_tiled_device), kind::mxf4 on request, and
-    // AND + popcount on the ALUs (any N).
+    // Row-major masks -- the two integer implementations the FP4 kernel on tiled masks
+    // (pk_gram_tiled_device, the merger's default) is checked against, and its stand-ins on a device
+    // that fails pk_gram_f4_exact: tcgen05 kind::i8 (N <= 256; integer accumulators) and AND +
+    // popcount on the ALUs (any N).  PYKMER_B200_GRAM=popc forces the latter (test hook).
     const char *algo = getenv("PYKMER_B200_GRAM");
     const bool want_popc = algo && strcmp(algo, "popc") == 0;
-    if (algo && strcmp(algo, "f4") == 0 && nsamples <= 256) {     // FP4 path on row-major masks (sweeps)
-        const char *tiled = getenv("PYKMER_B200_GRAM_TILED");    // the caller laid the words out in tiles
-        return pk_gram_f4_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st,
-                                 tiled && atoi(tiled) ? nsamples : 0);
-    }
     if (!want_popc && nsamples <= 256)
         return pk_gram_i8_launch(bits_dev, nsamples, words, stride_words, gram_dev, device, st);
     const int npanels = (nsamples + kPanel - 1) / kPanel;
@@ -384,13 +390,26 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
     pk_device_guard guard(device);
     if (!guard.ok) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice(%d) failed", device);
 
-    const size_t words = (n + 31) / 32;
+    // tiled masks + the FP4 Gram kernel (gram_f4.cu) unless the device fails its exactness check;
+    // PYKMER_B200_GRAM=i8|popc (test hook) keeps row-major masks and the integer kernel named
+    const int exact = pk_gram_f4_exact(device);
+    if (exact < 0) return exact;
+    const bool tiled = exact == 1 && nsamples <= PK_TILED_MAX_SAMPLES && getenv("PYKMER_B200_GRAM") == nullptr;
+    // The masks of ALL samples for one stretch of the k-mer axis must be resident for the contraction
+    // (N / 8 bytes per k-mer).  When the whole axis does not fit (K=17 x 255 samples: 548 GB) it is cut
+    // into chunks of whole 1024-k-mer tiles that do, and the chunks' Gram matrices are added up -- the
+    // sums of tools.py:480-482 are sums over that axis, like the reference's own 100 M-entry blocks
+    // (tools.py:449-489).  PYKMER_B200_MASK_BUDGET (bytes; test hook) forces small chunks.
+    size_t free_b = 0, total_b = 0;
+    PK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = free_b / 2;
+    if (const char *env = getenv("PYKMER_B200_MASK_BUDGET")) budget = (size_t)strtoull(env, nullptr, 10);
+    size_t per_chunk = std::max<size_t>(1024, (budget * 8 / (size_t)nsamples) / 1024 * 1024);
+    per_chunk = std::min(per_chunk, std::max<size_t>(n, 1));
+    const size_t words = (per_chunk + 31) / 32;                      // mask words per sample and chunk
     const size_t stride_words = (words + 3) & ~(size_t)3;
-    // <= 256 samples: tiled masks + the FP4 Gram kernel (gram_f4.cu); PYKMER_B200_GRAM=i8|popc|f4 keeps
-    // the row-major masks and the kernel named
-    const bool tiled = nsamples <= PK_TILED_MAX_SAMPLES && getenv("PYKMER_B200_GRAM") == nullptr;
     const size_t mask_words = tiled ? ((words + 31) / 32) * 32 * (size_t)nsamples : (size_t)nsamples * stride_words;
-    const size_t chunk = std::min<size_t>(n, 64u << 20);          // bytes per staged copy, multiple of 32
+    const size_t chunk = std::min<size_t>(per_chunk, 64u << 20);     // bytes per staged copy, multiple of 32
     uint8_t *stage[2] = {nullptr, nullptr};
     uint32_t *bits = nullptr;
     int64_t *gram = nullptr;
@@ -401,9 +420,9 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     step(cudaMalloc(&bits, mask_words * sizeof(uint32_t)));
     step(cudaMalloc(&gram, G.size() * sizeof(int64_t)));
-    if (tiled && e == cudaSuccess) step(cudaMemset(bits, 0, mask_words * sizeof(uint32_t)));   // tile padding
     step(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
     step(cudaStreamCreateWithFlags(&work_st, cudaStreamNonBlocking));
+    if (e == cudaSuccess) step(cudaMemsetAsync(gram, 0, G.size() * sizeof(int64_t), work_st));
     for (int i = 0; i < 2; i++) {
         step(cudaMalloc(&stage[i], chunk ? chunk : 32));
         step(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
@@ -411,25 +430,30 @@ PK_API int pk_merge_host(const uint8_t *const *tables_host, int nsamples, size_t
         if (e == cudaSuccess) step(cudaEventRecord(consumed[i], work_st));
     }
     int rc = PK_OK, buf = 0;
-    for (int s = 0; s < nsamples && e == cudaSuccess && rc == PK_OK; s++) {
-        for (size_t off = 0; off < n && e == cudaSuccess && rc == PK_OK; off += chunk) {
-            const size_t len = std::min(chunk, n - off);
-            step(cudaStreamWaitEvent(copy_st, consumed[buf], 0));
-            step(cudaMemcpyAsync(stage[buf], tables_host[s] + off, len, cudaMemcpyHostToDevice, copy_st));
-            step(cudaEventRecord(copied[buf], copy_st));
-            step(cudaStreamWaitEvent(work_st, copied[buf], 0));
-            if (e == cudaSuccess)
-                rc = tiled ? pk_threshold_pack_tiled_device(stage[buf], len, off / 32, min_count, max_count, bits, s,
-                                                            nsamples, work_st)
-                           : pk_threshold_pack_device(stage[buf], len, min_count, max_count,
-                                                      bits + (size_t)s * stride_words + off / 32, work_st);
-            step(cudaEventRecord(consumed[buf], work_st));
-            buf ^= 1;
+    for (size_t c0 = 0; c0 < n && e == cudaSuccess && rc == PK_OK; c0 += per_chunk) {
+        const size_t cn = std::min(per_chunk, n - c0);               // k-mers of this chunk
+        if (tiled) step(cudaMemsetAsync(bits, 0, mask_words * sizeof(uint32_t), work_st));   // tile padding
+        for (int s = 0; s < nsamples && e == cudaSuccess && rc == PK_OK; s++) {
+            for (size_t off = 0; off < cn && e == cudaSuccess && rc == PK_OK; off += chunk) {
+                const size_t len = std::min(chunk, cn - off);
+                step(cudaStreamWaitEvent(copy_st, consumed[buf], 0));
+                step(cudaMemcpyAsync(stage[buf], tables_host[s] + c0 + off, len, cudaMemcpyHostToDevice, copy_st));
+                step(cudaEventRecord(copied[buf], copy_st));
+                step(cudaStreamWaitEvent(work_st, copied[buf], 0));
+                if (e == cudaSuccess)
+                    rc = tiled ? pk_threshold_pack_tiled_device(stage[buf], len, off / 32, min_count, max_count, bits, s,
+                                                                nsamples, work_st)
+                               : pk_threshold_pack_device(stage[buf], len, min_count, max_count,
+                                                          bits + (size_t)s * stride_words + off / 32, work_st);
+                step(cudaEventRecord(consumed[buf], work_st));
+                buf ^= 1;
+            }
         }
+        const size_t cw = (cn + 31) / 32;
+        if (e == cudaSuccess && rc == PK_OK)
+            rc = tiled ? pk_gram_tiled_device(bits, nsamples, cw, gram, 1, work_st)
+                       : pk_gram_device(bits, nsamples, cw, stride_words, gram, 1, work_st);
     }
-    if (e == cudaSuccess && rc == PK_OK)
-        rc = tiled ? pk_gram_tiled_device(bits, nsamples, words, gram, 0, work_st)
-                   : pk_gram_device(bits, nsamples, words, stride_words, gram, 0, work_st);
     if (e == cudaSuccess && rc == PK_OK)
         step(cudaMemcpyAsync(G.data(), gram, G.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, work_st));
     if (e == cudaSuccess && rc == PK_OK) step(cudaStreamSynchronize(work_st));

@@ -38,6 +38,11 @@ def upload(t: torch.Tensor, non_blocking: bool = False) -> torch.Tensor:
     return t if t.is_cuda else t.to("cuda", non_blocking=non_blocking)
 
 
+def free_memory_bytes() -> int:
+    """Free memory of the current GPU."""
+    return int(torch.cuda.mem_get_info()[0])
+
+
 def stream_sync() -> None:
     torch.cuda.current_stream().synchronize()
 
@@ -328,7 +333,7 @@ def gram(bits: torch.Tensor, words: Optional[int] = None, out: Optional[torch.Te
     return out
 
 
-TILED_MAX_SAMPLES = 256
+TILED_MAX_SAMPLES = 4096
 
 
 def tiled_mask_words(words: int, nrows: int) -> int:
@@ -357,7 +362,8 @@ def threshold_pack_tiled(table: torch.Tensor, min_count: int, max_count: int, ou
 
 def gram_tiled(bits: torch.Tensor, nsamples: int, words: int, out: Optional[torch.Tensor] = None,
                accumulate: bool = False, stream=None) -> torch.Tensor:
-    """tiled mask buffer -> (N, N) int64 CUDA Gram matrix (N <= TILED_MAX_SAMPLES)."""
+    """tiled mask buffer -> (N, N) int64 CUDA Gram matrix (any N <= TILED_MAX_SAMPLES; more than 256
+    samples run block pair by block pair)."""
     assert bits.is_cuda and bits.element_size() == 4 and bits.is_contiguous()
     assert bits.numel() >= tiled_mask_words(words, nsamples)
     if out is None:
@@ -369,11 +375,27 @@ def gram_tiled(bits: torch.Tensor, nsamples: int, words: int, out: Optional[torc
     return out
 
 
-def use_tiled_masks(nsamples: int) -> bool:
-    """The merger's default for <= 256 samples; PYKMER_B200_GRAM=i8|popc|f4 selects a kernel on
-    row-major masks instead."""
+_F4_EXACT = {}
+
+
+def gram_tiled_exact(device: Optional[int] = None) -> bool:
+    """pk_gram_tiled_exact: does this device accumulate 0/1 FP4 products exactly up to 2^24?  (One
+    self-check per device, at first use.)"""
+    d = torch.cuda.current_device() if device is None else device
+    if d not in _F4_EXACT:
+        ok = ctypes.c_int(0)
+        nat.check(lib.pk_gram_tiled_exact(d, ctypes.byref(ok)))
+        _F4_EXACT[d] = bool(ok.value)
+    return _F4_EXACT[d]
+
+
+def use_tiled_masks(nsamples: int, device: Optional[int] = None) -> bool:
+    """The merger's default: tiled masks + the FP4 tensor-core Gram kernel.  Row-major masks and the
+    integer kernels (tcgen05 kind::i8 up to 256 samples, AND + popcount beyond) serve a device that
+    fails the exactness check, and PYKMER_B200_GRAM=i8|popc (test hook)."""
     import os
-    return nsamples <= TILED_MAX_SAMPLES and os.environ.get("PYKMER_B200_GRAM") is None
+    return (nsamples <= TILED_MAX_SAMPLES and os.environ.get("PYKMER_B200_GRAM") is None
+            and gram_tiled_exact(device))
 
 
 def matrix_from_gram(G: np.ndarray) -> np.ndarray:

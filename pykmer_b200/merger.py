@@ -180,66 +180,88 @@ class _SliceSource:
 
 
 def merge_tables(headers: List[Header], min_count: int, max_count: int, device: int = 0,
-                 slab_bytes: int = 256 << 20) -> np.ndarray:
+                 slab_bytes: int = 256 << 20, mask_budget_bytes: Optional[int] = None) -> np.ndarray:
     """Read each sample's table once (the file named by its JSON, .bgz preferred:
-    tools.py:185-196), threshold + pack it on the GPU, then one Gram pass.
+    tools.py:185-196), threshold + pack it on the GPU, and contract: G = B * B^T.
     -> (N, N, 3) uint64.
 
+    The presence masks of ALL samples for one stretch of the k-mer axis must be resident for the
+    contraction, N / 8 bytes per k-mer.  When the whole axis does not fit (K=17 x 255 samples is
+    548 GB) the axis is cut into chunks that do and the Gram matrices of the chunks are added up
+    (pk_gram_tiled_device(accumulate=1)) -- the sums of tools.py:480-482 are sums over that axis,
+    exactly like the reference's own 100 M-entry blocks (tools.py:449-489).  mask_budget_bytes
+    (default: 40 % of the free device memory) sets the chunk; the tests force small ones.
+
     Inside a torch.distributed job (torchrun merger.py ...) rank r takes slice r of the k-mer
-    axis of every sample -- the sums of tools.py:480-482 are sums over that axis, so the partial
-    Gram matrices simply add up (one all-reduce of N x N int64) -- and reads only
-    that slice of each file (Header.read_table_slice)."""
+    axis of every sample, for the same reason (one all-reduce of N x N int64), and
+    reads only that slice of each file (Header.read_table_slice)."""
     import torch
     from . import device as dev          # needs the CUDA library; no fallback
     from . import dist as pdist
 
     N = len(headers)
     T = headers[0].data_size
+    for h in headers:
+        assert h.data_size == T
     rank, world = pdist.world()
     lo, hi = pdist.shard_range(T, rank, world) if world > 1 else (0, T)
     n_own = hi - lo
-    words = (n_own + 31) // 32
-    stride = max(4, (words + 3) & ~3)
-    tiled = dev.use_tiled_masks(N)       # <= 256 samples: tiled masks + the FP4 tensor-core Gram kernel
     with dev.device_scope(device):
-        bits = dev.tiled_masks(words, N) if tiled else dev.zeros((N, stride), torch.int32)
+        tiled = dev.use_tiled_masks(N, device)     # tiled masks + the FP4 tensor-core Gram kernel
+        G = dev.zeros((N, N), torch.int64)
+        if mask_budget_bytes is None:
+            mask_budget_bytes = int(dev.free_memory_bytes() * 0.4)
+        # k-mers per chunk: whole tiles of 1024 (the tiled layout), at least one
+        per_chunk = max(1024, (mask_budget_bytes * 8 // max(N, 1)) // 1024 * 1024)
+        chunks = [(c, min(hi, c + per_chunk)) for c in range(lo, hi, per_chunk)]
+        c_words = (min(per_chunk, n_own) + 31) // 32
+        stride = max(4, (c_words + 3) & ~3)
+        bits = None
+        if chunks:
+            bits = dev.tiled_masks(c_words, N) if tiled else dev.zeros((N, stride), torch.int32)
         # Two pinned slabs in turn: a helper thread reads / inflates the next slab straight into one
         # while the other crosses PCIe.  A raw .kin is read at its offset with readinto (no
         # intermediate array); a .kin.bgz has to be inflated first (the slice only, Header.read_table_slice).
-        ring = [dev.pinned_empty(max(1, min(n_own, slab_bytes))) for _ in range(2)]
-        jobs = [(s, off) for s in range(N if n_own else 0) for off in range(0, n_own, slab_bytes)]
+        ring = [dev.pinned_empty(max(1, min(n_own, per_chunk, slab_bytes))) for _ in range(2)]
+        jobs = [(ci, s, off) for ci, (c0, c1) in enumerate(chunks) for s in range(N)
+                for off in range(0, c1 - c0, slab_bytes)]
         source: Dict[int, _SliceSource] = {}
 
         def read(j: int) -> int:
-            s, off = jobs[j]
+            ci, s, off = jobs[j]
+            c0, c1 = chunks[ci]
             if off == 0:
-                assert headers[s].data_size == T
-                source[s] = _SliceSource(headers[s], lo, hi)
+                source[s] = _SliceSource(headers[s], c0, c1)
             n = source[s].read_into(ring[j & 1].numpy())
-            if off + n >= n_own:
+            if off + n >= c1 - c0:
                 source.pop(s).close()
             return n
 
         from concurrent.futures import ThreadPoolExecutor
         reader = ThreadPoolExecutor(max_workers=1)
         ahead = reader.submit(read, 0) if jobs else None
-        for j, (s, off) in enumerate(jobs):
+        for j, (ci, s, off) in enumerate(jobs):
+            c0, c1 = chunks[ci]
             n = ahead.result()
-            assert n == min(slab_bytes, n_own - off)
+            assert n == min(slab_bytes, c1 - c0 - off)
             if j + 1 < len(jobs):
                 dev.stream_sync()                              # the other slab has crossed: refill it
                 ahead = reader.submit(read, j + 1)
+            if ci and s == 0 and off == 0:
+                bits.zero_()                                   # a shorter last chunk must not see stale words
             d = dev.upload(ring[j & 1][:n], non_blocking=True)
             if tiled:
                 dev.threshold_pack_tiled(d, min_count, max_count, bits, s, N, first_word=off // 32)
             else:
                 dev.threshold_pack(d, min_count, max_count, out=bits[s, off // 32:])
+            if s == N - 1 and off + n >= c1 - c0:              # the chunk is complete: contract it
+                w = (c1 - c0 + 31) // 32
+                if tiled:
+                    dev.gram_tiled(bits, N, w, out=G, accumulate=True)
+                else:
+                    dev.gram(bits, words=w, out=G, accumulate=True)
         dev.stream_sync()
         reader.shutdown()
-        if n_own:
-            G = dev.gram_tiled(bits, N, words) if tiled else dev.gram(bits, words=words)
-        else:                                                  # tiny table, more ranks than slices
-            G = dev.zeros((N, N), torch.int64)
         pdist.reduce_gram(G)
         Gh = G.cpu().numpy()
     return dev.matrix_from_gram(Gh)

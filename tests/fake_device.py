@@ -74,8 +74,12 @@ class Indexer:
         return dst
 
 
-def use_tiled_masks(nsamples):
+def use_tiled_masks(nsamples, device=None):
     return False
+
+
+def free_memory_bytes():
+    return 1 << 30
 
 
 def threshold_pack(table, min_count, max_count, out=None, stream=None):
@@ -86,7 +90,14 @@ def threshold_pack(table, min_count, max_count, out=None, stream=None):
 
 def gram(bits, words=None, out=None, accumulate=False, stream=None):
     b = bits.numpy().view(np.uint32)[:, :bits.shape[1] if words is None else words]
-    return torch.from_numpy(oracle.gram_from_bits(np.ascontiguousarray(b)).astype(np.int64))
+    G = torch.from_numpy(oracle.gram_from_bits(np.ascontiguousarray(b)).astype(np.int64))
+    if out is None:
+        return G
+    if accumulate:
+        out += G
+    else:
+        out.copy_(G)
+    return out
 
 
 def matrix_from_gram(G):

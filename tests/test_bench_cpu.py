@@ -20,7 +20,8 @@ def _run(extra, env=None):
 
 
 @pytest.mark.parametrize("extra,metric", [
-    (["--kmer", "11", "--scale", "0.004", "--cpu-sample-mbp", "2"], "indexer_bp_per_s_K11"),
+    (["--workload", "indexer", "--kmer", "11", "--scale", "0.004", "--cpu-sample-mbp", "2"], "indexer_bp_per_s_K11"),
+    (["--workload", "indexer", "--kmer", "11", "--scale", "0.004"], "indexer_bp_per_s_K11"),
     (["--workload", "merger", "--kmer", "9", "--samples", "6"], "merger_bitmask_GB_per_s"),
 ])
 def test_reference_arm_prints_one_contract_line(extra, metric):
@@ -33,6 +34,28 @@ def test_reference_arm_prints_one_contract_line(extra, metric):
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_default_line_carries_every_named_metric():
+    """No --workload: the headline indexer line + the merger sub-objects (BASELINE.json names indexer
+    bp/s AND merger GB/s); the workload strings are the ones the CUDA arm prints (same_config)."""
+    import bench
+    lines = _run(["--kmer", "11", "--scale", "0.004", "--no-reference-python", "--sub-steps", "1"])
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert KEYS <= set(line) and line["metric"] == "indexer_bp_per_s_K11"
+    assert line["config"]["workload"] == bench.workload_name("indexer", 11, bp=3130073)
+    for tag, n, mc in (("n50", 50, 50), ("n255", 255, 255)):
+        sub = line["merger"][tag]
+        assert KEYS <= set(sub) and sub["metric"] == "merger_bitmask_GB_per_s" and sub["value"] > 0
+        assert sub["config"]["workload"] == bench.workload_name("merger", 15, N=n, max_count=mc)
+
+
+def test_reference_python_leg_reports_unavailable_without_a_copy(tmp_path, monkeypatch):
+    """cpu_baseline.reference_python never takes the line down: without baseline/_ref it says so."""
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert "unavailable" in bench.reference_python()
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -278,16 +278,10 @@ def test_threshold_pack_vs_oracle(env, n, lohi):
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), want)
 
 
-F4_ENABLED = os.environ.get("PYKMER_B200_TEST_F4", "1") == "1"
-F4_SKIP = "FP4 Gram tests switched off (PYKMER_B200_TEST_F4=0)"
-
-
-@pytest.fixture(params=["i8", "popc", "f4"])
+@pytest.fixture(params=["i8", "popc"])
 def gram_algo(request):
-    """The exact Gram implementations on row-major masks: tcgen05 kind::i8 tensor cores, AND +
-    popcount, tcgen05 kind::mxf4 (FP4; on tiled masks it is the merger's default, tested below)."""
-    if request.param == "f4" and not F4_ENABLED:
-        pytest.skip(F4_SKIP)
+    """The two integer Gram implementations on row-major masks: tcgen05 kind::i8 tensor cores and
+    AND + popcount.  (The merger's default -- tcgen05 kind::mxf4 on tiled masks -- is tested below.)"""
     os.environ["PYKMER_B200_GRAM"] = request.param
     yield request.param
     os.environ.pop("PYKMER_B200_GRAM", None)
@@ -314,24 +308,52 @@ def test_gram_vs_oracle(env, gram_algo, N, words):
     assert np.array_equal(G2.cpu().numpy(), 2 * want)
 
 
-@pytest.mark.skipif(not F4_ENABLED, reason=F4_SKIP)
-@pytest.mark.parametrize("N", [3, 130])
+def _tile(rows_t):
+    """(N, words) row-major int32 CUDA masks -> the tiled buffer (words a multiple of 32)."""
+    N, words = rows_t.shape
+    return rows_t.view(N, words // 32, 32).permute(1, 0, 2).contiguous().view(-1)
+
+
+@pytest.mark.parametrize("N", [3, 100, 130])
 def test_gram_f4_every_partial_sum_is_exact(env, N):
-    """All-ones masks, 2^19 words per CTA: the FP32 accumulators walk through every multiple of 64
-    up to 2^24 -- the largest value a CTA may reach -- so any lost low bit shows up in G."""
+    """All-ones masks, 2^19 words per accumulator (<= 64 samples: a CTA runs two half slabs, each
+    with its own accumulator block): the FP32 accumulators walk through every multiple of 64 up to
+    2^24 -- the largest value an accumulator may reach -- so any lost low bit shows up in G.
+    (The odd values are walked in tests/test_gpu_at_scale.py.)"""
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    words = sms << 19
+    words = sms << (20 if N <= 64 else 19)
     d = torch.full((N, words), -1, dtype=torch.int32, device="cuda")
     d[N - 1, 1::2] = 0x55555555                                   # one sample with half the bits
-    os.environ["PYKMER_B200_GRAM"] = "f4"
-    try:
-        G = env["dev"].gram(d, words=words).cpu().numpy()
-    finally:
-        os.environ.pop("PYKMER_B200_GRAM", None)
+    G = env["dev"].gram_tiled(_tile(d), N, words).cpu().numpy()
     want = np.full((N, N), 32 * words, dtype=np.int64)
     want[N - 1, :] = want[:, N - 1] = 16 * words + 16 * (words // 2)
     assert np.array_equal(G, want)
+
+
+def test_gram_f4_exactness_check_and_fallback(env, tmp_path):
+    """pk_gram_tiled_exact: the once-per-device self-check passes on this GPU; a process in which it
+    fails (test hook) refuses the FP4 kernel loudly and the merger takes the integer kernels."""
+    import subprocess
+    import sys
+    assert env["dev"].gram_tiled_exact(0) is True
+    code = (
+        "import numpy as np, torch\n"
+        "from pykmer_b200 import device as dev, _native as nat, synth\n"
+        "assert dev.gram_tiled_exact(0) is False and not dev.use_tiled_masks(6)\n"
+        "try:\n"
+        "    dev.gram_tiled(dev.tiled_masks(32, 3), 3, 32)\n"
+        "    raise SystemExit('the FP4 kernel ran on a device marked inexact')\n"
+        "except nat.PkError as e:\n"
+        "    assert 'exact' in str(e)\n"
+        "from oracle import oracle\n"
+        "tables = np.stack([synth.synth_table(s, 9) for s in range(6)])\n"
+        "m = dev.merge_host(list(tables), 1, 50, device=0)\n"
+        "assert np.array_equal(m, oracle.merge_matrix(tables, 1, 50))\n"
+        "print('fallback ok')\n")
+    res = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PYKMER_B200_F4_EXACT="0"))
+    assert res.returncode == 0 and "fallback ok" in res.stdout, res.stderr[-2000:]
 
 
 @pytest.mark.parametrize("N,n", [(1, 5), (2, 100), (3, 1024), (7, 33_000), (50, 70_001), (64, 40_000),
@@ -366,8 +388,26 @@ def test_tiled_masks_pack_and_gram_vs_oracle(env, N, n):
     assert np.array_equal(G, want)
     G2 = dev.gram_tiled(bits, N, words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
     assert np.array_equal(G2.cpu().numpy(), 2 * want)
-    with pytest.raises(ValueError):                                # more than one tensor-core tile of samples
-        dev.gram_tiled(dev.tiled_masks(1, 257), 257, 1)
+
+
+@pytest.mark.parametrize("N,words", [(257, 64), (300, 4096), (384, 2048), (513, 320), (640, 96)])
+def test_tiled_gram_more_than_256_samples_vs_oracle(env, N, words):
+    """More than 256 samples stay on the tensor cores: 128-row block pairs of one tiled buffer
+    (merger.py:139-153 merges any N)."""
+    import torch
+    dev = env["dev"]
+    rng = np.random.default_rng(N + words)
+    rows = rng.integers(0, 2 ** 32, size=(N, words), dtype=np.uint64).astype(np.uint32)
+    rows[rng.random(N) < 0.1] = 0                                  # a few empty samples
+    d = torch.from_numpy(rows.view(np.int32)).cuda()
+    G = dev.gram_tiled(_tile(d), N, words).cpu().numpy()
+    B = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little").astype(np.float32)
+    want = (B.astype(np.float64) @ B.T.astype(np.float64)).astype(np.int64)
+    assert np.array_equal(G, want)
+    G2 = dev.gram_tiled(_tile(d), N, words, out=torch.from_numpy(want.copy()).cuda(), accumulate=True)
+    assert np.array_equal(G2.cpu().numpy(), 2 * want)
+    with pytest.raises(ValueError):
+        dev.gram_tiled(dev.tiled_masks(1, 4097), 4097, 1)
 
 
 MERGER_CASES = sorted(glob.glob(os.path.join(GOLD, "merger", "matrix_*.npz")))
@@ -385,6 +425,40 @@ def test_merge_matches_reference_golden(env, path):
     assert m.dtype == np.uint64 and np.array_equal(m[off], gold[off])
     assert np.array_equal(m, env["oracle"].merge_matrix(tables, lo, hi))
     assert env["dev"].pair_counts(tables[1], tables[4], lo, hi) == tuple(int(v) for v in gold[1, 4])
+
+
+@pytest.mark.parametrize("budget", [1, 4096, 40_000])
+def test_merge_in_k_axis_chunks_matches_reference_golden(env, budget, tmp_path):
+    """A working set larger than the device memory set aside for masks (K=17 x 255 samples would be
+    548 GB) is contracted chunk by chunk along the k-mer axis and summed, like the reference's own
+    100 M-entry blocks (tools.py:449-489).  Forced here with tiny mask budgets -- 1 byte = one
+    1024-k-mer tile per chunk, 16 chunks at K=7 -- through pk_merge_host and through
+    merger.merge_tables, against the reference's own .kma matrices and the oracle."""
+    from pykmer_b200 import merger, tools
+    tables = np.load(os.path.join(GOLD, "merger", "samples_K07.npz"))["tables"]
+    N = tables.shape[0]
+    off = ~np.eye(N, dtype=bool)
+    os.environ["PYKMER_B200_MASK_BUDGET"] = str(budget)
+    try:
+        for path in MERGER_CASES[:3]:
+            gold = np.load(path)["matrix"]
+            meta = json.load(open(path[:-4] + ".json"))
+            m = env["dev"].merge_host(list(tables), meta["min_count"], meta["max_count"])
+            assert np.array_equal(m[off], gold[off])
+    finally:
+        os.environ.pop("PYKMER_B200_MASK_BUDGET", None)
+    # the CLI's route: files on disk, merge_tables with the same budget
+    headers = []
+    for s in range(N):
+        src = tmp_path / f"s{s}.fa"
+        src.write_text(">x\nACGT\n")
+        h = tools.Header(str(src), input_file=str(src), kmer_len=7)
+        tables[s].tofile(h.index_file_root)
+        headers.append(h)
+    want = env["oracle"].merge_matrix(tables, 2, 9)
+    for tail in (budget, None):
+        m = merger.merge_tables(headers, 2, 9, mask_budget_bytes=tail, slab_bytes=4096)
+        assert np.array_equal(m, want)
 
 
 def test_merger_cli_writes_reference_files(env, tmp_path):
