@@ -41,6 +41,8 @@
 #include <stdlib.h>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.h"
 #include "tcgen05_util.h"
 
@@ -52,18 +54,6 @@ using namespace pk_umma;
 // scale format UE8M0, N >> 3 at bit 17, M >> 4 at bit 24, K = 64 (bit 31 clear), SF ids 0
 __host__ __device__ constexpr uint32_t make_idesc_f4(int m, int n) {
     return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
-}
-
-// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]^T
-__device__ __forceinline__ void mma_f4_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
-        : "memory");
 }
 
 // D[tmem] (+)= A[tmem: lane = row, 8 columns = 64 E2M1] * B[smem descriptor]^T
@@ -99,41 +89,51 @@ __device__ __forceinline__ uint4 expand_word_f4(uint32_t w) {
     return q;
 }
 
-// One TILE = 32 mask words per row = 1024 k-mers = 16 K=64 steps; a thread owns one row of the staged
-// block and always takes a whole 128-byte line of it.
-//   NP = 256: rows = two 128-row blocks (lo, hi); three accumulators (lo,lo), (lo,hi), (hi,hi); all
-//             256 producer threads fill every stage.
-//   NP = 128: one 128-row block, one accumulator; the two halves of the producer warps (warps 0..3,
-//             warps 4..7 -- both reach all 128 TMEM lanes) take alternate tiles.
+// One TILE = 32 mask words per row = 1024 k-mers = 16 K=64 steps.  The raw tile (all staged rows x 128
+// bytes) is fetched by TMA (cp.async.bulk.tensor, 64-row boxes, SWIZZLE_128B) into a ring in shared
+// memory; a producer thread owns one row of the staged block, reads ITS 128-byte line back (the swizzle
+// makes a warp's reads of 32 different rows conflict-free) and expands it.
+//   NP = 256: rows = two 128-row blocks (lo, hi); three accumulators (lo,lo), (lo,hi), (hi,hi).  Two
+//             producer groups of 256 threads take alternate STAGES (2 K=64 steps = one 16-byte chunk of
+//             every line each), so one group expands while the other sits in its fence / arrive chain.
+//   NP = 128: one 128-row block, one accumulator; two producer groups of 128 threads (each reaches all
+//             128 TMEM lanes) take alternate TILES.
 //             DUAL: the block is [<= 64 samples over the first half of the CTA's tiles; the same samples
 //             over the second half].
+// Warps: producers, then one MMA-issuing warp, then one TMA-issuing warp.
 constexpr int kTileWords = 32;
 constexpr int kTileSteps = 16;                          // K=64 steps per tile
+constexpr int kBoxRows = 64;                            // rows per TMA box
+constexpr int kBoxBytes = kBoxRows * 128;
 
 template <int NP>
 struct F4Cfg {
-    static constexpr int kProducerWarps = 8;
-    static constexpr int kProducerThreads = kProducerWarps * 32;
-    static constexpr int kThreads = kProducerThreads + 32;            // + the MMA-issuing warp
-    static constexpr int kGroups = NP == 256 ? 1 : 2;                 // producer groups filling different tiles
-    static constexpr int kGroupThreads = kProducerThreads / kGroups;
+    static constexpr int kGroups = 2;
+    static constexpr int kGroupWarps = NP / 32;                       // one thread per staged row
+    static constexpr int kGroupThreads = kGroupWarps * 32;
+    static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16 / 8
+    static constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1;
+    static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576 / 320
     static constexpr int kKB = NP == 256 ? 2 : 4;                     // K=64 steps per stage
-    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds
+    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 8 / 4
     static constexpr int kStages = NP == 256 ? 3 : 6;
     static constexpr int kStepBytes = NP * 32;                        // one K=64 step of all NP rows
     static constexpr int kStageBytes = kKB * kStepBytes;              // 16 KB either way
+    static constexpr int kRawBytes = NP * 128;                        // one raw tile: 32 KB / 16 KB
+    static constexpr int kRawSlots = NP == 256 ? 3 : 4;
+    static constexpr int kRawReaders = NP == 256 ? 2 * kGroupThreads : kGroupThreads;   // threads reading one raw tile
     static constexpr int kAccs = NP == 256 ? 3 : 1;
     static constexpr int kSfCol = kAccs * 128;                        // scale factors behind the accumulators
     static constexpr int kACol = kSfCol + 32;                         // ring of A operands behind them
     static constexpr int kAStageCols = kKB * 8 * (NP / 128);          // 8 columns per step and 128-row block
     static constexpr int kTmemCols = 512;
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 256 + 1024;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + (size_t)kRawSlots * kRawBytes + 512 + 1024;
     static_assert(kACol + kStages * kAStageCols <= kTmemCols, "TMEM budget");
     static_assert(kStages >= kGroups && kSmem <= 227 * 1024, "ring depth / shared memory budget");
 };
 
 struct GramArgs {
-    const uint32_t *bits;      // tiled masks: word g of row r at ((g / 32) * tile_rows + r) * 32 + g % 32
+    CUtensorMap tmap;          // tiled masks as a 3-D tensor {32 words, tile_rows, tiles}, box {32, 64, 1}, SWIZZLE_128B
     size_t tiles;              // tiles per row (words / 32)
     int tile_rows;             // rows of the tiled buffer
     int row_lo, n_lo;          // first 128-row block: rows [row_lo, row_lo + n_lo)
@@ -143,21 +143,35 @@ struct GramArgs {
     int ld;
     size_t tiles_per_cta;
     int diag;                  // PYKMER_B200_GRAM_DIAG (timing experiments only -- the result is then meaningless):
-                               // bit 0 = no global loads, bit 1 = no MMAs, bit 2 = no operand stores
+                               // bit 0 = no TMA loads, bit 1 = no MMAs, bit 2 = no operand stores
 };
 
-template <int NP, bool DUAL, bool ATM>
-__global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramArgs g) {
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// one 64-row x 128-byte box of tile `tile`, rows [row, row + 64) (rows past the buffer read as zeros)
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int row, int tile, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(0), "r"(row), "r"(tile), "r"(bar)
+        : "memory");
+}
+
+template <int NP, bool DUAL>
+__global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid_constant__ GramArgs g) {
     using C = F4Cfg<NP>;
     static_assert(!DUAL || NP == 128, "the dual slab is a form of the one-block kernel");
     constexpr int kKB = C::kKB;
-    constexpr int kMmaWarp = C::kProducerWarps;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *ctrl = smem + (size_t)C::kStages * C::kStageBytes;
+    uint8_t *raw = smem + (size_t)C::kStages * C::kStageBytes;             // [kRawSlots][kRawBytes], 1024-aligned
+    uint8_t *ctrl = raw + (size_t)C::kRawSlots * C::kRawBytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);               // [kStages]
     uint64_t *empty_bar = full_bar + C::kStages;                            // [kStages]
-    uint64_t *done_bar = empty_bar + C::kStages;
+    uint64_t *raw_full = empty_bar + C::kStages;                            // [kRawSlots]
+    uint64_t *raw_empty = raw_full + C::kRawSlots;                          // [kRawSlots]
+    uint64_t *done_bar = raw_empty + C::kRawSlots;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,10 +188,14 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
             mbar_init(smem_u32(&full_bar[s]), C::kGroupThreads);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
+        for (int s = 0; s < C::kRawSlots; s++) {
+            mbar_init(smem_u32(&raw_full[s]), 1);
+            mbar_init(smem_u32(&raw_empty[s]), C::kRawReaders);
+        }
         mbar_init(smem_u32(done_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) {
+    if (warp == C::kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)), "n"(C::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -202,89 +220,71 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp < kMmaWarp) {
+    if (warp < C::kProducerWarps) {
         // ------------------------------------------------------------ producers
-        // thread -> TMEM lane r of quarter (warp % 4); half = warp / 4 picks the block (NP = 256)
-        // or the producer group (NP = 128)
-        const int quarter = warp & 3, half = warp >> 2;
+        // thread -> staged row srow; TMEM lane r = srow % 128 lies in the quarter (warp % 4) this warp reaches
+        const int group = warp / C::kGroupWarps, wg = warp % C::kGroupWarps;
+        const int quarter = wg & 3, half = wg >> 2;                         // half: lo / hi block (NP = 256)
         const int r = quarter * 32 + lane;
-        const int group = NP == 256 ? 0 : half;
-        int src_row;                                   // row of the tiled buffer this thread expands
         bool valid;
-        size_t first_tile = t0, my_tiles = ntiles;
-        if (NP == 256) {
-            src_row = half ? g.row_hi + r : g.row_lo + r;
-            valid = r < (half ? g.n_hi : g.n_lo);
-        } else if (DUAL) {
-            src_row = g.row_lo + (r & 63);
-            valid = (r & 63) < g.n_lo;
-            if (r >= 64) { first_tile = tm; my_tiles = t1 - tm; }
-        } else {
-            src_row = g.row_lo + r;
-            valid = r < g.n_lo;
-        }
-        const int srow = NP == 256 ? half * 128 + r : r;                    // row inside the staged step
+        size_t my_tiles = ntiles;
+        if (NP == 256) valid = r < (half ? g.n_hi : g.n_lo);
+        else if (DUAL) { valid = (r & 63) < g.n_lo; if (r >= 64) my_tiles = t1 - tm; }
+        else valid = r < g.n_lo;
+        const int srow = NP == 256 ? half * 128 + r : r;                    // row inside the staged step / raw tile
         const uint32_t soff = (uint32_t)(srow >> 3) * 256u + (uint32_t)(srow & 7) * 16u;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)C::kACol +
                                (NP == 256 ? (uint32_t)(half * kKB * 8) : 0u);
-        const uint4 *line_base = reinterpret_cast<const uint4 *>(g.bits) +
-                                 ((size_t)first_tile * g.tile_rows + src_row) * (kTileWords / 4);
-        const size_t line_stride = (size_t)g.tile_rows * (kTileWords / 4);   // uint4 per tile
+        // this thread's line inside a raw slot: box srow / 64, row srow % 64; chunk c sits at c ^ (row & 7)
+        const uint32_t roff = (uint32_t)(srow / kBoxRows) * kBoxBytes + (uint32_t)(srow % kBoxRows) * 128u;
+        const uint32_t rxor = (uint32_t)(srow & 7);
 
-        uint32_t line[2][kTileWords];
-        auto fetch = [&](uint32_t (&dst)[kTileWords], size_t t) {
-            if (!valid || t >= my_tiles || (g.diag & 1)) {
+        constexpr int kMyChunks = NP == 256 ? 4 : 8;                        // 16-byte chunks of a line this thread expands
+        auto produce_stage = [&](size_t it, const uint4 *ch) {              // ch: kKB / 2 chunks = kKB steps
+            const int s = (int)(it % C::kStages);
+            const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
+            mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint8_t *dst = smem + (size_t)s * C::kStageBytes + soff;
+            const uint32_t tdst = tlane + (uint32_t)(s * C::kAStageCols);
+            if (!(g.diag & 4)) {
 #pragma unroll
-                for (int k = 0; k < kTileWords; k++) dst[k] = 0;
-                return;
-            }
-            const uint4 *src = line_base + t * line_stride;
-#pragma unroll
-            for (int k = 0; k < kTileWords / 4; k++) {
-                const uint4 q = __ldg(src + k);
-                dst[4 * k] = q.x; dst[4 * k + 1] = q.y; dst[4 * k + 2] = q.z; dst[4 * k + 3] = q.w;
-            }
-        };
-        auto produce = [&](const uint32_t (&src)[kTileWords], size_t t) {
-#pragma unroll
-            for (int j = 0; j < C::kTileStages; j++) {
-                const size_t it = t * C::kTileStages + j;
-                const int s = (int)(it % C::kStages);
-                const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
-                mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint8_t *dst = smem + (size_t)s * C::kStageBytes + soff;
-                const uint32_t tdst = tlane + (uint32_t)(s * C::kAStageCols);
-                if (!(g.diag & 4)) {
-#pragma unroll
-                    for (int k = 0; k < kKB; k++) {        // K=64 step k of the stage: two words -> chunks 0, 1
-                        const uint4 c0 = expand_word_f4(src[(j * kKB + k) * 2]);
-                        const uint4 c1 = expand_word_f4(src[(j * kKB + k) * 2 + 1]);
-                        *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes) = c0;
-                        *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes + 128) = c1;
-                        if (ATM) tmem_st8(tdst + (uint32_t)(k * 8), c0, c1);
-                    }
+                for (int k = 0; k < kKB; k++) {            // K=64 step k of the stage: two words -> chunks 0, 1
+                    const uint4 q = ch[k >> 1];
+                    const uint4 c0 = expand_word_f4((k & 1) ? q.z : q.x);
+                    const uint4 c1 = expand_word_f4((k & 1) ? q.w : q.y);
+                    *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes) = c0;
+                    *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes + 128) = c1;
+                    tmem_st8(tdst + (uint32_t)(k * 8), c0, c1);
                 }
-                if (ATM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(smem_u32(&full_bar[s]));
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(smem_u32(&full_bar[s]));
         };
 
-        fetch(line[0], (size_t)group);
-        fetch(line[1], (size_t)group + C::kGroups);
-        for (size_t t = group; t < ntiles; t += 2 * C::kGroups) {
+        for (size_t t = (NP == 256 ? 0 : group); t < ntiles; t += (NP == 256 ? 1 : C::kGroups)) {
+            const int rs = (int)(t % C::kRawSlots);
+            mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((t / C::kRawSlots) & 1));
+            uint4 ch[kMyChunks];
+            const uint8_t *line = raw + (size_t)rs * C::kRawBytes + roff;
+            const bool have = valid && t < my_tiles && !(g.diag & 1);
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
-                const size_t cur = t + (size_t)b * C::kGroups;
-                if (cur < ntiles) {
-                    produce(line[b], cur);
-                    fetch(line[b], cur + 2 * C::kGroups);
-                }
+            for (int m = 0; m < kMyChunks; m++) {
+                const uint32_t c = NP == 256 ? (uint32_t)(2 * m + group) : (uint32_t)m;   // chunk of the line
+                ch[m] = have ? *reinterpret_cast<const uint4 *>(line + ((c ^ rxor) << 4)) : make_uint4(0, 0, 0, 0);
+            }
+            mbar_arrive(smem_u32(&raw_empty[rs]));          // the slot may be refilled
+            if (NP == 256) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) produce_stage(t * C::kTileStages + 2 * m + group, &ch[m]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) produce_stage(t * C::kTileStages + j, &ch[2 * j]);
             }
         }
-    } else {
+    } else if (warp == C::kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
         const uint32_t idesc = make_idesc_f4(128, 128);
         const uint64_t desc0 = make_desc(smem_u32(smem), 128, 256);
@@ -304,20 +304,13 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
                     const uint32_t acc = (it | kb) ? 1u : 0u;
                     if (g.diag & 2) continue;
                     if (NP == 128) {
-                        if (ATM) mma_f4_ts(tmem_base, astage + kb * 8, lo, idesc, acc, sf, sf);
-                        else     mma_f4_ss(tmem_base, lo, lo, idesc, acc, sf, sf);
+                        mma_f4_ts(tmem_base, astage + kb * 8, lo, idesc, acc, sf, sf);
                     } else {
                         const uint64_t hi = lo + (uint64_t)((128 * 32) >> 4);            // rows 128..255
                         const uint32_t alo = astage + kb * 8, ahi = alo + kKB * 8;
-                        if (ATM) {
-                            if (g.acc_mask & 1) mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);         // (lo,lo)
-                            if (g.acc_mask & 2) mma_f4_ts(tmem_base + 128, alo, hi, idesc, acc, sf, sf);   // (lo,hi)
-                            if (g.acc_mask & 4) mma_f4_ts(tmem_base + 256, ahi, hi, idesc, acc, sf, sf);   // (hi,hi)
-                        } else {
-                            if (g.acc_mask & 1) mma_f4_ss(tmem_base, lo, lo, idesc, acc, sf, sf);
-                            if (g.acc_mask & 2) mma_f4_ss(tmem_base + 128, lo, hi, idesc, acc, sf, sf);
-                            if (g.acc_mask & 4) mma_f4_ss(tmem_base + 256, hi, hi, idesc, acc, sf, sf);
-                        }
+                        if (g.acc_mask & 1) mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);         // (lo,lo)
+                        if (g.acc_mask & 2) mma_f4_ts(tmem_base + 128, alo, hi, idesc, acc, sf, sf);   // (lo,hi)
+                        if (g.acc_mask & 4) mma_f4_ts(tmem_base + 256, ahi, hi, idesc, acc, sf, sf);   // (hi,hi)
                     }
                 }
                 mma_commit(smem_u32(&empty_bar[s]));      // frees the stage when the MMAs retire
@@ -326,21 +319,58 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
         }
         if (elect_one()) mma_commit(smem_u32(done_bar));
         __syncwarp();
+    } else {
+        // ------------------------------------------------------------ TMA issuer: raw tiles into the ring
+        if (lane == 0 && !(g.diag & 1)) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmap) : "memory");
+            const int nb_lo = (min(g.n_lo, 128) + kBoxRows - 1) / kBoxRows;
+            const int nb_hi = NP == 256 ? (min(g.n_hi, 128) + kBoxRows - 1) / kBoxRows : 0;
+            for (size_t t = 0; t < ntiles; t++) {
+                const int rs = (int)(t % C::kRawSlots);
+                mbar_wait(smem_u32(&raw_empty[rs]), (uint32_t)(((t / C::kRawSlots) & 1) ^ 1));
+                const uint32_t bar = smem_u32(&raw_full[rs]);
+                const uint32_t dst = smem_u32(raw + (size_t)rs * C::kRawBytes);
+                const int tile = (int)(t0 + t);
+                if (DUAL) {
+                    const bool second = tm + t < t1;
+                    mbar_expect_tx(bar, (second ? 2u : 1u) * kBoxBytes);
+                    tma_load_box(dst, &g.tmap, g.row_lo, tile, bar);
+                    if (second) tma_load_box(dst + kBoxBytes, &g.tmap, g.row_lo, (int)(tm + t), bar);
+                } else {
+                    mbar_expect_tx(bar, (uint32_t)(nb_lo + nb_hi) * kBoxBytes);
+                    for (int b = 0; b < nb_lo; b++)
+                        tma_load_box(dst + b * kBoxBytes, &g.tmap, g.row_lo + b * kBoxRows, tile, bar);
+                    for (int b = 0; b < nb_hi; b++)
+                        tma_load_box(dst + (2 + b) * kBoxBytes, &g.tmap, g.row_hi + b * kBoxRows, tile, bar);
+                }
+            }
+        } else if (lane == 0) {
+            // diag & 1: no loads -- just hand the (uninitialised) slots round
+            for (size_t t = 0; t < ntiles; t++) {
+                const int rs = (int)(t % C::kRawSlots);
+                mbar_wait(smem_u32(&raw_empty[rs]), (uint32_t)(((t / C::kRawSlots) & 1) ^ 1));
+                mbar_arrive(smem_u32(&raw_full[rs]));
+            }
+        }
+        __syncwarp();
     }
 
-    if (warp < kMmaWarp && nst && !(g.diag & 2)) {
+    if (warp < C::kProducerWarps && nst && !(g.diag & 2)) {
         // ------------------------------------------------------------ epilogue
-        // warp w reads TMEM lanes 32 (w % 4) ..: row (w % 4) * 32 + lane of an accumulator; the two
-        // warps that share a lane quarter take alternate 32-column chunks
+        // a producer warp reads the TMEM lanes of its quarter: row quarter * 32 + lane of an accumulator; the
+        // warps that share a quarter take different 32-column chunks
         mbar_wait(smem_u32(done_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3, half = warp >> 2;
+        const int group = warp / C::kGroupWarps, wg = warp % C::kGroupWarps;
+        const int quarter = wg & 3;
+        const int cstart = NP == 256 ? 32 * ((wg >> 2) + 2 * group) : 32 * group;
+        constexpr int cstep = NP == 256 ? 128 : 64;
         const int r = quarter * 32 + lane;
         const size_t ld = (size_t)g.ld;
         if (NP == 128 && DUAL) {
             // rows 0..63 x columns 0..63 and rows 64..127 x columns 64..127 are the two halves' Gram blocks
             const int i = r & 63;
-            const int c0 = (r >= 64 ? 64 : 0) + half * 32;
+            const int c0 = (r >= 64 ? 64 : 0) + cstart;
             if ((c0 & 63) < g.n_lo) {                                   // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -361,7 +391,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
                 const int cbase = a == 0 ? g.row_lo : g.row_hi, nc = a == 0 ? g.n_lo : g.n_hi;
                 if (quarter * 32 >= nr) continue;                        // warp-uniform
 #pragma unroll 1
-                for (int c0 = half * 32; c0 < 128; c0 += 64) {
+                for (int c0 = cstart; c0 < 128; c0 += cstep) {
                     if (c0 >= nc) break;
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 128 + c0), v);
@@ -381,24 +411,48 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const GramAr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == C::kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "n"(C::kTmemCols));
     }
 }
 
-// the A operand from tensor memory (default) or, PYKMER_B200_GRAM_A=smem, both operands from shared
-// memory as in round 1 (kept for the measurement that decided it, profiles/r02*_gram_*)
-bool a_from_tmem() {
-    static const bool v = [] {
-        const char *e = getenv("PYKMER_B200_GRAM_A");
-        return !(e && e[0] == 's');
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*pk_encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+
+pk_encode_tiled_t encode_tiled() {
+    static pk_encode_tiled_t fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<pk_encode_tiled_t>(p);
     }();
-    return v;
+    return fn;
+}
+
+int make_tmap(CUtensorMap *map, const uint32_t *bits, int tile_rows, size_t tiles) {
+    pk_encode_tiled_t enc = encode_tiled();
+    if (!enc) return pk_set_error(PK_ERR_CUDA, "gram_f4: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {kTileWords, (cuuint64_t)tile_rows, (cuuint64_t)tiles};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)tile_rows * 128};       // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {kTileWords, kBoxRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t *>(bits), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return pk_set_error(PK_ERR_CUDA, "gram_f4: cuTensorMapEncodeTiled failed (%d) for %d rows x %zu tiles", (int)r,
+                            tile_rows, tiles);
+    return PK_OK;
 }
 
 template <int NP, bool DUAL>
-int launch_one(GramArgs a, int device, cudaStream_t st, size_t force_grid) {
+int launch_one(GramArgs &a, int device, cudaStream_t st, size_t force_grid) {
     using C = F4Cfg<NP>;
     // an FP32 accumulator must stay an exact integer: at most 2^24 k-mers = 2^14 tiles each (the dual
     // slab has one accumulator block per half)
@@ -411,13 +465,8 @@ int launch_one(GramArgs a, int device, cudaStream_t st, size_t force_grid) {
         return pk_set_error(PK_ERR_ARG, "gram_f4: %zu tiles per CTA exceed the exact range of an FP32 accumulator", a.tiles_per_cta);
     a.diag = 0;
     if (const char *env = getenv("PYKMER_B200_GRAM_DIAG")) a.diag = atoi(env);
-    if (a_from_tmem()) {
-        PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, DUAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-        k_gram_f4<NP, DUAL, true><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(a);
-    } else {
-        PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, DUAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-        k_gram_f4<NP, DUAL, false><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(a);
-    }
+    PK_CUDA(cudaFuncSetAttribute(k_gram_f4<NP, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    k_gram_f4<NP, DUAL><<<(unsigned)grid, C::kThreads, C::kSmem, st>>>(a);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -462,9 +511,10 @@ int selfcheck(int device) {
     if (e == cudaSuccess) {
         k_selfcheck_fill<<<296, 256, 0, st>>>(bits);
         GramArgs a{};
-        a.bits = bits; a.tiles = kCheckTiles; a.tile_rows = 3; a.row_lo = 0; a.n_lo = 3; a.acc_mask = 1;
+        a.tiles = kCheckTiles; a.tile_rows = 3; a.row_lo = 0; a.n_lo = 3; a.acc_mask = 1;
         a.gram = gram; a.ld = 3;
-        rc = launch_one<128, false>(a, device, st, 1);
+        rc = make_tmap(&a.tmap, bits, 3, kCheckTiles);
+        if (rc == PK_OK) rc = launch_one<128, false>(a, device, st, 1);
         if (rc == PK_OK) e = cudaMemcpyAsync(h, gram, sizeof h, cudaMemcpyDeviceToHost, st);
         if (rc == PK_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
@@ -514,9 +564,15 @@ int pk_gram_f4_launch(const uint32_t *bits_dev, int nsamples, size_t words, int6
     if (!exact)
         return pk_set_error(PK_ERR_STATE, "gram_f4: this device does not accumulate FP4 products exactly up to 2^24 "
                             "(pk_gram_f4_exact); use the integer Gram kernels (row-major masks, pk_gram_device)");
+    if ((uintptr_t)bits_dev & 15u) return pk_set_error(PK_ERR_ARG, "gram_f4: the masks must be 16-byte aligned");
     GramArgs a{};
-    a.bits = bits_dev; a.tiles = words / 32; a.tile_rows = nsamples;
+    a.tiles = words / 32; a.tile_rows = nsamples;
     a.gram = reinterpret_cast<unsigned long long *>(gram_dev); a.ld = nsamples;
+    if (a.tiles == 0) return PK_OK;
+    {
+        const int rc = make_tmap(&a.tmap, bits_dev, nsamples, a.tiles);
+        if (rc != PK_OK) return rc;
+    }
     if (nsamples <= 64) {
         a.row_lo = 0; a.n_lo = nsamples; a.acc_mask = 1;
         return a.tiles >= 2 ? launch_one<128, true>(a, device, st, 0) : launch_one<128, false>(a, device, st, 0);

@@ -1284,6 +1284,8 @@ size_t scatter_smem_bytes(uint32_t nb) {
 
 }  // namespace
 
+static int g_persist_users[64];               // handles per device holding a persisting-L2 carve-out
+
 struct pk_indexer {
     int K = 0, device = 0, mode = PK_MODE_DIRECT;
     uint64_t lo = 0, hi = 0;
@@ -1943,10 +1945,12 @@ PK_API int pk_indexer_create(pk_indexer **out, int kmer_len, int device, uint64_
             const size_t want = ix->scratch_bytes;
             size_t grant = std::min<size_t>(want, (size_t)std::max(max_persist, 0));
             if (grant && (size_t)max_window >= want &&
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess)
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, grant) == cudaSuccess) {
                 ix->l2_persist_bytes = grant;
-            else
+                g_persist_users[device & 63]++;
+            } else {
                 cudaGetLastError();
+            }
             if (getenv("PYKMER_B200_VERBOSE"))
                 fprintf(stderr, "[pykmer_b200] L2 persist: max %d B, max window %d B, window counters "
                         "%zu B, granted %zu B\n", max_persist, max_window, want, ix->l2_persist_bytes);
@@ -1987,7 +1991,16 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part); cudaFree(ix->route); cudaFree(ix->pool2); cudaFree(ix->sub);
     cudaFree(ix->ovf.keys); cudaFree(ix->ovf.vals); cudaFree(ix->ovf.list); cudaFree(ix->ovf.meta);
-    if (ix->l2_persist_bytes) cudaCtxResetPersistingL2Cache();   // give the carve-out's lines back
+    if (ix->l2_persist_bytes) {
+        // give the carve-out back with its last user: left in place it shrinks the L2 of everything that
+        // runs later in the process (measured: K=17's in-place byte windows after a K=15 handle,
+        // 23.2 ms against 17.2 ms, profiles/r02a_bench_default_line_1gpu.json)
+        cudaCtxResetPersistingL2Cache();
+        if (--g_persist_users[ix->device & 63] <= 0) {
+            g_persist_users[ix->device & 63] = 0;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        }
+    }
     for (int i = 0; i < 16; i++)
         if (ix->peer_ipc[i]) cudaIpcCloseMemHandle(ix->peer_ipc[i]);
     for (int i = 0; i < 2; i++)
