@@ -56,6 +56,18 @@ __host__ __device__ constexpr uint32_t make_idesc_f4(int m, int n) {
     return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
 }
 
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]^T
+__device__ __forceinline__ void mma_f4_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+}
+
 // D[tmem] (+)= A[tmem: lane = row, 8 columns = 64 E2M1] * B[smem descriptor]^T
 __device__ __forceinline__ void mma_f4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
@@ -93,13 +105,18 @@ __device__ __forceinline__ uint4 expand_word_f4(uint32_t w) {
 // bytes) is fetched by TMA (cp.async.bulk.tensor, 64-row boxes, SWIZZLE_128B) into a ring in shared
 // memory; a producer thread owns one row of the staged block, reads ITS 128-byte line back (the swizzle
 // makes a warp's reads of 32 different rows conflict-free) and expands it.
-//   NP = 256: rows = two 128-row blocks (lo, hi); three accumulators (lo,lo), (lo,hi), (hi,hi).  Two
-//             producer groups of 256 threads take alternate STAGES (2 K=64 steps = one 16-byte chunk of
-//             every line each), so one group expands while the other sits in its fence / arrive chain.
-//   NP = 128: one 128-row block, one accumulator; two producer groups of 128 threads (each reaches all
-//             128 TMEM lanes) take alternate TILES.
+//   NP = 256: rows = two 128-row blocks (lo, hi); accumulators (lo,lo) | (lo,hi) -- ONE N=256 instruction with
+//             A = lo from tensor memory -- and (hi,hi), whose A operand stays in shared memory: the 96 TMEM
+//             columns left beside 384 of accumulators and 32 of scale factors hold three 4-step stages of
+//             the lo block, and what bounds the kernel is how many stages are in flight, not their bytes.
+//   NP = 128: one 128-row block, one accumulator, A from tensor memory.
 //             DUAL: the block is [<= 64 samples over the first half of the CTA's tiles; the same samples
 //             over the second half].
+// A stage is big (4 / 8 K=64 steps): the producers' chain per stage -- wait for the slot, store, drain the
+// tensor-memory and shared-memory stores, proxy fence, arrive -- costs several hundred cycles whatever
+// the stage holds (measured, profiles/r02b_gram_sweep_v3_tma_3stage_ring.txt: 2-step stages ran at 220
+// cycles per step with NO MMAs).  Two producer groups of NP threads take alternate stages, so one
+// expands while the other sits in that chain.
 // Warps: producers, then one MMA-issuing warp, then one TMA-issuing warp.
 constexpr int kTileWords = 32;
 constexpr int kTileSteps = 16;                          // K=64 steps per tile
@@ -112,20 +129,22 @@ struct F4Cfg {
     static constexpr int kGroupWarps = NP / 32;                       // one thread per staged row
     static constexpr int kGroupThreads = kGroupWarps * 32;
     static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16 / 8
-    static constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1;
+    static constexpr int kMmaWarp = kProducerWarps;                   // the TMA warp follows it
     static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576 / 320
-    static constexpr int kKB = NP == 256 ? 2 : 4;                     // K=64 steps per stage
-    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 8 / 4
-    static constexpr int kStages = NP == 256 ? 3 : 6;
+    static constexpr int kKB = NP == 256 ? 4 : 8;                     // K=64 steps per stage
+    static constexpr int kStageChunks = kKB / 2;                      // 16-byte chunks of a line per stage
+    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 4 / 2
+    static constexpr int kMyStages = kTileStages / kGroups;           // ... of which a group takes every other one
+    static constexpr int kStages = NP == 256 ? 3 : 4;
     static constexpr int kStepBytes = NP * 32;                        // one K=64 step of all NP rows
-    static constexpr int kStageBytes = kKB * kStepBytes;              // 16 KB either way
+    static constexpr int kStageBytes = kKB * kStepBytes;              // 32 KB either way
     static constexpr int kRawBytes = NP * 128;                        // one raw tile: 32 KB / 16 KB
     static constexpr int kRawSlots = NP == 256 ? 3 : 4;
-    static constexpr int kRawReaders = NP == 256 ? 2 * kGroupThreads : kGroupThreads;   // threads reading one raw tile
+    static constexpr int kRawReaders = kGroups * kGroupThreads;       // every producer reads part of every raw tile
     static constexpr int kAccs = NP == 256 ? 3 : 1;
     static constexpr int kSfCol = kAccs * 128;                        // scale factors behind the accumulators
-    static constexpr int kACol = kSfCol + 32;                         // ring of A operands behind them
-    static constexpr int kAStageCols = kKB * 8 * (NP / 128);          // 8 columns per step and 128-row block
+    static constexpr int kACol = kSfCol + 32;                         // ring of A operands (the lo block) behind them
+    static constexpr int kAStageCols = kKB * 8;                       // 8 columns per step
     static constexpr int kTmemCols = 512;
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + (size_t)kRawSlots * kRawBytes + 512 + 1024;
     static_assert(kACol + kStages * kAStageCols <= kTmemCols, "TMEM budget");
@@ -143,7 +162,8 @@ struct GramArgs {
     int ld;
     size_t tiles_per_cta;
     int diag;                  // PYKMER_B200_GRAM_DIAG (timing experiments only -- the result is then meaningless):
-                               // bit 0 = no TMA loads, bit 1 = no MMAs, bit 2 = no operand stores
+                               // bit 0 = no TMA loads, bit 1 = no MMAs, bit 2 = no operand stores,
+                               // bit 3 = (lo,lo) and (lo,hi) as two N=128 instructions instead of one N=256
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -233,14 +253,13 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
         else valid = r < g.n_lo;
         const int srow = NP == 256 ? half * 128 + r : r;                    // row inside the staged step / raw tile
         const uint32_t soff = (uint32_t)(srow >> 3) * 256u + (uint32_t)(srow & 7) * 16u;
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)C::kACol +
-                               (NP == 256 ? (uint32_t)(half * kKB * 8) : 0u);
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)C::kACol;
+        const bool to_tmem = NP == 128 || half == 0;                        // the lo block is the A operand in TMEM
         // this thread's line inside a raw slot: box srow / 64, row srow % 64; chunk c sits at c ^ (row & 7)
         const uint32_t roff = (uint32_t)(srow / kBoxRows) * kBoxBytes + (uint32_t)(srow % kBoxRows) * 128u;
         const uint32_t rxor = (uint32_t)(srow & 7);
 
-        constexpr int kMyChunks = NP == 256 ? 4 : 8;                        // 16-byte chunks of a line this thread expands
-        auto produce_stage = [&](size_t it, const uint4 *ch) {              // ch: kKB / 2 chunks = kKB steps
+        auto produce_stage = [&](size_t it, const uint4 *ch) {              // ch: kStageChunks chunks = kKB steps
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
@@ -255,16 +274,17 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
                     const uint4 c1 = expand_word_f4((k & 1) ? q.w : q.y);
                     *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes) = c0;
                     *reinterpret_cast<uint4 *>(dst + (size_t)k * C::kStepBytes + 128) = c1;
-                    tmem_st8(tdst + (uint32_t)(k * 8), c0, c1);
+                    if (to_tmem) tmem_st8(tdst + (uint32_t)(k * 8), c0, c1);
                 }
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (to_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(smem_u32(&full_bar[s]));
         };
 
-        for (size_t t = (NP == 256 ? 0 : group); t < ntiles; t += (NP == 256 ? 1 : C::kGroups)) {
+        constexpr int kMyChunks = C::kMyStages * C::kStageChunks;           // chunks of a line this thread expands: 4
+        for (size_t t = 0; t < ntiles; t++) {
             const int rs = (int)(t % C::kRawSlots);
             mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((t / C::kRawSlots) & 1));
             uint4 ch[kMyChunks];
@@ -272,24 +292,23 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
             const bool have = valid && t < my_tiles && !(g.diag & 1);
 #pragma unroll
             for (int m = 0; m < kMyChunks; m++) {
-                const uint32_t c = NP == 256 ? (uint32_t)(2 * m + group) : (uint32_t)m;   // chunk of the line
+                // my m-th chunk: stage (m / kStageChunks) * 2 + group of the tile, chunk m % kStageChunks of it
+                const uint32_t c = (uint32_t)(((m / C::kStageChunks) * C::kGroups + group) * C::kStageChunks +
+                                              m % C::kStageChunks);
                 ch[m] = have ? *reinterpret_cast<const uint4 *>(line + ((c ^ rxor) << 4)) : make_uint4(0, 0, 0, 0);
             }
             mbar_arrive(smem_u32(&raw_empty[rs]));          // the slot may be refilled
-            if (NP == 256) {
 #pragma unroll
-                for (int m = 0; m < 4; m++) produce_stage(t * C::kTileStages + 2 * m + group, &ch[m]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) produce_stage(t * C::kTileStages + j, &ch[2 * j]);
-            }
+            for (int m = 0; m < C::kMyStages; m++)
+                produce_stage(t * C::kTileStages + (size_t)(m * C::kGroups + group), &ch[m * C::kStageChunks]);
         }
     } else if (warp == C::kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc_f4(128, 128);
+        const uint32_t idesc = make_idesc_f4(128, 128), idesc256 = make_idesc_f4(128, 256);
         const uint64_t desc0 = make_desc(smem_u32(smem), 128, 256);
         const uint32_t sf = tmem_base + (uint32_t)C::kSfCol;
         const uint32_t a0 = tmem_base + (uint32_t)C::kACol;
+        const bool fused = NP == 256 && (g.acc_mask & 3) == 3 && !(g.diag & 8);
         for (size_t it = 0; it < nst; it++) {
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
@@ -301,16 +320,20 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
 #pragma unroll
                 for (int kb = 0; kb < kKB; kb++) {
                     const uint64_t lo = dstage + (uint64_t)((kb * C::kStepBytes) >> 4);   // rows 0..127
+                    const uint32_t alo = astage + kb * 8;
                     const uint32_t acc = (it | kb) ? 1u : 0u;
                     if (g.diag & 2) continue;
                     if (NP == 128) {
-                        mma_f4_ts(tmem_base, astage + kb * 8, lo, idesc, acc, sf, sf);
+                        mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);
                     } else {
                         const uint64_t hi = lo + (uint64_t)((128 * 32) >> 4);            // rows 128..255
-                        const uint32_t alo = astage + kb * 8, ahi = alo + kKB * 8;
-                        if (g.acc_mask & 1) mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);         // (lo,lo)
-                        if (g.acc_mask & 2) mma_f4_ts(tmem_base + 128, alo, hi, idesc, acc, sf, sf);   // (lo,hi)
-                        if (g.acc_mask & 4) mma_f4_ts(tmem_base + 256, ahi, hi, idesc, acc, sf, sf);   // (hi,hi)
+                        if (fused) {
+                            mma_f4_ts(tmem_base, alo, lo, idesc256, acc, sf, sf);        // (lo,lo) | (lo,hi): B = all 256 rows
+                        } else {
+                            if (g.acc_mask & 1) mma_f4_ts(tmem_base, alo, lo, idesc, acc, sf, sf);         // (lo,lo)
+                            if (g.acc_mask & 2) mma_f4_ts(tmem_base + 128, alo, hi, idesc, acc, sf, sf);   // (lo,hi)
+                        }
+                        if (g.acc_mask & 4) mma_f4_ss(tmem_base + 256, hi, hi, idesc, acc, sf, sf);        // (hi,hi)
                     }
                 }
                 mma_commit(smem_u32(&empty_bar[s]));      // frees the stage when the MMAs retire

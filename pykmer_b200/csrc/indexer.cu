@@ -430,6 +430,50 @@ __global__ void __launch_bounds__(256) k_feed_settle(uint32_t *__restrict__ cnt,
     }
 }
 
+// ---- routed scan (sequence-sharded multi-GPU without a host round trip) -------------------------
+// Every (source rank, window) owns a fixed region of the window owner's k-mer buffer, sized once from
+// a planning scan; pass 2 stores straight into it (capacity-checked like the estimated pass 1).  The
+// fill counts then travel the same way: k_publish_fill writes them into a small table at the tail of
+// every owner's buffer, and after one stream-ordered collective k_adopt_published turns that table
+// into the owner's segment tables.  kPubEntries 32-bit slots: [source rank][window of the whole job].
+constexpr size_t kPubEntries = (size_t)1 << 18;        // 16 ranks x 16384 windows
+
+struct PublishPeers {
+    uint32_t *pool[16];
+    unsigned long long pub_base[16];
+};
+
+__global__ void __launch_bounds__(256) k_publish_fill(const uint32_t *__restrict__ fill,
+                                                      const uint32_t *__restrict__ cap, uint32_t nb,
+                                                      const uint32_t *__restrict__ owner, const PublishPeers pp,
+                                                      uint32_t self_rank, uint32_t *__restrict__ ctl,
+                                                      unsigned long long *__restrict__ num_kmers,
+                                                      uint32_t *__restrict__ status) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+        const uint32_t o = owner[b];
+        pp.pool[o][pp.pub_base[o] + (size_t)self_rank * nb + b] = min(fill[b], cap[b]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(ctl + 4);
+        *num_kmers += *tmp;
+        *tmp = 0ull;
+        if (status) status[0] = ctl[1];                   // 1: a region overflowed, the step must be redone exactly
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adopt_published(const uint32_t *__restrict__ tail, uint32_t nranks,
+                                                         uint32_t nb_total, uint32_t w0, uint32_t nb_local,
+                                                         const uint32_t *__restrict__ import_off,
+                                                         uint32_t *__restrict__ seg_cnt0,
+                                                         uint32_t *__restrict__ seg_off0) {
+    const uint32_t n = nranks * nb_local;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t src = i / nb_local, w = i % nb_local;
+        seg_cnt0[i] = tail[(size_t)src * nb_total + w0 + w];
+        seg_off0[i] = import_off[i];
+    }
+}
+
 // pass 2: the same scan again; entries are ranked per window in shared memory, staged
 // window by window, and written out as contiguous runs into the segments pass 1 sized.
 // entry = (run length - 1) << kEntShift | offset inside the window.
@@ -1313,7 +1357,13 @@ struct pk_indexer {
     // fused exchange: peer-mapped pools of the window owners and the per-window routing
     uint32_t *peer_pool[16] = {nullptr};
     void *peer_ipc[16] = {nullptr};            // cudaIpcOpenMemHandle bases to close
-    uint32_t *route = nullptr;                 // device: [2][nbuckets] owner, destination offset
+    uint32_t *route = nullptr;                 // device: [3][kMaxBuckets] owner, destination offset, room (routed scan)
+    bool routed = false;                       // pk_indexer_set_route has been called
+    uint32_t *routed_status = nullptr;         // caller's device word receiving the overflow flag of a routed scan
+    int self_rank = 0;
+    unsigned long long pub_base[16] = {0};     // entry index of the published-count table in each owner's buffer
+    uint32_t *import_off = nullptr;            // owner: device [import_nseg][nbuckets] layout of what peers store here
+    uint32_t import_nseg = 0, import_w0 = 0, import_nb_total = 0;
     const uint8_t *p1_seq = nullptr;           // sequence of the pending pass 1
     size_t p1_n = 0;
     size_t pool_cap = 0, pool_ub = 0;          // capacity / upper bound of entries in use
@@ -1614,7 +1664,7 @@ static int indexer_flush(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8
                           : indexer_flush_l2(ix, st, with_stats, table_host);
 }
 
-enum { SCAN_BOTH = 0, SCAN_PASS1 = 1, SCAN_PASS2_REMOTE = 2 };
+enum { SCAN_BOTH = 0, SCAN_PASS1 = 1, SCAN_PASS2_REMOTE = 2, SCAN_ROUTED = 3 };
 
 static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n, cudaStream_t st,
                                int phase = SCAN_BOTH) {
@@ -1675,7 +1725,8 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         bool estimate = phase == SCAN_BOTH && ix->mode == PK_MODE_PARTITION && ix->est_shift > 0 &&
                         n >= ix->est_min && est_need <= ix->pool_cap && est_need < (1ull << 32);
         const size_t need = estimate ? est_need : n;
-        if (phase != SCAN_PASS2_REMOTE && (ix->nseg == kMaxSegments || ix->pool_ub + need > ix->pool_cap)) {
+        const bool remote = phase == SCAN_PASS2_REMOTE || phase == SCAN_ROUTED;
+        if (!remote && (ix->nseg == kMaxSegments || ix->pool_ub + need > ix->pool_cap)) {
             if (ix->mode == PK_MODE_SCAN)
                 return pk_set_error(PK_ERR_STATE, "scan-only handle: k-mer buffer full (%zu entries, %d segments); "
                                     "export and reset before feeding more", ix->pool_cap, ix->nseg);
@@ -1728,7 +1779,7 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             ix->launches += 4;
             p.run_if = ix->cursor + 1;                     // the exact kernels below run only after an overflow
         }
-        if (phase != SCAN_PASS2_REMOTE) {
+        if (!remote) {
             prof_scope ps(ix, st, PROF_BUCKET_COUNT);
             PK_LAUNCH_SCAN(k_scan_bucket_count, grid1, smem1);
             ix->launches += 1;
@@ -1746,10 +1797,15 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
             ix->last_stream = st;
             return PK_OK;                              // pass 2 follows once the routing is known
         }
-        if (phase == SCAN_PASS2_REMOTE) {
+        if (remote) {
             p.win_owner = ix->route;
-            p.dest_off = ix->route + ix->nbuckets;
+            p.dest_off = ix->route + kMaxBuckets;
             for (int i = 0; i < 16; i++) p.peer[i] = ix->peer_pool[i];
+        }
+        if (phase == SCAN_ROUTED) {                        // one pass: fixed, capacity-checked regions; pass 2 tallies
+            p.seg_cap = ix->route + 2 * kMaxBuckets;
+            p.pass1_tally = 0;
+            p.pass2_tally = 1;
         }
         {
             prof_scope ps(ix, st, PROF_SCATTER);
@@ -1757,6 +1813,16 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
         }
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
+        if (phase == SCAN_ROUTED) {
+            PublishPeers pp;
+            for (int i = 0; i < 16; i++) { pp.pool[i] = ix->peer_pool[i]; pp.pub_base[i] = ix->pub_base[i]; }
+            prof_scope ps(ix, st, PROF_OFFSETS);
+            k_publish_fill<<<(ix->nbuckets + 255) / 256, 256, 0, st>>>(
+                seg_fill(ix, f), ix->route + 2 * kMaxBuckets, ix->nbuckets, ix->route, pp, (uint32_t)ix->self_rank,
+                ix->cursor, ix->counters, ix->routed_status);
+            PK_CUDA(cudaGetLastError());
+            ix->launches += 1;
+        }
         if (phase == SCAN_BOTH) {
             ix->nseg++;
             ix->pool_ub += need;
@@ -1990,6 +2056,7 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part); cudaFree(ix->route); cudaFree(ix->pool2); cudaFree(ix->sub);
+    cudaFree(ix->import_off);
     cudaFree(ix->ovf.keys); cudaFree(ix->ovf.vals); cudaFree(ix->ovf.list); cudaFree(ix->ovf.meta);
     if (ix->l2_persist_bytes) {
         // give the carve-out back with its last user: left in place it shrinks the L2 of everything that
@@ -2398,10 +2465,11 @@ PK_API int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32
         PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
         PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
     }
-    if (!ix->route) PK_CUDA(cudaMalloc(&ix->route, (size_t)2 * kMaxBuckets * sizeof(uint32_t)));
+    if (!ix->route) PK_CUDA(cudaMalloc(&ix->route, (size_t)3 * kMaxBuckets * sizeof(uint32_t)));
     PK_CUDA(cudaMemcpyAsync(ix->route, owner_host, ix->nbuckets * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(ix->route + ix->nbuckets, dest_off_host, ix->nbuckets * sizeof(uint32_t),
+    PK_CUDA(cudaMemcpyAsync(ix->route + kMaxBuckets, dest_off_host, ix->nbuckets * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, st));
+    ix->routed = false;                        // the routing of a routed scan, if any, has been replaced
     const uint8_t *seq = ix->p1_seq;
     const size_t n = ix->p1_n;
     ix->p1_seq = nullptr;
@@ -2409,6 +2477,105 @@ PK_API int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32
     const int rc = indexer_launch_scan(ix, seq, n, st, SCAN_PASS2_REMOTE);
     if (rc != PK_OK) return rc;
     PK_CUDA(cudaStreamSynchronize(st));        // the pageable routing tables may go away; stores have landed
+    return PK_OK;
+}
+
+// ---- routed scan: fixed regions, no host round trip per step -------------------------------------
+PK_API int pk_indexer_pub_base(pk_indexer *ix, uint64_t *entry_index) {
+    PK_REQUIRE(ix != nullptr && entry_index != nullptr, "pk_indexer_pub_base: NULL argument");
+    PK_REQUIRE(ix->pool != nullptr && ix->pool_cap > 2 * kPubEntries, "pk_indexer_pub_base: the handle's k-mer buffer is too small");
+    *entry_index = ix->pool_cap - kPubEntries;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_set_route(pk_indexer *ix, int nranks, int self_rank, const uint32_t *owner_host,
+                                const uint32_t *dest_off_host, const uint32_t *cap_host,
+                                const uint64_t *pub_base_host) {
+    PK_REQUIRE(ix != nullptr && ix->mode == PK_MODE_SCAN, "pk_indexer_set_route: needs a scan-only handle");
+    PK_REQUIRE(owner_host && dest_off_host && cap_host && pub_base_host, "pk_indexer_set_route: NULL argument");
+    PK_REQUIRE(nranks >= 1 && nranks <= 16 && self_rank >= 0 && self_rank < nranks, "pk_indexer_set_route: rank %d of %d", self_rank, nranks);
+    PK_REQUIRE((size_t)nranks * ix->nbuckets <= kPubEntries, "pk_indexer_set_route: %d ranks x %u windows exceed the published-count table", nranks, ix->nbuckets);
+    for (uint32_t b = 0; b < ix->nbuckets; b++) {
+        PK_REQUIRE(owner_host[b] < (uint32_t)nranks && ix->peer_pool[owner_host[b]] != nullptr,
+                   "pk_indexer_set_route: window %u routed to rank %u whose buffer is not open", b, owner_host[b]);
+        PK_REQUIRE((uint64_t)dest_off_host[b] + cap_host[b] <= pub_base_host[owner_host[b]],
+                   "pk_indexer_set_route: the region of window %u runs into the published-count table", b);
+    }
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));
+    if (!ix->route) PK_CUDA(cudaMalloc(&ix->route, (size_t)3 * kMaxBuckets * sizeof(uint32_t)));
+    PK_CUDA(cudaMemcpy(ix->route, owner_host, ix->nbuckets * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemcpy(ix->route + kMaxBuckets, dest_off_host, ix->nbuckets * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemcpy(ix->route + 2 * kMaxBuckets, cap_host, ix->nbuckets * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 16; i++) ix->pub_base[i] = i < nranks ? pub_base_host[i] : 0;
+    ix->self_rank = self_rank;
+    ix->routed = true;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_scan_routed(pk_indexer *ix, const uint8_t *seq_dev, size_t n, uint32_t *status_dev,
+                                  pk_stream stream) {
+    PK_REQUIRE(ix != nullptr && ix->mode == PK_MODE_SCAN && ix->routed, "pk_indexer_scan_routed: needs a scan-only handle with a route (pk_indexer_set_route)");
+    PK_REQUIRE(seq_dev != nullptr && n > 0 && n <= kMaxFeed, "pk_indexer_scan_routed: between 1 and 2^30 bases per pass");
+    PK_REQUIRE(((uintptr_t)seq_dev & 15u) == 0, "pk_indexer_scan_routed: seq_dev must be 16-byte aligned");
+    PK_REQUIRE(ix->nseg == 0 && ix->p1_seq == nullptr && !ix->fed, "pk_indexer_scan_routed: one routed scan per reset");
+    pk_device_guard guard(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != ix->last_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
+    }
+    ix->routed_status = status_dev;
+    const int rc = indexer_launch_scan(ix, seq_dev, n, st, SCAN_ROUTED);
+    ix->routed_status = nullptr;
+    return rc;
+}
+
+PK_API int pk_indexer_set_import_layout(pk_indexer *ix, uint32_t nseg, const uint32_t *seg_off_host,
+                                        uint32_t first_window, uint32_t nwindows_total) {
+    PK_REQUIRE(ix != nullptr && ix->mode == PK_MODE_PARTITION, "pk_indexer_set_import_layout: the handle must count in PARTITION mode");
+    PK_REQUIRE(nseg >= 1 && nseg <= 16 && seg_off_host != nullptr, "pk_indexer_set_import_layout: 1..16 source ranks");
+    PK_REQUIRE((size_t)nseg * nwindows_total <= kPubEntries && first_window + ix->nbuckets <= nwindows_total,
+               "pk_indexer_set_import_layout: windows [%u, +%u) of %u", first_window, ix->nbuckets, nwindows_total);
+    PK_REQUIRE(ix->pool_cap > 2 * kPubEntries, "pk_indexer_set_import_layout: the handle's k-mer buffer is too small");
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));
+    cudaFree(ix->import_off);
+    ix->import_off = nullptr;
+    const size_t n = (size_t)nseg * ix->nbuckets;
+    PK_CUDA(cudaMalloc(&ix->import_off, n * sizeof(uint32_t)));
+    PK_CUDA(cudaMemcpy(ix->import_off, seg_off_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ix->import_nseg = nseg; ix->import_w0 = first_window; ix->import_nb_total = nwindows_total;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_import_published(pk_indexer *ix, pk_stream stream) {
+    PK_REQUIRE(ix != nullptr && ix->import_off != nullptr, "pk_indexer_import_published: no import layout (pk_indexer_set_import_layout)");
+    PK_REQUIRE(ix->nseg == 0, "pk_indexer_import_published: the handle already buffers k-mers of its own");
+    pk_device_guard guard(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != ix->last_stream) {
+        PK_CUDA(cudaEventRecord(ix->joined, ix->last_stream));
+        PK_CUDA(cudaStreamWaitEvent(st, ix->joined, 0));
+    }
+    const uint32_t n = ix->import_nseg * ix->nbuckets;
+    k_adopt_published<<<(n + 255) / 256, 256, 0, st>>>(ix->pool + (ix->pool_cap - kPubEntries), ix->import_nseg,
+                                                       ix->import_nb_total, ix->import_w0, ix->nbuckets, ix->import_off,
+                                                       seg_cnt(ix, 0), seg_off(ix, 0));
+    PK_CUDA(cudaGetLastError());
+    ix->launches += 1;
+    ix->pool_ext = ix->pool;
+    ix->nseg = (int)ix->import_nseg;
+    ix->stats_valid = false;
+    ix->last_stream = st;
     return PK_OK;
 }
 
