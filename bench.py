@@ -69,9 +69,11 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=50, help="merger: number of samples")
     ap.add_argument("--max-count", type=int, default=50, help="merger: --max-count")
     ap.add_argument("--mode", type=int, default=0, help="indexer counting mode (0 auto)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="sequence sharding: 'fused' = pass 2 stores into the owners' buffers over NVLink "
-                         "(CUDA IPC peer mappings), 'nccl' = bucket locally, then torch all_to_all_single")
+    ap.add_argument("--exchange", default="routed", choices=["routed", "fused", "nccl"],
+                    help="sequence sharding: 'routed' = ONE scan pass stores into fixed regions of the owners' "
+                         "buffers over NVLink (CUDA IPC peer mappings), sized once by the planning scan, no host "
+                         "round trip inside a step; 'fused' = exact two-pass form (counts all-gathered through the "
+                         "host every step), 'nccl' = bucket locally, then torch all_to_all_single")
     ap.add_argument("--shard", default="auto", choices=["auto", "sequence", "kmer"],
                     help="N > 1 indexer: 'sequence' = each rank scans 1/N of the stream and the k-mer entries "
                          "go to the window owners; 'kmer' = every rank scans everything, keeps its k-mer range")
@@ -512,13 +514,17 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
     wl = scanner.window_log2()
     lo, hi = w0 << wl, min(T, w1 << wl)
     counter = dev.Indexer(K, device=local_rank, range_lo=lo, range_hi=hi, mode=nat.PK_MODE_PARTITION)
-    fused = args.exchange == "fused"
+    routed = args.exchange == "routed"
+    fused = args.exchange in ("fused", "routed")
     if fused:
         pdist.connect_peer_pools(scanner, counter)
+    if routed:
+        pdist.setup_routed(scanner, counter, all_cnt.sum(axis=1), owners)
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
     stage = torch.empty(b - a, dtype=torch.uint8, device="cuda") if fused else None
-    last = {}
+    last = {"exact_redo": 0}
 
-    def step_device(src_host=None, table_out=None):
+    def step_device(src_host=None, table_out=None, exact=False):
         if fused:
             scanner.reset()
             scanner.prime(halo, a)
@@ -527,7 +533,12 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
             if src_host is not None:
                 stage.copy_(src_host, non_blocking=True)
                 src = stage
-            buf = pdist.exchange_fused(scanner, counter, src, owners)
+            if routed and not exact:
+                status.zero_()
+                pdist.exchange_routed(scanner, counter, src, status)
+                buf = None
+            else:
+                buf = pdist.exchange_fused(scanner, counter, src, owners)
         else:
             scan(src_host)
             counter.reset()
@@ -535,6 +546,11 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
         hist, st = counter.finalize(table_out=table_out)
         st["num_kmers"] = scanner.scan_result()
         hist, st = pdist.reduce_index_stats(hist, st)
+        if routed and not exact and int(status[0].item()):
+            # a region overflowed somewhere (the stream no longer looks like the planning scan): the
+            # step is void, redo it with the exact two-pass protocol -- inside the timed region
+            last["exact_redo"] += 1
+            return step_device(src_host, table_out, exact=True)
         last["hist"], last["st"], last["buf"] = hist, st, buf
 
     sampler = ClockSampler(local_rank)
@@ -551,7 +567,13 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     if fused:
         scanner.reset(); scanner.prime(halo, a); counter.reset()
-        ev[0].record(); pdist.exchange_fused(scanner, counter, d_slice, owners); ev[1].record()
+        ev[0].record()
+        if routed:
+            status.zero_()
+            pdist.exchange_routed(scanner, counter, d_slice, status)
+        else:
+            pdist.exchange_fused(scanner, counter, d_slice, owners)
+        ev[1].record()
     else:
         scan(); counter.reset()
         ev[0].record(); last["buf"] = pdist.exchange_entries(scanner, counter, owners); ev[1].record()
@@ -599,8 +621,9 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
         "data": "synthetic",
         "config": {"workload": workload_name("indexer", K, bp=L),
                    "parallelism": f"sequence x{world} scan, k-mer entries to window owners "
-                                  f"({'stores over NVLink fused into pass 2' if fused else 'NCCL all-to-all'}), "
+                                  f"({'stores over NVLink fused into the scan, fixed regions, no host round trip' if routed else 'stores over NVLink fused into pass 2' if fused else 'NCCL all-to-all'}), "
                                   f"kmer-window x{world} count",
+                   "exact_redo_steps": last["exact_redo"],
                    "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
                    "vals_count": st["vals_count"], "vals_max": st["vals_max"],
                    "records_with_kmers": int(flags.sum())},

@@ -164,6 +164,30 @@ int pk_indexer_pass1_counts(pk_indexer *ix, uint32_t *counts_host, size_t nwindo
 int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32_t *owner_host,
                                  const uint32_t *dest_off_host, pk_stream stream);
 
+/* Routed scan: the same fused exchange with NO host round trip inside a step -- for jobs that index
+ * the same kind of stream again and again (bench.py's steady state; a planning scan sizes it once).
+ * Every (source rank, window) owns a fixed region of the window owner's k-mer buffer:
+ * pk_indexer_set_route gives a scanner, per window, the owner rank, the region's offset in the owner's
+ * buffer and its room in entries (plus, per rank, where the owner's published-count table starts:
+ * pk_indexer_pub_base, the last 2^18 entries of its buffer).  pk_indexer_scan_routed is then ONE pass:
+ * scan, store into the regions (capacity-checked), count num_kmers, flag records, and write the fill
+ * counts into every owner's table -- all asynchronous on `stream`; status_dev[0] (device memory of the
+ * caller) becomes 1 if a region overflowed, in which case the step must be redone with the exact
+ * two-pass protocol above.  After ONE stream-ordered collective over all ranks (e.g. an NCCL
+ * all-reduce of the status words: every rank's stores have landed when it completes)
+ * pk_indexer_import_published turns the table into the owner's segment tables (layout given once by
+ * pk_indexer_set_import_layout: seg_off_host[source][local window], first_window = global index of the
+ * owner's window 0, nwindows_total = windows of the whole job) and pk_indexer_finalize counts. */
+int pk_indexer_pub_base(pk_indexer *ix, uint64_t *entry_index);
+int pk_indexer_set_route(pk_indexer *scanner, int nranks, int self_rank, const uint32_t *owner_host,
+                         const uint32_t *dest_off_host, const uint32_t *cap_host,
+                         const uint64_t *pub_base_host);
+int pk_indexer_scan_routed(pk_indexer *scanner, const uint8_t *seq_dev, size_t n, uint32_t *status_dev,
+                           pk_stream stream);
+int pk_indexer_set_import_layout(pk_indexer *owner, uint32_t nseg, const uint32_t *seg_off_host,
+                                 uint32_t first_window, uint32_t nwindows_total);
+int pk_indexer_import_published(pk_indexer *owner, pk_stream stream);
+
 /* Per-kernel-class device time, measured with CUDA events on the launching stream
  * around every launch made through the handle while enabled.  Classes (index into
  * ms_host / launches_host): 0 scan_count_direct, 1 scan_bucket_count, 2 bucket_offsets,

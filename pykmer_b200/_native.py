@@ -26,6 +26,8 @@ SYMBOLS = (
     "pk_indexer_prime", "pk_indexer_scan_result", "pk_indexer_export_segments",
     "pk_indexer_import_segments", "pk_indexer_pool_ipc_handle", "pk_indexer_open_peer_pool",
     "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
+    "pk_indexer_pub_base", "pk_indexer_set_route", "pk_indexer_scan_routed", "pk_indexer_set_import_layout",
+    "pk_indexer_import_published",
     "pk_table_stats_device",
     "pk_threshold_pack_device", "pk_gram_device", "pk_threshold_pack_tiled_device", "pk_gram_tiled_device", "pk_gram_tiled_exact", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device", "pk_bgzf_inflate", "pk_fasta_clean", "pk_bgzf_deflate", "pk_fasta_find_headers",
@@ -85,6 +87,11 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_scan_pass1": [vp, vp, sz, vp],
         "pk_indexer_pass1_counts": [vp, vp, sz],
         "pk_indexer_scan_pass2_remote": [vp, i32, vp, vp, vp],
+        "pk_indexer_pub_base": [vp, c.POINTER(u64)],
+        "pk_indexer_set_route": [vp, i32, i32, vp, vp, vp, vp],
+        "pk_indexer_scan_routed": [vp, vp, sz, vp, vp],
+        "pk_indexer_set_import_layout": [vp, c.c_uint32, vp, c.c_uint32, c.c_uint32],
+        "pk_indexer_import_published": [vp, vp],
         "pk_table_stats_device": [vp, sz, vp, vp, vp],
         "pk_threshold_pack_device": [vp, sz, i32, i32, vp, vp],
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],

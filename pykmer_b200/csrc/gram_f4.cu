@@ -166,6 +166,12 @@ struct GramArgs {
                                // bit 3 = (lo,lo) and (lo,hi) as two N=128 instructions instead of one N=256
 };
 
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+            __syncwarp();          // lanes leave the wait loop one by one; tcgen05.st / wait::st below are .aligned
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint8_t *dst = smem + (size_t)s * C::kStageBytes + soff;
             const uint32_t tdst = tlane + (uint32_t)(s * C::kAStageCols);
@@ -287,17 +294,22 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
         for (size_t t = 0; t < ntiles; t++) {
             const int rs = (int)(t % C::kRawSlots);
             mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((t / C::kRawSlots) & 1));
+            __syncwarp();
             uint4 ch[kMyChunks];
-            const uint8_t *line = raw + (size_t)rs * C::kRawBytes + roff;
+            const uint32_t line = smem_u32(raw) + (uint32_t)rs * C::kRawBytes + roff;
             const bool have = valid && t < my_tiles && !(g.diag & 1);
 #pragma unroll
             for (int m = 0; m < kMyChunks; m++) {
                 // my m-th chunk: stage (m / kStageChunks) * 2 + group of the tile, chunk m % kStageChunks of it
                 const uint32_t c = (uint32_t)(((m / C::kStageChunks) * C::kGroups + group) * C::kStageChunks +
                                               m % C::kStageChunks);
-                ch[m] = have ? *reinterpret_cast<const uint4 *>(line + ((c ^ rxor) << 4)) : make_uint4(0, 0, 0, 0);
+                ch[m] = have ? lds128(line + ((c ^ rxor) << 4)) : make_uint4(0, 0, 0, 0);
             }
-            mbar_arrive(smem_u32(&raw_empty[rs]));          // the slot may be refilled
+            // The slot may be refilled -- once the loads above have RETURNED.  mbarrier.arrive does not wait
+            // for outstanding loads by itself (SASS: LD ... SYNCS.ARRIVE back to back), and a TMA write that
+            // overtakes them showed up as one stale row in a few launches out of ten (round 2, pass c).
+            __threadfence_block();
+            mbar_arrive(smem_u32(&raw_empty[rs]));
 #pragma unroll
             for (int m = 0; m < C::kMyStages; m++)
                 produce_stage(t * C::kTileStages + (size_t)(m * C::kGroups + group), &ch[m * C::kStageChunks]);
@@ -313,6 +325,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&full_bar[s]), phase);
+            __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint64_t dstage = desc0 + (uint64_t)((s * C::kStageBytes) >> 4);
@@ -383,6 +396,7 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
         // a producer warp reads the TMEM lanes of its quarter: row quarter * 32 + lane of an accumulator; the
         // warps that share a quarter take different 32-column chunks
         mbar_wait(smem_u32(done_bar), 0);
+        __syncwarp();              // tcgen05.ld below is .aligned
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int group = warp / C::kGroupWarps, wg = warp % C::kGroupWarps;
         const int quarter = wg & 3;

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
             const int s = (int)(it % C::kStages);
             const uint32_t phase = (uint32_t)((it / C::kStages) & 1);
             mbar_wait(smem_u32(&full_bar[s]), phase);
+            __syncwarp();          // lanes leave the wait loop one by one; elect.sync wants the whole warp
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 // descriptor start address is in 16-byte units: stage and K-step are plain adds
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(GramCfg<NP>::kThreads, 1) k_gram_i8(const uint
     if (warp < 4 && nst) {
         // ------------------------------------------------------------ epilogue
         mbar_wait(smem_u32(done_bar), 0);
+        __syncwarp();              // tcgen05.ld below is .aligned
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int mt = 0; mt < C::kMTiles; mt++) {

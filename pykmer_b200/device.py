@@ -261,6 +261,40 @@ class Indexer:
         nat.check(lib.pk_indexer_import_segments(self._h, None, seg_off.shape[0], seg_off.ctypes.data,
                                                  seg_cnt.ctypes.data))
 
+    # ---- routed scan: fixed regions in the owners' buffers, no host round trip per step ---------
+    def pub_base(self) -> int:
+        v = ctypes.c_uint64(0)
+        nat.check(lib.pk_indexer_pub_base(self._h, ctypes.byref(v)))
+        return int(v.value)
+
+    def set_route(self, nranks: int, self_rank: int, owner: np.ndarray, dest_off: np.ndarray, cap: np.ndarray,
+                  pub_base: Sequence[int]) -> None:
+        owner = np.ascontiguousarray(owner, dtype=np.uint32)
+        dest_off = np.ascontiguousarray(dest_off, dtype=np.uint32)
+        cap = np.ascontiguousarray(cap, dtype=np.uint32)
+        pb = np.ascontiguousarray(pub_base, dtype=np.uint64)
+        assert pb.size == nranks
+        nat.check(lib.pk_indexer_set_route(self._h, nranks, self_rank, owner.ctypes.data, dest_off.ctypes.data,
+                                           cap.ctypes.data, pb.ctypes.data))
+
+    def scan_routed(self, seq: torch.Tensor, status: torch.Tensor, stream=None) -> None:
+        """One asynchronous pass: scan `seq`, store the entries into the owners' regions, publish the
+        fill counts; status (int32 CUDA tensor) [0] = 1 if a region overflowed."""
+        assert seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()
+        assert status.is_cuda and status.element_size() == 4
+        self._keep.append(seq)
+        nat.check(lib.pk_indexer_scan_routed(self._h, seq.data_ptr(), seq.numel(), status.data_ptr(),
+                                             _stream_ptr(stream)))
+
+    def set_import_layout(self, seg_off: np.ndarray, first_window: int, nwindows_total: int) -> None:
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint32)
+        assert seg_off.ndim == 2
+        nat.check(lib.pk_indexer_set_import_layout(self._h, seg_off.shape[0], seg_off.ctypes.data, first_window,
+                                                   nwindows_total))
+
+    def import_published(self, stream=None) -> None:
+        nat.check(lib.pk_indexer_import_published(self._h, _stream_ptr(stream)))
+
     PROFILE_CLASSES = ("scan_count_direct", "scan_bucket_count", "bucket_offsets", "scan_scatter",
                        "window_count", "window_commit", "table_stats", "update_carry")
 

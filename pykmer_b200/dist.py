@@ -11,7 +11,7 @@ The sequence itself is either read by every rank or broadcast once from rank 0
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -372,3 +372,56 @@ def exchange_fused(scanner, counter, seq: torch.Tensor, owners: List[Tuple[int, 
     dist.barrier(group=group)                                       # ... on every rank
     counter.import_own_pool(imp_off, imp_cnt)
     return all_cnt
+
+
+# ---------------------------------------------------------------------------------------------
+# Routed exchange: the fused exchange without a host round trip inside a step.  A planning scan
+# (exact per-window counts of every rank, once, untimed) sizes a fixed region per (source rank,
+# window) in the owner's buffer; a step is then ONE scan pass per rank that stores into the regions
+# and publishes its fill counts into a table at the tail of every owner's buffer, ONE stream-ordered
+# all-reduce (it carries the overflow flags and orders every rank's stores before every owner's
+# count), and the owners' count + commit.  The host only reads the statistics at the end.
+
+def plan_routed(all_cnt: np.ndarray, owners: List[Tuple[int, int]], rank: int, pub_base: Sequence[int],
+                slack: int = 4096):
+    """all_cnt[s, w] = entries of source rank s in window w (planning scan).  Room of a region =
+    count * (1 + 1/16) + slack.  -> (owner_of[w], dest_off_mine[w], cap_mine[w], imp_off[s, local w])."""
+    nranks, nwin = all_cnt.shape
+    cnt = all_cnt.astype(np.int64)
+    cap = cnt + cnt // 16 + slack
+    owner_of = np.zeros(nwin, dtype=np.uint32)
+    off = np.zeros((nranks, nwin), dtype=np.int64)
+    for d, (a, b) in enumerate(owners):
+        owner_of[a:b] = d
+        flat = cap[:, a:b].reshape(-1)                       # source by source, window by window
+        start = np.concatenate(([0], np.cumsum(flat)[:-1])) if flat.size else np.zeros(0, dtype=np.int64)
+        off[:, a:b] = start.reshape(nranks, b - a)
+        total = int(flat.sum())
+        if total > int(pub_base[d]):
+            raise ValueError(f"routed exchange: rank {d} would receive up to {total} entries, its buffer holds {int(pub_base[d])}")
+    assert off.max(initial=0) < 2 ** 32 and cap.max(initial=0) < 2 ** 32
+    w0, w1 = owners[rank]
+    return owner_of, off[rank].astype(np.uint32), cap[rank].astype(np.uint32), off[:, w0:w1].astype(np.uint32)
+
+
+def setup_routed(scanner, counter, all_cnt: np.ndarray, owners: List[Tuple[int, int]], group=None) -> None:
+    """Once per job, after connect_peer_pools: exchange the owners' table positions, give the
+    scanner its route and the counter its import layout."""
+    rank, nranks = world()
+    dev = _device_for_backend()
+    mine = torch.tensor([counter.pub_base()], dtype=torch.int64, device=dev)
+    every = torch.empty(nranks, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    pub = [int(v) for v in every.cpu().tolist()]
+    owner_of, dest_off, cap, imp_off = plan_routed(all_cnt, owners, rank, pub)
+    scanner.set_route(nranks, rank, owner_of, dest_off, cap, pub)
+    counter.set_import_layout(imp_off, owners[rank][0], all_cnt.shape[1])
+
+
+def exchange_routed(scanner, counter, seq: torch.Tensor, status: torch.Tensor, group=None) -> None:
+    """One step of the routed exchange (scanner reset + primed, counter reset; setup_routed done).
+    Nothing here waits on the host.  After counter.finalize() the caller reads status[0]: non-zero =
+    some region overflowed on some rank, redo the step with exchange_fused."""
+    scanner.scan_routed(seq, status)
+    dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)      # overflow flags + "all stores have landed"
+    counter.import_published()

@@ -971,6 +971,82 @@ def test_fused_exchange_routing_on_one_gpu(env, K, wlog, nranks):
     assert np.array_equal(np.concatenate(tables), want)
 
 
+@pytest.mark.parametrize("K,wlog,nranks", [(9, 10, 3), (11, 12, 2), (15, 24, 4), (17, 12, 4)])
+def test_routed_exchange_on_one_gpu(env, K, wlog, nranks):
+    """The routed multi-GPU path -- fixed, capacity-checked regions per (source rank, window) sized
+    from a planning scan, fill counts published into the owners' buffers, no host round trip -- with
+    all 'ranks' living on one GPU.  Also: regions that are too small raise the overflow status
+    instead of writing past their room."""
+    import torch
+    from pykmer_b200 import dist as pdist, _native as nat
+    dev, oracle = env["dev"], env["oracle"]
+    rng = np.random.default_rng(K * 13 + nranks)
+    s = _random_stream(rng, 150_000)
+    if K > 13:
+        s[::7] = ord("A"); s[1::7] = ord("A"); s[2::7] = ord("A")
+    starts = np.array([0, 30_000, 30_001, 90_000], dtype=np.uint64)
+    hi_all = min(4 ** K, 1 << (22 if wlog < 24 else 26))
+    want, num, oflags = oracle.index_stream(s, K, range_hi=hi_all, rec_starts=starts)
+    os.environ["PYKMER_B200_WINDOW_LOG2"] = str(wlog)
+    try:
+        scanners, pieces, halos, offs = [], [], [], []
+        for r in range(nranks):
+            a, b = pdist.slice_bounds(len(s), r, nranks)
+            sc = dev.Indexer(K, range_hi=hi_all, mode=nat.PK_MODE_SCAN)
+            sc.set_records(starts)
+            halos.append(torch.from_numpy(s[max(0, a - 32):a].copy()).cuda() if a > 0 else None)
+            offs.append(a)
+            pieces.append(torch.from_numpy(s[a:b].copy()).cuda())
+            sc.prime(halos[r], a)
+            sc.scan_pass1(pieces[r])                           # the planning scan: exact counts per window
+            scanners.append(sc)
+        all_cnt = np.stack([sc.pass1_counts() for sc in scanners]).astype(np.int64)
+        nwin = all_cnt.shape[1]
+        owners = pdist.balanced_window_owners(all_cnt.sum(axis=0), nranks, overhead=10)
+        counters = []
+        for d in range(nranks):
+            w0, w1 = owners[d]
+            counters.append(dev.Indexer(K, range_lo=w0 << wlog, range_hi=min(hi_all, w1 << wlog),
+                                        mode=nat.PK_MODE_PARTITION))
+        pub = [ct.pub_base() for ct in counters]
+        status = torch.zeros((nranks, 4), dtype=torch.int32, device="cuda")
+        for attempt, (counts, slack) in enumerate(((all_cnt // 3, 0), (all_cnt, 64))):
+            for r, sc in enumerate(scanners):
+                for d in range(nranks):
+                    sc.open_peer_pool(d, local_owner=counters[d])
+                owner_of, dest_off, cap, _ = pdist.plan_routed(counts, owners, r, pub, slack=slack)
+                sc.set_route(nranks, r, owner_of, dest_off, cap, pub)
+                sc.reset()
+                sc.prime(halos[r], offs[r])
+                sc.scan_routed(pieces[r], status[r])
+            for d, ct in enumerate(counters):
+                _, _, _, imp_off = pdist.plan_routed(counts, owners, d, pub, slack=slack)
+                ct.reset()
+                ct.set_import_layout(imp_off, owners[d][0], nwin)
+                ct.import_published()
+            flagged = status[:, 0].cpu().numpy()
+            if attempt == 0:
+                assert flagged.any(), "regions a third of the size they need must overflow"
+                for ct in counters:
+                    ct.finalize()                              # harmless: the step is discarded
+                continue
+            assert not flagged.any()
+            tables = []
+            for ct in counters:
+                ct.finalize()
+                tables.append(ct.table_to_host().numpy().copy())
+        total = sum(sc.scan_result() for sc in scanners)
+        flags = np.zeros(len(starts), dtype=np.uint8)
+        for sc in scanners:
+            flags |= sc.record_flags()
+        for h in scanners + counters:
+            h.close()
+    finally:
+        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
+    assert total == num and np.array_equal(flags, oflags)
+    assert np.array_equal(np.concatenate(tables), want)
+
+
 # ---------------------------------------------------------------------------------------------
 # The CLIs as multi-rank jobs with the real library: two ranks (gloo rendezvous, both on cuda:0)
 # each own half of the canonical k-mer axis.  The host protocol alone is covered on the CPU in
