@@ -91,6 +91,9 @@ int pk_indexer_reset(pk_indexer *ix, pk_stream stream);
  * (records are discovered as the file is parsed); entries already registered
  * must not change. */
 int pk_indexer_set_records(pk_indexer *ix, const uint64_t *rec_starts_host, size_t nrec);
+/* The same table grown by n more records: only the new offsets are checked and uploaded (a draft
+ * assembly or a read set has millions of records and arrives in hundreds of pieces). */
+int pk_indexer_append_records(pk_indexer *ix, const uint64_t *new_starts_host, size_t n);
 
 /* seq_dev must be 16-byte aligned.  Asynchronous on `stream`. */
 int pk_indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_stream stream);
@@ -100,6 +103,9 @@ int pk_indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_
  * untouched until pk_indexer_sync / pk_indexer_finalize. */
 int pk_indexer_feed_host(pk_indexer *ix, const uint8_t *seq_host, size_t n);
 int pk_indexer_sync(pk_indexer *ix);
+/* PARTITION mode: count everything buffered so far into the table now (asynchronous; statistics are
+ * left to pk_indexer_finalize).  Lets pk_indexer_import_segments be called once per piece of a stream. */
+int pk_indexer_flush(pk_indexer *ix);
 
 /* Finish counting and compute the statistics of tools.py:246-263 over the
  * handle's range.  hist_host[i] = #{table == i+1}, i in 0..254.
@@ -130,7 +136,9 @@ int pk_indexer_launch_count(pk_indexer *ix, uint64_t *launches);
  *
  * pk_indexer_prime: start a slice in the middle of the stream -- the up-to-32 bytes that
  *   precede it become the window carry (no k-mer is counted for them) and stream_off is the
- *   stream offset of the next byte fed (record flags use it).
+ *   stream offset of the next byte fed (record flags use it).  On a scan-only handle with nothing
+ *   buffered it also starts the per-window counts from zero again (num_kmers and the record flags
+ *   keep accumulating), so one scanner can take a slice of every piece of a long stream.
  * pk_indexer_export_segments: device pointer of the entry buffer and, per fed segment and
  *   window, the offset and count of its entries (host arrays of nseg * nwindows uint32;
  *   pass NULL arrays to query nseg / nwindows).  Synchronises.

@@ -19,6 +19,7 @@ SYMBOLS = (
     "pk_abi_version", "pk_last_error", "pk_device_count", "pk_device_info",
     "pk_host_alloc", "pk_host_free",
     "pk_indexer_create", "pk_indexer_destroy", "pk_indexer_reset", "pk_indexer_set_records",
+    "pk_indexer_append_records", "pk_indexer_flush",
     "pk_indexer_feed_device", "pk_indexer_feed_host", "pk_indexer_sync", "pk_indexer_finalize",
     "pk_indexer_finalize_to_host",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
@@ -64,6 +65,8 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_destroy": [vp],
         "pk_indexer_reset": [vp, vp],
         "pk_indexer_set_records": [vp, vp, sz],
+        "pk_indexer_append_records": [vp, vp, sz],
+        "pk_indexer_flush": [vp],
         "pk_indexer_feed_device": [vp, vp, sz, vp],
         "pk_indexer_feed_host": [vp, vp, sz],
         "pk_indexer_sync": [vp],

@@ -151,19 +151,29 @@ def read_index(index_file: str) -> List[Tuple[int, int]]:
 
 
 def scan_index(path: str) -> List[Tuple[int, int]]:
-    """The same list from the member headers of the file itself (`bgzip -r`)."""
+    """The same list from the member headers of the file itself (`bgzip -r`).  Walks the members with
+    seeks and two small reads each (header: BSIZE; trailer: ISIZE) -- the compressed payload, hundreds
+    of MB for a K >= 15 table, is never read, so a rank that wants 1/N of a table does not pay for all
+    of it."""
     entries, comp_off, raw_off = [], 0, 0
-    with open(path, "rb") as fh:
-        data = memoryview(fh.read())
-    while comp_off < len(data):
-        size = _bgzf_block_size(data, comp_off)
-        if size <= 0 or comp_off + size > len(data):
-            raise OSError(f"{path}: not a whole BGZF block at offset {comp_off}")
-        isize = int.from_bytes(data[comp_off + size - 4:comp_off + size], "little")
-        if isize:
-            entries.append((comp_off, raw_off))
-        comp_off += size
-        raw_off += isize
+    total = os.path.getsize(path)
+    with open(path, "rb", buffering=0) as fh:
+        while comp_off < total:
+            fh.seek(comp_off)
+            head = fh.read(18)
+            size = _bgzf_block_size(head, 0)
+            if size == 0 and len(head) == 18:                    # a longer extra field than the usual 6 bytes
+                xlen = head[10] | (head[11] << 8)
+                fh.seek(comp_off)
+                size = _bgzf_block_size(fh.read(12 + xlen), 0)
+            if size <= 0 or comp_off + size > total:
+                raise OSError(f"{path}: not a whole BGZF block at offset {comp_off}")
+            fh.seek(comp_off + size - 4)
+            isize = int.from_bytes(fh.read(4), "little")
+            if isize:
+                entries.append((comp_off, raw_off))
+            comp_off += size
+            raw_off += isize
     return entries
 
 

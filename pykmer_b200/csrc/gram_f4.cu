@@ -479,9 +479,13 @@ int make_tmap(CUtensorMap *map, const uint32_t *bits, int tile_rows, size_t tile
     const cuuint64_t strides[2] = {128, (cuuint64_t)tile_rows * 128};       // bytes, dimensions 1 and 2
     const cuuint32_t box[3] = {kTileWords, kBoxRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    // L2 promotion no wider than the 128-byte lines: a tile starts at tile_rows * 128 bytes, which is only
+    // 128-byte aligned when the number of samples is odd, and with 256-byte promotion the FIRST line of a
+    // box then came back stale in about half of the launches (N = 253, 255: row 0 of the Gram matrix off
+    // by a few counts; N = 254, 256 never; none / 128-byte promotion never -- 8 launches each, round 2)
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t *>(bits), dims, strides, box,
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return pk_set_error(PK_ERR_CUDA, "gram_f4: cuTensorMapEncodeTiled failed (%d) for %d rows x %zu tiles", (int)r,
                             tile_rows, tiles);

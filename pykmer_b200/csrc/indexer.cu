@@ -1342,6 +1342,7 @@ struct pk_indexer {
     uint64_t *rec_starts = nullptr;
     uint8_t *rec_flags = nullptr;
     size_t nrec = 0, rec_cap = 0;
+    uint64_t last_rec_start = 0;
     uint8_t *stage[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
@@ -2152,7 +2153,63 @@ PK_API int pk_indexer_set_records(pk_indexer *ix, const uint64_t *rec_starts_hos
     }
     PK_CUDA(cudaMemcpy(ix->rec_starts, rec_starts_host, nrec * sizeof(uint64_t), cudaMemcpyHostToDevice));
     ix->nrec = nrec;
+    ix->last_rec_start = rec_starts_host[nrec - 1];
     return PK_OK;
+}
+
+PK_API int pk_indexer_append_records(pk_indexer *ix, const uint64_t *new_starts_host, size_t n) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_append_records: NULL handle");
+    PK_REQUIRE(n == 0 || new_starts_host != nullptr, "pk_indexer_append_records: NULL table");
+    if (n == 0) return PK_OK;
+    for (size_t i = 1; i < n; i++)
+        PK_REQUIRE(new_starts_host[i - 1] <= new_starts_host[i],
+                   "pk_indexer_append_records: offsets must ascend (entry %zu)", i);
+    PK_REQUIRE(ix->nrec == 0 || ix->last_rec_start <= new_starts_host[0],
+               "pk_indexer_append_records: offsets must ascend (first new entry)");
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    const size_t nrec = ix->nrec + n;
+    if (nrec > ix->rec_cap) {
+        PK_CUDA(cudaStreamSynchronize(ix->work_stream));   // kernels may still read the old table
+        const size_t cap = std::max<size_t>(std::max<size_t>(nrec, 2 * ix->rec_cap), 1024);
+        uint64_t *starts = nullptr;
+        uint8_t *flags = nullptr;
+        PK_CUDA(cudaMalloc(&starts, cap * sizeof(uint64_t)));
+        cudaError_t e = cudaMalloc(&flags, cap);
+        if (e == cudaSuccess) e = cudaMemset(flags, 0, cap);
+        if (e == cudaSuccess && ix->nrec) {
+            e = cudaMemcpy(flags, ix->rec_flags, ix->nrec, cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(starts, ix->rec_starts, ix->nrec * sizeof(uint64_t), cudaMemcpyDeviceToDevice);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(starts); cudaFree(flags);
+            return pk_set_error(PK_ERR_CUDA, "pk_indexer_append_records: %s", cudaGetErrorString(e));
+        }
+        cudaFree(ix->rec_starts); cudaFree(ix->rec_flags);
+        ix->rec_starts = starts; ix->rec_flags = flags; ix->rec_cap = cap;
+    }
+    // entries beyond nrec are not read by kernels already queued (they were launched with the old count)
+    PK_CUDA(cudaMemcpyAsync(ix->rec_starts + ix->nrec, new_starts_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                            ix->work_stream));
+    PK_CUDA(cudaStreamSynchronize(ix->work_stream));       // the host array may go away
+    ix->last_rec_start = new_starts_host[n - 1];
+    ix->nrec = nrec;
+    return PK_OK;
+}
+
+PK_API int pk_indexer_flush(pk_indexer *ix) {
+    PK_REQUIRE(ix != nullptr, "pk_indexer_flush: NULL handle");
+    if (ix->mode != PK_MODE_PARTITION || (ix->nseg == 0 && ix->table_valid)) return PK_OK;   // nothing buffered
+    pk_device_guard guard(ix->device);
+    {
+        const int rc = indexer_join(ix);
+        if (rc != PK_OK) return rc;
+    }
+    return indexer_flush(ix, ix->work_stream, false, nullptr);
 }
 
 PK_API int pk_indexer_feed_device(pk_indexer *ix, const uint8_t *seq_dev, size_t n, pk_stream stream) {
@@ -2317,6 +2374,15 @@ PK_API int pk_indexer_prime(pk_indexer *ix, const uint8_t *halo_dev, size_t n, u
         k_update_carry<<<1, 32, 0, st>>>(ix->carry, halo_dev, n, nullptr);
         PK_CUDA(cudaGetLastError());
         ix->launches += 1;
+    }
+    if (ix->mode == PK_MODE_SCAN && ix->nseg == 0) {
+        // a scanner begins a new slice: its per-window counts / cursors start from zero again, while
+        // num_kmers and the record flags keep accumulating (pk_indexer_reset clears those)
+        PK_CUDA(cudaMemsetAsync(ix->seg, 0, (size_t)4 * kMaxSegments * ix->nbuckets * sizeof(uint32_t), st));
+        PK_CUDA(cudaMemsetAsync(ix->cursor, 0, 32, st));
+        ix->p1_seq = nullptr;
+        ix->p1_n = 0;
+        ix->fed = false;
     }
     ix->stream_off = stream_off;
     ix->last_stream = st;

@@ -13,6 +13,7 @@ import torch
 from . import _native as nat
 
 lib = nat.lib
+HAS_SCAN_MODE = True       # sequence-sharded multi-GPU indexing (scan-only handles, peer-mapped buffers)
 
 
 def _stream_ptr(stream: Optional["torch.cuda.Stream"] = None) -> int:
@@ -114,6 +115,18 @@ class Indexer:
         starts = np.ascontiguousarray(starts, dtype=np.uint64)
         nat.check(lib.pk_indexer_set_records(self._h, starts.ctypes.data, starts.size))
         self._nrec = int(starts.size)
+
+    def append_records(self, new_starts) -> None:
+        """Grow the record table by the offsets in new_starts (only these are checked and uploaded)."""
+        new_starts = np.ascontiguousarray(new_starts, dtype=np.uint64)
+        if new_starts.size:
+            nat.check(lib.pk_indexer_append_records(self._h, new_starts.ctypes.data, new_starts.size))
+            self._nrec += int(new_starts.size)
+
+    def flush(self) -> None:
+        """PARTITION mode: count what is buffered into the table now (asynchronous)."""
+        nat.check(lib.pk_indexer_flush(self._h))
+        self._keep.clear()
 
     def feed_device(self, seq: torch.Tensor, stream=None) -> None:
         assert seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()

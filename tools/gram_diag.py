@@ -13,7 +13,7 @@ from pykmer_b200 import device as dev  # noqa: E402
 def main():
     n = int(os.environ.get("DIAG_N", "255"))
     g = torch.Generator(device="cuda").manual_seed(1)
-    for logw in (15, 19, 23):
+    for logw in [int(v) for v in os.environ.get("DIAG_LOGW", "15,19,23").split(",")]:
         words = 1 << logw
         rows = torch.randint(-2 ** 31, 2 ** 31 - 1, (n, words), dtype=torch.int32, device="cuda", generator=g)
         os.environ["PYKMER_B200_GRAM"] = "i8"
@@ -26,7 +26,8 @@ def main():
                 G = dev.gram_tiled(tiled, n, words)
                 d = (G - ref)
                 h = min(n, 128)
-                blocks = {"lolo": d[:h, :h], "lohi": d[:h, h:], "hihi": d[h:, h:]}
+                blocks = {"lolo": d[:h, :h], "lohi": d[:h, h:], "hihi": d[h:, h:], "lolo_row0": d[:1, :h],
+                          "lolo_col0": d[1:h, :1]}
                 msg = ", ".join(f"{k}: {int((v != 0).sum())} cells, max {int(v.abs().max()) if v.numel() else 0}, "
                                 f"sum {int(v.sum())}" for k, v in blocks.items())
                 bad_rows = torch.nonzero((d != 0).sum(dim=1) > n // 4).flatten().tolist()
