@@ -58,6 +58,24 @@ def raise_together(error: Optional[BaseException], src: int = 0, group=None) -> 
         raise RuntimeError(f"rank {src} failed: {box[0]}")
 
 
+def agree(error: Optional[BaseException], group=None) -> None:
+    """EVERY rank reports whether its last stage failed (allocating a 32 GiB shard, feeding, writing its
+    slice of the table ...); if any did, every rank raises -- nobody is left waiting in the next
+    collective for a rank that has gone.  The failing rank re-raises its own exception."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if error is not None:
+            raise error
+        return
+    mine = None if error is None else f"{type(error).__name__}: {error}"
+    every = [None] * dist.get_world_size(group)
+    dist.all_gather_object(every, mine, group=group)
+    if error is not None:
+        raise error
+    for r, msg in enumerate(every):
+        if msg is not None:
+            raise RuntimeError(f"rank {r} failed: {msg}")
+
+
 def shard_range(total: int, rank: int, nranks: int, align: int = ALIGN) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of the k-mer axis owned by `rank`; slices tile [0, total)."""
     def cut(r: int) -> int:
@@ -149,6 +167,22 @@ def balanced_window_owners(per_window: np.ndarray, nranks: int, overhead: int = 
         cuts.append(w)
     cuts.append(nwin)
     return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
+
+
+def analytic_window_owners(nwindows: int, nranks: int, kmers: float, overhead: int = 3_000_000) -> List[Tuple[int, int]]:
+    """balanced_window_owners WITHOUT a planning scan (the CLI sees the stream once): the expected
+    entries per window follow the leading base of a canonical k-mer -- min(fwd, rc) starts with A, C,
+    G, T with probability 7/16, 5/16, 3/16, 1/16 -- spread evenly inside each quarter of the axis."""
+    if nwindows < 4 * 1 or nwindows < nranks:
+        return window_owner_ranges(nwindows, nranks)
+    shares = (7 / 16, 5 / 16, 3 / 16, 1 / 16)
+    per_window = np.zeros(nwindows, dtype=np.float64)
+    edges = [nwindows * q // 4 for q in range(5)]
+    for q in range(4):
+        n = edges[q + 1] - edges[q]
+        if n:
+            per_window[edges[q]:edges[q + 1]] = kmers * shares[q] / n
+    return balanced_window_owners(per_window.astype(np.int64), nranks, overhead=overhead)
 
 
 def balanced_kmer_ranges(per_window: np.ndarray, nranks: int, window_log2: int, total: int,
@@ -356,19 +390,25 @@ def connect_peer_pools(scanner, counter, group=None) -> None:
             scanner.open_peer_pool(d, handle=allh[d].tobytes())
 
 
-def exchange_fused(scanner, counter, seq: torch.Tensor, owners: List[Tuple[int, int]], group=None) -> np.ndarray:
+def exchange_fused(scanner, counter, seq: Optional[torch.Tensor], owners: List[Tuple[int, int]], group=None) -> np.ndarray:
     """One sequence-sharded scan step with the exchange fused into pass 2.  `seq` is this rank's
-    slice (the scanner must have been reset and primed).  Leaves the counter importing what
+    slice (the scanner must have been reset / primed); None or empty = this rank has nothing to scan
+    in this step but still takes part in the collectives.  Leaves the counter importing what
     landed in its buffer; returns all_cnt."""
     rank, nranks = world()
-    scanner.scan_pass1(seq)
-    cnt = scanner.pass1_counts()
-    dev = seq.device
+    have = seq is not None and seq.numel() > 0
+    if have:
+        scanner.scan_pass1(seq)
+        cnt = scanner.pass1_counts()
+    else:
+        cnt = np.zeros(scanner.mode()[1], dtype=np.uint32)
+    dev = _device_for_backend()
     gathered = torch.empty((nranks, cnt.size), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(cnt.astype(np.int64)).to(dev), group=group)
     all_cnt = gathered.cpu().numpy()
     owner_of, dest_off, imp_off, imp_cnt, landed = plan_fused(all_cnt, owners, rank)
-    scanner.scan_pass2_remote(nranks, owner_of, dest_off)          # synchronises: stores have landed
+    if have:
+        scanner.scan_pass2_remote(nranks, owner_of, dest_off)      # synchronises: stores have landed
     dist.barrier(group=group)                                       # ... on every rank
     counter.import_own_pool(imp_off, imp_cnt)
     return all_cnt

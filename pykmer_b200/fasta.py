@@ -201,6 +201,7 @@ class FastaStream:
         self.names: List[str] = []
         self.starts: List[int] = []
         self.lengths: List[int] = []
+        self.bases = 0                          # running sum of self.lengths
         self._pos = 0            # stream offset of the next byte to be emitted
         self._open = False       # a record is open (a header has been seen)
 
@@ -223,6 +224,7 @@ class FastaStream:
             return
         out.append(seq)
         self.lengths[-1] += len(seq)
+        self.bases += len(seq)
         self._pos += len(seq)
 
     # -- chunk processing ------------------------------------------------------------
@@ -390,6 +392,7 @@ class FastaStream:
                 return opos
             n = kept.value
             self.lengths[-1] += n
+            self.bases += n
             self._pos += n
             return opos + n
         # inner white space (maybe a header behind leading blanks) or non-ASCII bytes: this

@@ -80,11 +80,13 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
         cap = chunk_bytes + (chunk_bytes >> 3) + (1 << 17)
         ring = [dev.pinned_empty(cap) for _ in range(2)]
         views = [r.numpy() for r in ring]
+        nrec = 0
         for piece in fs.pieces(buffers=views):
-            ix.set_records(fs.starts)
+            ix.append_records(fs.starts[nrec:])        # only the records opened since the last piece
+            nrec = len(fs.starts)
             ix.feed_host(piece)
             ix.sync()                     # the buffer may be rewritten from here on
-            header.timer.update(sum(fs.lengths))
+            header.timer.update(fs.bases)
         out = out_buf.result()
         hist, st = ix.finalize(table_out=out)      # table windows stream out as they are committed
         flags = ix.record_flags() if fs.starts else np.zeros(0, dtype=np.uint8)
@@ -113,28 +115,36 @@ def create_fasta_index(project_name: str, sample_name: Optional[str], input_file
 
 def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool, device: int,
                                 chunk_bytes: int) -> Header:
-    """The same job inside a torch.distributed group (BASELINE config 5: the
-    256 GiB table of K=19 does not fit one GPU).  Rank g owns the canonical k-mer values
-    [g * 4^K / G, (g+1) * 4^K / G): rank 0 reads the FASTA and broadcasts every cleaned piece of
-    the stream (NCCL: over NVLink), every rank scans it and counts the k-mers of its own range,
-    writes its slice of the .kin at its own offset, and the statistics meet in one small
-    collective (hist / num_kmers / vals_sum / vals_count add up, vals_min / vals_max are min /
-    max, a record is listed if any rank counted one of its k-mers).  Rank 0 writes the JSON."""
+    """The same job inside a torch.distributed group.  Rank 0 reads the FASTA and
+    broadcasts every cleaned piece of the stream (NCCL: over NVLink); the table is partitioned along
+    the canonical k-mer axis, every rank writes its slice of the .kin at its own offset, and the
+    statistics meet in one small collective (hist / num_kmers / vals_sum / vals_count add up,
+    vals_min / vals_max are min / max, a record is listed if any rank counted one of its k-mers).
+    Rank 0 writes the JSON.  Two schemes, the ones bench.py measures:
+
+    * K <= 17 -- sequence slices + fused exchange: rank r scans only slice r of every piece (scan-only
+      handle over the full k-mer range) and stores the bucketed k-mer entries straight into the
+      buffer of the rank that owns their table window (CUDA-IPC peer mapping, pykmer_b200/dist.py
+      exchange_fused); each rank counts its own windows.  Windows are owned in contiguous ranges
+      balanced on the leading-base shares of canonical k-mers (dist.analytic_window_owners).
+    * K >= 19 (BASELINE config 5: the 256 GiB table does not fit one GPU), tables with fewer windows
+      than ranks, and PYKMER_B200_SHARD=kmer -- k-mer ranges, replicated scan: every rank scans the
+      whole piece and counts only the canonical values of its own range (balanced analytically for
+      K >= 19, dist.analytic_kmer_ranges).
+
+    A failure on any rank at any stage (refusing to overwrite, text the reader rejects, a shard that
+    does not fit, a full disk) is agreed on by all ranks (dist.agree) and raised everywhere."""
     import torch
     import torch.distributed as tdist
     from . import device as dev, dist as pdist
+    from . import _native as nat
     from .tools import gen_checksum
 
     rank, world = pdist.world()
-    if header.kmer_len >= 19:
-        # very sparse table, counted DIRECT: balance updates + zero-fill analytically (canonical k-mers
-        # crowd the low values).  The k-mer count is not known before the file is read; every rank
-        # derives the same estimate from the size of the input (about 3.5 bases per compressed byte).
-        size = os.path.getsize(header.input_file_path)
-        packed = header.input_file_path.endswith((".gz", ".bgz"))
-        lo, hi = pdist.analytic_kmer_ranges(header.data_size, world, size * (3.5 if packed else 1.0))[rank]
-    else:
-        lo, hi = pdist.shard_range(header.data_size, rank, world)
+    K, T = header.kmer_len, header.data_size
+    size = os.path.getsize(header.input_file_path)
+    packed = header.input_file_path.endswith((".gz", ".bgz"))
+    est_kmers = size * (3.5 if packed else 1.0)              # about 3.5 bases per compressed byte
     t_start = time.perf_counter()
     error = None
     if rank == 0:
@@ -142,7 +152,7 @@ def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool
             header.init_index_tmp_file(overwrite=overwrite)
         except (ValueError, OSError) as exc:
             error = exc
-    pdist.raise_together(error)
+    pdist.agree(error)
 
     from concurrent.futures import ThreadPoolExecutor
     helpers = ThreadPoolExecutor(max_workers=2)
@@ -154,9 +164,41 @@ def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool
         cap = chunk_bytes + (chunk_bytes >> 3) + (1 << 17)
         ring = [dev.pinned_empty(cap) for _ in range(2)]
         pieces = fs.pieces(buffers=[r.numpy() for r in ring])
-    nrec = 0
+
     with dev.device_scope(device):
-        ix = dev.Indexer(header.kmer_len, device=device, range_lo=lo, range_hi=hi) if hi > lo else None
+        # ---- handles ---------------------------------------------------------------------------
+        scanner, ix, owners, error = None, None, None, None
+        lo, hi = 0, 0
+        try:
+            seq_mode = (K <= 17 and getattr(dev, "HAS_SCAN_MODE", False)
+                        and os.environ.get("PYKMER_B200_SHARD", "sequence") != "kmer")
+            if seq_mode:
+                scanner = dev.Indexer(K, device=device, mode=nat.PK_MODE_SCAN)
+                wl, nwin = scanner.window_log2(), scanner.mode()[1]
+                if nwin < world:                              # fewer table windows than ranks
+                    scanner.close()
+                    scanner, seq_mode = None, False
+            if seq_mode:
+                owners = pdist.analytic_window_owners(nwin, world, est_kmers)
+                lo, hi = owners[rank][0] << wl, min(T, owners[rank][1] << wl)
+                ix = dev.Indexer(K, device=device, range_lo=lo, range_hi=hi, mode=nat.PK_MODE_PARTITION)
+            else:
+                if K >= 19:
+                    # very sparse table, counted DIRECT: balance updates + zero-fill analytically
+                    lo, hi = pdist.analytic_kmer_ranges(T, world, est_kmers)[rank]
+                else:
+                    lo, hi = pdist.shard_range(T, rank, world)
+                ix = dev.Indexer(K, device=device, range_lo=lo, range_hi=hi) if hi > lo else None
+        except Exception as exc:                              # e.g. the shard does not fit this GPU
+            error = exc
+        pdist.agree(error)
+        if seq_mode:
+            pdist.connect_peer_pools(scanner, ix)
+        tagger = scanner if seq_mode else ix                  # the handle that flags records
+
+        # ---- the stream, piece by piece ---------------------------------------------------------
+        nrec, stream_off = 0, 0
+        tail = None                                           # the last 32 bytes fed so far (device)
         while True:
             note, piece, error = [None], None, None
             if rank == 0:
@@ -165,62 +207,100 @@ def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool
                 except (ValueError, OSError) as exc:       # text the reader rejects, damaged .bgz
                     error = exc
                 if piece is not None:
-                    note = [(int(piece.size), [int(v) for v in fs.starts])]
-            pdist.raise_together(error)
+                    new = [int(v) for v in fs.starts[nrec:]]
+                    note = [(int(piece.size), new)]        # only the records opened since the last piece
+                elif error is not None:
+                    note = [("error",)]
             tdist.broadcast_object_list(note, src=0)
+            if note[0] is not None and note[0][0] == "error":
+                pdist.agree(error)
             if note[0] is None:
                 break
-            nbytes, starts = note[0]
-            nrec = len(starts)
-            if nbytes == 0:
-                continue
-            chunk = None
+            nbytes, new_starts = note[0]
+            nrec += len(new_starts)
+            error = None
+            try:
+                if tagger is not None and new_starts:
+                    tagger.append_records(new_starts)
+                if nbytes:
+                    chunk = None
+                    if rank == 0:
+                        chunk = torch.from_numpy(piece)
+                        if tdist.get_backend() == "nccl":
+                            chunk = dev.upload(chunk)
+                    chunk = pdist.broadcast_stream(chunk, nbytes, src=0)
+                    d_chunk = dev.upload(chunk)
+                    if seq_mode:
+                        # rank r scans slice r of the piece; a short piece goes to rank 0 whole
+                        a, b = pdist.slice_bounds(nbytes, rank, world) if nbytes >= 4096 * world else \
+                            ((0, nbytes) if rank == 0 else (nbytes, nbytes))
+                        ext = d_chunk if tail is None else torch.cat((tail, d_chunk))
+                        shift = 0 if tail is None else tail.numel()
+                        halo = ext[max(0, a + shift - 32):a + shift].clone() if a + shift > 0 else None
+                        scanner.prime(halo, stream_off + a)
+                        part = d_chunk[a:b]
+                        pdist.exchange_fused(scanner, ix, part if b > a else None, owners)
+                        ix.flush()                         # count what landed; the buffer is free for the next piece
+                        ix.sync()
+                        scanner.sync()
+                        tail = ext[-32:].clone()
+                        del ext, part
+                    elif ix is not None:
+                        ix.feed_device(d_chunk)
+                        ix.sync()                          # the piece may be dropped from here on
+                    stream_off += nbytes
+                    del d_chunk, chunk
+            except Exception as exc:
+                error = exc
+            pdist.agree(error)
             if rank == 0:
-                chunk = torch.from_numpy(piece)
-                if tdist.get_backend() == "nccl":
-                    chunk = dev.upload(chunk)
-            chunk = pdist.broadcast_stream(chunk, nbytes, src=0)
-            if ix is not None:
-                d_chunk = dev.upload(chunk)
-                ix.set_records(starts)
-                ix.feed_device(d_chunk)
-                ix.sync()                                  # the piece may be dropped from here on
-                del d_chunk
-            if rank == 0:
-                header.timer.update(sum(fs.lengths))
+                header.timer.update(fs.bases)
 
-        if ix is not None:
-            hist, st = ix.finalize()
-            flags = ix.record_flags() if nrec else np.zeros(0, dtype=np.uint8)
-        else:                                              # tiny table, more ranks than slices
-            hist = [0] * 255
-            st = {"num_kmers": 0, "vals_sum": 0, "vals_count": 0, "vals_min": 255, "vals_max": 0}
-            flags = np.zeros(nrec, dtype=np.uint8)
+        # ---- statistics ------------------------------------------------------------------------
+        error = None
+        try:
+            if ix is not None:
+                hist, st = ix.finalize()
+            else:                                              # tiny table, more ranks than slices
+                hist = [0] * 255
+                st = {"num_kmers": 0, "vals_sum": 0, "vals_count": 0, "vals_min": 255, "vals_max": 0}
+            if seq_mode:
+                st["num_kmers"] = scanner.scan_result()
+            flags = tagger.record_flags() if (tagger is not None and nrec) else np.zeros(nrec, dtype=np.uint8)
+        except Exception as exc:
+            error = exc
+        pdist.agree(error)
         hist, st = pdist.reduce_index_stats(hist, st)
         if nrec:
             flags = pdist.reduce_flags(flags)
         t_gpu = time.perf_counter()
 
         # every rank writes its own slice of the table at its own offset of the (sparse) tmp file
-        if ix is not None:
-            step = 256 << 20
-            stage = [dev.pinned_empty(min(hi - lo, step)) for _ in range(2)]
-            fd = os.open(header.index_tmp_file, os.O_WRONLY)
-            try:
-                jobs = [None, None]
-                for i, off in enumerate(range(0, hi - lo, step)):
-                    n = min(step, hi - lo - off)
-                    if jobs[i & 1] is not None:
-                        jobs[i & 1].result()               # its buffer is free again
-                    ix.table_to_host(dst=stage[i & 1], offset=off, nbytes=n)
-                    jobs[i & 1] = helpers.submit(os.pwrite, fd, memoryview(stage[i & 1].numpy())[:n], lo + off)
-                for job in jobs:
-                    if job is not None:
-                        job.result()
-            finally:
-                os.close(fd)
-            ix.close()
-    tdist.barrier()
+        error = None
+        try:
+            if ix is not None:
+                step = 256 << 20
+                stage = [dev.pinned_empty(min(hi - lo, step)) for _ in range(2)]
+                fd = os.open(header.index_tmp_file, os.O_WRONLY)
+                try:
+                    jobs = [None, None]
+                    for i, off in enumerate(range(0, hi - lo, step)):
+                        n = min(step, hi - lo - off)
+                        if jobs[i & 1] is not None:
+                            jobs[i & 1].result()               # its buffer is free again
+                        ix.table_to_host(dst=stage[i & 1], offset=off, nbytes=n)
+                        jobs[i & 1] = helpers.submit(os.pwrite, fd, memoryview(stage[i & 1].numpy())[:n], lo + off)
+                    for job in jobs:
+                        if job is not None:
+                            job.result()
+                finally:
+                    os.close(fd)
+        except Exception as exc:                               # a full disk, a vanished directory
+            error = exc
+        pdist.agree(error)
+        for h in (scanner, ix):
+            if h is not None:
+                h.close()
     t_write = time.perf_counter()
 
     header.num_kmers = st["num_kmers"]
@@ -237,13 +317,14 @@ def _create_fasta_index_sharded(header: Header, input_file: str, overwrite: bool
         except (AssertionError, OSError) as exc:           # tools.py:367-368: no k-mer at all
             error = exc
     helpers.shutdown()
-    pdist.raise_together(error)
+    pdist.agree(error)
     t_end = time.perf_counter()
     header.wall_seconds = {"ingest_and_gpu": t_gpu - t_start, "write_table": t_write - t_gpu,
                            "metadata_and_sha256": t_end - t_write, "total": t_end - t_start}
     if rank == 0:
-        print("  wall ({} ranks): ingest+GPU {ingest_and_gpu:.2f} s, table write {write_table:.2f} s, "
-              "metadata + sha256 {metadata_and_sha256:.2f} s, total {total:.2f} s".format(world, **header.wall_seconds))
+        scheme = "sequence slices + fused exchange" if seq_mode else "k-mer ranges, replicated scan"
+        print("  wall ({} ranks, {}): ingest+GPU {ingest_and_gpu:.2f} s, table write {write_table:.2f} s, "
+              "metadata + sha256 {metadata_and_sha256:.2f} s, total {total:.2f} s".format(world, scheme, **header.wall_seconds))
     return header
 
 

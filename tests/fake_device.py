@@ -51,6 +51,9 @@ class Indexer:
     def set_records(self, starts):
         self.starts = np.asarray(starts, dtype=np.uint64)
 
+    def append_records(self, new_starts):
+        self.starts = np.concatenate((self.starts, np.asarray(new_starts, dtype=np.uint64)))
+
     def feed_device(self, seq, stream=None):
         self.parts.append(seq.numpy().copy())
 

@@ -1052,8 +1052,20 @@ def test_routed_exchange_on_one_gpu(env, K, wlog, nranks):
 # each own half of the canonical k-mer axis.  The host protocol alone is covered on the CPU in
 # tests/test_dist_gloo.py; here the range-restricted handles and the sliced merge do the work.
 
-@pytest.mark.parametrize("case", ["rand200k.fa.bgz.13", "saturating.fa.gz.11", "tiny_mixed.fa.03"])
-def test_indexer_cli_two_ranks_on_one_gpu(env, case, tmp_path):
+@pytest.mark.parametrize("case,nranks,hooks,scheme", [
+    ("rand200k.fa.bgz.13", 2, {}, "sequence slices"),                      # 4 windows of 2^24 entries
+    ("rand200k.fa.bgz.13", 3, {"PYKMER_B200_WINDOW_LOG2": "14"}, "sequence slices"),
+    ("saturating.fa.gz.11", 2, {"PYKMER_B200_WINDOW_LOG2": "12"}, "sequence slices"),
+    ("tiny_mixed.fa.09", 2, {"PYKMER_B200_WINDOW_LOG2": "8"}, "sequence slices"),
+    ("rand200k.fa.bgz.13", 2, {"PYKMER_B200_SHARD": "kmer"}, "k-mer ranges"),
+    ("saturating.fa.gz.11", 2, {}, "k-mer ranges"),                        # one window: fewer than ranks
+    ("tiny_mixed.fa.03", 2, {}, "k-mer ranges"),
+])
+def test_indexer_cli_two_ranks_on_one_gpu(env, case, nranks, hooks, scheme, tmp_path):
+    """torchrun indexer.py as a multi-rank job with the real library (all ranks on cuda:0, gloo
+    rendezvous): K <= 17 with enough table windows runs sequence slices + the fused exchange through
+    CUDA-IPC peer mappings, everything else k-mer ranges with a replicated scan; outputs equal the
+    reference's own files either way."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import multirank
@@ -1062,8 +1074,14 @@ def test_indexer_cli_two_ranks_on_one_gpu(env, case, tmp_path):
     gold = json.load(open(os.path.join(GOLD, "indexer", case + ".json")))
     src = str(tmp_path / fname)
     shutil.copy(os.path.join(GOLD, "inputs", fname), src)
-    res = multirank.run_cli(tmp_path, "indexer", [src, "sample", K], nranks=2, fake=False)
+    os.environ.update(hooks)
+    try:
+        res = multirank.run_cli(tmp_path, "indexer", [src, "sample", K], nranks=nranks, fake=False)
+    finally:
+        for k in hooks:
+            os.environ.pop(k, None)
     assert all(rc == 0 for rc, _ in res), "\n".join(out for _, out in res)
+    assert scheme in res[0][1], res[0][1][-600:]
     kin = f"{src}.{K:02d}.kin"
     meta = json.load(open(kin + ".json"))
     for k, v in gold.items():
