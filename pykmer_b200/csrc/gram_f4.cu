@@ -125,19 +125,24 @@ constexpr int kBoxBytes = kBoxRows * 128;
 
 template <int NP>
 struct F4Cfg {
-    static constexpr int kGroups = 2;
+    // 16 producer warps either way: what bounds a producer is the latency of its own chain (dependent
+    // PRMT / STS / tcgen05.st, then the drain + fence + arrive per stage), so the SM needs four warps per
+    // scheduler to hide it (measured with 8 warps at NP = 128: 105 cycles per instruction with NO MMAs,
+    // profiles/r02e_gram_sweep_v4.txt).  NP = 256: two groups of 256 threads; NP = 128: four of 128 --
+    // every group reaches all the TMEM lanes of its rows; group g of G takes stages g, g + G, ...
+    static constexpr int kGroups = NP == 256 ? 2 : 4;
     static constexpr int kGroupWarps = NP / 32;                       // one thread per staged row
     static constexpr int kGroupThreads = kGroupWarps * 32;
-    static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16 / 8
+    static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16
     static constexpr int kMmaWarp = kProducerWarps;                   // the TMA warp follows it
-    static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576 / 320
-    static constexpr int kKB = NP == 256 ? 4 : 8;                     // K=64 steps per stage
+    static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576
+    static constexpr int kKB = 4;                                     // K=64 steps per stage
     static constexpr int kStageChunks = kKB / 2;                      // 16-byte chunks of a line per stage
-    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 4 / 2
-    static constexpr int kMyStages = kTileStages / kGroups;           // ... of which a group takes every other one
-    static constexpr int kStages = NP == 256 ? 3 : 4;
+    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 4
+    static constexpr int kMyStages = kTileStages / kGroups;           // ... of which a group takes 2 / 1
+    static constexpr int kStages = NP == 256 ? 3 : 6;
     static constexpr int kStepBytes = NP * 32;                        // one K=64 step of all NP rows
-    static constexpr int kStageBytes = kKB * kStepBytes;              // 32 KB either way
+    static constexpr int kStageBytes = kKB * kStepBytes;              // 32 KB / 16 KB
     static constexpr int kRawBytes = NP * 128;                        // one raw tile: 32 KB / 16 KB
     static constexpr int kRawSlots = NP == 256 ? 3 : 4;
     static constexpr int kRawReaders = kGroups * kGroupThreads;       // every producer reads part of every raw tile
@@ -148,7 +153,7 @@ struct F4Cfg {
     static constexpr int kTmemCols = 512;
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + (size_t)kRawSlots * kRawBytes + 512 + 1024;
     static_assert(kACol + kStages * kAStageCols <= kTmemCols, "TMEM budget");
-    static_assert(kStages >= kGroups && kSmem <= 227 * 1024, "ring depth / shared memory budget");
+    static_assert(kTileStages % kGroups == 0 && kStages >= kGroups - 1 && kSmem <= 227 * 1024, "ring depth / shared memory budget");
 };
 
 struct GramArgs {
@@ -400,15 +405,16 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int group = warp / C::kGroupWarps, wg = warp % C::kGroupWarps;
         const int quarter = wg & 3;
+        // four warps share a quarter (NP = 256: lo/hi half x 2 groups; NP = 128: 4 groups): one 32-column chunk each
         const int cstart = NP == 256 ? 32 * ((wg >> 2) + 2 * group) : 32 * group;
-        constexpr int cstep = NP == 256 ? 128 : 64;
+        constexpr int cstep = 128;
         const int r = quarter * 32 + lane;
         const size_t ld = (size_t)g.ld;
         if (NP == 128 && DUAL) {
             // rows 0..63 x columns 0..63 and rows 64..127 x columns 64..127 are the two halves' Gram blocks
             const int i = r & 63;
-            const int c0 = (r >= 64 ? 64 : 0) + cstart;
-            if ((c0 & 63) < g.n_lo) {                                   // warp-uniform
+            const int c0 = (r >= 64 ? 64 : 0) + (cstart & 63);
+            if (group < 2 && (c0 & 63) < g.n_lo) {                      // warp-uniform; two chunks per half
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 if (i < g.n_lo) {
