@@ -90,14 +90,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 a, const ui
 // 2 mask bits -> one byte of two E2M1 nibbles: 00 -> 0x00, 01 -> 0x02, 10 -> 0x20, 11 -> 0x22
 constexpr uint32_t kPairLut = 0x22200200u;
 
-// one bitmask word -> 16 bytes = 32 nibbles (one 16-byte K chunk of a row)
+// one bitmask word -> 16 bytes = 32 nibbles (one 16-byte K chunk of a row).
+// LOP3 / SHF / PRMT all issue on the ALU pipe at one warp instruction per two cycles per scheduler, and the
+// expansion is what the producers spend most of their issue slots on; the three shifts are therefore
+// written as high multiplies (IMAD.HI, FMA pipe): 6 ALU-pipe + 3 FMA-pipe instructions per word instead of 9 + 0.
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, uint32_t pow2_32_minus_n) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2_32_minus_n));
+    return r;
+}
+
 __device__ __forceinline__ uint4 expand_word_f4(uint32_t w) {
-    const uint32_t s0 = w & 0x33333333u, s1 = (w >> 2) & 0x33333333u;       // PRMT selectors 0..3
+    const uint32_t s0 = w & 0x33333333u;                                    // PRMT selectors 0..3
+    const uint32_t s1 = shr_fma(w & 0xCCCCCCCCu, 1u << 30);                  // (w >> 2) & 0x33333333
     uint4 q;
     q.x = __byte_perm(kPairLut, 0u, s0);
-    q.y = __byte_perm(kPairLut, 0u, s0 >> 16);
+    q.y = __byte_perm(kPairLut, 0u, shr_fma(s0, 1u << 16));                  // s0 >> 16
     q.z = __byte_perm(kPairLut, 0u, s1);
-    q.w = __byte_perm(kPairLut, 0u, s1 >> 16);
+    q.w = __byte_perm(kPairLut, 0u, shr_fma(s1, 1u << 16));
     return q;
 }
 
@@ -125,24 +135,23 @@ constexpr int kBoxBytes = kBoxRows * 128;
 
 template <int NP>
 struct F4Cfg {
-    // 16 producer warps either way: what bounds a producer is the latency of its own chain (dependent
-    // PRMT / STS / tcgen05.st, then the drain + fence + arrive per stage), so the SM needs four warps per
-    // scheduler to hide it (measured with 8 warps at NP = 128: 105 cycles per instruction with NO MMAs,
-    // profiles/r02e_gram_sweep_v4.txt).  NP = 256: two groups of 256 threads; NP = 128: four of 128 --
-    // every group reaches all the TMEM lanes of its rows; group g of G takes stages g, g + G, ...
-    static constexpr int kGroups = NP == 256 ? 2 : 4;
+    // Two producer groups of NP threads (each reaches all the TMEM lanes of its rows); group g takes
+    // stages g, g + 2, ...  NP = 128 with FOUR groups and 4-step stages was measured and is slower
+    // (N=128: 110 against 100 cycles per step, profiles/r02g_gram_sweep_np128_four_groups.txt): the stage
+    // handshake, not the number of warps, is what a smaller stage makes worse.
+    static constexpr int kGroups = 2;
     static constexpr int kGroupWarps = NP / 32;                       // one thread per staged row
     static constexpr int kGroupThreads = kGroupWarps * 32;
-    static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16
+    static constexpr int kProducerWarps = kGroups * kGroupWarps;      // 16 / 8
     static constexpr int kMmaWarp = kProducerWarps;                   // the TMA warp follows it
-    static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576
-    static constexpr int kKB = 4;                                     // K=64 steps per stage
+    static constexpr int kThreads = (kProducerWarps + 2) * 32;        // 576 / 320
+    static constexpr int kKB = NP == 256 ? 4 : 8;                     // K=64 steps per stage
     static constexpr int kStageChunks = kKB / 2;                      // 16-byte chunks of a line per stage
-    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 4
+    static constexpr int kTileStages = kTileSteps / kKB;              // stages one tile feeds: 4 / 2
     static constexpr int kMyStages = kTileStages / kGroups;           // ... of which a group takes 2 / 1
-    static constexpr int kStages = NP == 256 ? 3 : 6;
+    static constexpr int kStages = NP == 256 ? 3 : 4;
     static constexpr int kStepBytes = NP * 32;                        // one K=64 step of all NP rows
-    static constexpr int kStageBytes = kKB * kStepBytes;              // 32 KB / 16 KB
+    static constexpr int kStageBytes = kKB * kStepBytes;              // 32 KB either way
     static constexpr int kRawBytes = NP * 128;                        // one raw tile: 32 KB / 16 KB
     static constexpr int kRawSlots = NP == 256 ? 3 : 4;
     static constexpr int kRawReaders = kGroups * kGroupThreads;       // every producer reads part of every raw tile
@@ -405,16 +414,16 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int group = warp / C::kGroupWarps, wg = warp % C::kGroupWarps;
         const int quarter = wg & 3;
-        // four warps share a quarter (NP = 256: lo/hi half x 2 groups; NP = 128: 4 groups): one 32-column chunk each
+        // NP = 256: four warps share a quarter (lo/hi half x 2 groups), one 32-column chunk each; NP = 128: two
         const int cstart = NP == 256 ? 32 * ((wg >> 2) + 2 * group) : 32 * group;
-        constexpr int cstep = 128;
+        constexpr int cstep = NP == 256 ? 128 : 64;
         const int r = quarter * 32 + lane;
         const size_t ld = (size_t)g.ld;
         if (NP == 128 && DUAL) {
             // rows 0..63 x columns 0..63 and rows 64..127 x columns 64..127 are the two halves' Gram blocks
             const int i = r & 63;
-            const int c0 = (r >= 64 ? 64 : 0) + (cstart & 63);
-            if (group < 2 && (c0 & 63) < g.n_lo) {                      // warp-uniform; two chunks per half
+            const int c0 = (r >= 64 ? 64 : 0) + cstart;
+            if ((c0 & 63) < g.n_lo) {                                   // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 if (i < g.n_lo) {

@@ -274,3 +274,88 @@ def test_analytic_kmer_ranges_tile_the_axis_and_balance_the_model():
     lead = np.minimum(fwd, rc) // 4 ** 8
     got = np.bincount(lead, minlength=4) / lead.size
     assert np.allclose(got, [7 / 16, 5 / 16, 3 / 16, 1 / 16], atol=0.01)
+
+
+def test_routed_plan_gives_every_source_its_own_region_in_the_owner():
+    """plan_routed (host logic of the routed exchange): the regions of all (source rank, window)
+    pairs tile each owner's buffer without overlap, leave room for count * (1 + 1/16) + slack, stay
+    below the owner's published-count table, and every rank derives the same layout."""
+    from pykmer_b200 import dist as pdist
+    rng = np.random.default_rng(5)
+    nranks, nwin = 4, 23
+    all_cnt = rng.integers(0, 100_000, size=(nranks, nwin)).astype(np.int64)
+    all_cnt[1, 5:9] = 0
+    owners = pdist.balanced_window_owners(all_cnt.sum(axis=0), nranks, overhead=10)
+    pub = [1 << 30] * nranks
+    plans = [pdist.plan_routed(all_cnt, owners, r, pub, slack=64) for r in range(nranks)]
+    for d, (w0, w1) in enumerate(owners):
+        spans = []
+        for s in range(nranks):
+            owner_of, dest_off, cap, _ = plans[s]
+            assert (owner_of[w0:w1] == d).all()
+            for w in range(w0, w1):
+                assert cap[w] >= all_cnt[s, w] + all_cnt[s, w] // 16 + 64
+                spans.append((int(dest_off[w]), int(dest_off[w]) + int(cap[w])))
+                # the owner's import layout names the same place
+                assert int(plans[d][3][s, w - w0]) == int(dest_off[w])
+        spans.sort()
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert spans[-1][1] <= pub[d]
+    with pytest.raises(ValueError):                                  # an owner whose buffer is too small
+        pdist.plan_routed(all_cnt, owners, 0, [1000] * nranks)
+
+
+def test_analytic_window_owners_follow_the_leading_base_shares():
+    """Window ownership without a planning scan: contiguous, every rank owns a window, and the low
+    windows -- where canonical k-mers crowd (7/16 start with A) -- are shared out more finely."""
+    from pykmer_b200 import dist as pdist
+    for nwin, nranks in ((64, 2), (64, 8), (256, 8), (4, 4), (5, 3), (3, 2)):
+        owners = pdist.analytic_window_owners(nwin, nranks, kmers=7.8e8)
+        assert owners[0][0] == 0 and owners[-1][1] == nwin
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(owners, owners[1:])) and owners[-1][0] < nwin
+    owners = pdist.analytic_window_owners(64, 8, kmers=7.8e8)
+    widths = [b - a for a, b in owners]
+    assert widths[0] < widths[-1] and widths[0] <= min(widths) + 1
+    # expected cost per rank (share of k-mers + 3 M per window) within 25 % of the mean
+    per = np.zeros(64)
+    for q, share in enumerate((7 / 16, 5 / 16, 3 / 16, 1 / 16)):
+        per[16 * q:16 * q + 16] = 7.8e8 * share / 16
+    cost = [per[a:b].sum() + 3e6 * (b - a) for a, b in owners]
+    assert max(cost) < 1.25 * (sum(cost) / len(cost))
+
+
+AGREE_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import torch.distributed as dist
+    from pykmer_b200 import dist as pdist
+    dist.init_process_group("gloo")
+    rank, world = pdist.world()
+    pdist.agree(None)                                   # nobody failed: returns on every rank
+    try:
+        pdist.agree(MemoryError("shard does not fit") if rank == 1 else None)
+    except MemoryError as e:
+        print("own", e)
+    except RuntimeError as e:
+        print("other", e)
+    else:
+        print("no error seen")
+    dist.destroy_process_group()
+""")
+
+
+def test_agree_raises_on_every_rank_when_any_rank_fails(tmp_path):
+    """dist.agree: a failure on a rank other than 0 (an allocation, a write) stops all ranks instead
+    of leaving them in the next collective."""
+    script = tmp_path / "agree_worker.py"
+    script.write_text(AGREE_WORKER % {"root": ROOT})
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1",
+                                       MASTER_PORT=str(port)))
+             for r in range(3)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "own shard does not fit" in outs[1]
+    assert "other rank 1 failed: MemoryError: shard does not fit" in outs[0]
+    assert "other rank 1 failed" in outs[2]
