@@ -90,24 +90,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 a, const ui
 // 2 mask bits -> one byte of two E2M1 nibbles: 00 -> 0x00, 01 -> 0x02, 10 -> 0x20, 11 -> 0x22
 constexpr uint32_t kPairLut = 0x22200200u;
 
-// one bitmask word -> 16 bytes = 32 nibbles (one 16-byte K chunk of a row).
-// LOP3 / SHF / PRMT all issue on the ALU pipe at one warp instruction per two cycles per scheduler, and the
-// expansion is what the producers spend most of their issue slots on; the three shifts are therefore
-// written as high multiplies (IMAD.HI, FMA pipe): 6 ALU-pipe + 3 FMA-pipe instructions per word instead of 9 + 0.
-__device__ __forceinline__ uint32_t shr_fma(uint32_t x, uint32_t pow2_32_minus_n) {
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2_32_minus_n));
-    return r;
-}
-
+// one bitmask word -> 16 bytes = 32 nibbles (one 16-byte K chunk of a row): 2 LOP3 + 3 SHF + 4 PRMT, all on
+// the ALU pipe (one warp instruction per two cycles per scheduler) -- what the producers spend most of
+// their issue slots on.  Moving the three shifts to the FMA pipe as high multiplies (IMAD.HI) was measured
+// and is slower (N=255: 268 against 243 cycles per step, profiles/r02h_gram_sweep_imad_hi_shifts_lost.txt).
 __device__ __forceinline__ uint4 expand_word_f4(uint32_t w) {
-    const uint32_t s0 = w & 0x33333333u;                                    // PRMT selectors 0..3
-    const uint32_t s1 = shr_fma(w & 0xCCCCCCCCu, 1u << 30);                  // (w >> 2) & 0x33333333
+    const uint32_t s0 = w & 0x33333333u, s1 = (w >> 2) & 0x33333333u;       // PRMT selectors 0..3
     uint4 q;
     q.x = __byte_perm(kPairLut, 0u, s0);
-    q.y = __byte_perm(kPairLut, 0u, shr_fma(s0, 1u << 16));                  // s0 >> 16
+    q.y = __byte_perm(kPairLut, 0u, s0 >> 16);
     q.z = __byte_perm(kPairLut, 0u, s1);
-    q.w = __byte_perm(kPairLut, 0u, shr_fma(s1, 1u << 16));
+    q.w = __byte_perm(kPairLut, 0u, s1 >> 16);
     return q;
 }
 
