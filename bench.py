@@ -769,6 +769,10 @@ def bench_indexer(args, K, rank, local_rank, world, steps, warmup, cpu_sample_mb
         roofline["atomic"] = {"op": op, "achieved_per_s": rate, "peak_per_s": peak_ops, "frac": rate / peak_ops,
                               "peak_source": "builder-measured micro-benchmark on this pool's B200 (tools/microbench.cu, "
                                              "microbench2.cu), not a driver-measured peak"}
+        if dom == "scan_count_direct" and K >= 19:
+            roofline["note"] = ("step_frac may exceed 1: SURVEY 8d credits 2 B per table entry (zero-fill + statistics "
+                                "pass); the DIRECT scheme writes the table once and keeps the histogram as transitions, "
+                                "so it never reads the table back")
         if dom == "window_count":
             roofline["note"] = ("frac > 1 against HBM is not a physical HBM fraction: SURVEY 8d credits every counted "
                                 "k-mer with 64 B of DRAM traffic (sector read + write-back), which counting in an "
