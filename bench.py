@@ -533,9 +533,10 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
             if src_host is not None:
                 stage.copy_(src_host, non_blocking=True)
                 src = stage
+            every = None
             if routed and not exact:
                 status.zero_()
-                pdist.exchange_routed(scanner, counter, src, status)
+                every = pdist.exchange_routed(scanner, counter, src, status)
                 buf = None
             else:
                 buf = pdist.exchange_fused(scanner, counter, src, owners)
@@ -544,9 +545,14 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
             counter.reset()
             buf = pdist.exchange_entries(scanner, counter, owners)
         hist, st = counter.finalize(table_out=table_out)
-        st["num_kmers"] = scanner.scan_result()
+        overflow = False
+        if fused and routed and not exact:
+            overflow, _, per_rank_kmers = pdist.read_routed_status(every)
+            st["num_kmers"] = per_rank_kmers[rank]
+        else:
+            st["num_kmers"] = scanner.scan_result()
         hist, st = pdist.reduce_index_stats(hist, st)
-        if routed and not exact and int(status[0].item()):
+        if overflow:
             # a region overflowed somewhere (the stream no longer looks like the planning scan): the
             # step is void, redo it with the exact two-pass protocol -- inside the timed region
             last["exact_redo"] += 1
@@ -583,6 +589,14 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
     scanner.set_profiling(False); counter.set_profiling(False)
     n_k_local = int(all_cnt[:, :, w0:w1].sum())
     table_bytes = hi - lo
+    # every rank's share, for reading the max-over-ranks step time
+    mine = torch.tensor([w1 - w0, n_k_local / 1e6, prof.get("scan_scatter", (0.0, 0))[0],
+                         prof.get("window_count", (0.0, 0))[0], prof.get("window_commit", (0.0, 0))[0]],
+                        dtype=torch.float64, device="cuda")
+    every = torch.empty((world, 5), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(every.view(-1), mine)
+    per_rank = [{"windows": int(a_), "entries_M": round(b_, 1), "scatter_ms": round(c_, 3), "count_ms": round(d_, 3),
+                 "commit_ms": round(e_, 3)} for a_, b_, c_, d_, e_ in every.cpu().tolist()]
     peaks = measured_peaks()
     step_alg = stream.size + 64 * st["num_kmers"] + 2 * T
     # the byte-bound classes only: pass 2 is issue-bound and has no meaning as a fraction of HBM
@@ -623,7 +637,7 @@ def bench_indexer_seqshard(args, K, rank, local_rank, world, steps, warmup):
                    "parallelism": f"sequence x{world} scan, k-mer entries to window owners "
                                   f"({'stores over NVLink fused into the scan, fixed regions, no host round trip' if routed else 'stores over NVLink fused into pass 2' if fused else 'NCCL all-to-all'}), "
                                   f"kmer-window x{world} count",
-                   "exact_redo_steps": last["exact_redo"],
+                   "exact_redo_steps": last["exact_redo"], "per_rank": per_rank,
                    "l2": L2_NOTE, "num_kmers": st["num_kmers"], "vals_sum": st["vals_sum"],
                    "vals_count": st["vals_count"], "vals_max": st["vals_max"],
                    "records_with_kmers": int(flags.sum())},

@@ -179,9 +179,9 @@ int pk_indexer_scan_pass2_remote(pk_indexer *ix, int nranks, const uint32_t *own
  * buffer and its room in entries (plus, per rank, where the owner's published-count table starts:
  * pk_indexer_pub_base, the last 2^18 entries of its buffer).  pk_indexer_scan_routed is then ONE pass:
  * scan, store into the regions (capacity-checked), count num_kmers, flag records, and write the fill
- * counts into every owner's table -- all asynchronous on `stream`; status_dev[0] (device memory of the
- * caller) becomes 1 if a region overflowed, in which case the step must be redone with the exact
- * two-pass protocol above.  After ONE stream-ordered collective over all ranks (e.g. an NCCL
+ * counts into every owner's table -- all asynchronous on `stream`; status_dev (four 32-bit words of the
+ * caller's device memory) receives [0] = 1 if a region overflowed, in which case the step must be redone
+ * with the exact two-pass protocol above, [1], [2] = low / high word of the scanner's num_kmers so far.  After ONE stream-ordered collective over all ranks (e.g. an NCCL
  * all-reduce of the status words: every rank's stores have landed when it completes)
  * pk_indexer_import_published turns the table into the owner's segment tables (layout given once by
  * pk_indexer_set_import_layout: seg_off_host[source][local window], first_window = global index of the

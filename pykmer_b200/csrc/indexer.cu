@@ -457,7 +457,11 @@ __global__ void __launch_bounds__(256) k_publish_fill(const uint32_t *__restrict
         unsigned long long *tmp = reinterpret_cast<unsigned long long *>(ctl + 4);
         *num_kmers += *tmp;
         *tmp = 0ull;
-        if (status) status[0] = ctl[1];                   // 1: a region overflowed, the step must be redone exactly
+        if (status) {
+            status[0] = ctl[1];                           // 1: a region overflowed, the step must be redone exactly
+            status[1] = (uint32_t)*num_kmers;             // this scanner's windows counted since its reset,
+            status[2] = (uint32_t)(*num_kmers >> 32);     // so that no separate read-back is needed
+        }
     }
 }
 

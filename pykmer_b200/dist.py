@@ -458,10 +458,23 @@ def setup_routed(scanner, counter, all_cnt: np.ndarray, owners: List[Tuple[int, 
     counter.set_import_layout(imp_off, owners[rank][0], all_cnt.shape[1])
 
 
-def exchange_routed(scanner, counter, seq: torch.Tensor, status: torch.Tensor, group=None) -> None:
+def exchange_routed(scanner, counter, seq: torch.Tensor, status: torch.Tensor, group=None) -> torch.Tensor:
     """One step of the routed exchange (scanner reset + primed, counter reset; setup_routed done).
-    Nothing here waits on the host.  After counter.finalize() the caller reads status[0]: non-zero =
-    some region overflowed on some rank, redo the step with exchange_fused."""
+    Nothing here waits on the host.  Returns the status words of every rank, (nranks, 4) int32 on the
+    device: after counter.finalize() the caller reads them once -- read_routed_status()."""
     scanner.scan_routed(seq, status)
-    dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)      # overflow flags + "all stores have landed"
+    rank, nranks = world()
+    every = torch.empty((nranks, status.numel()), dtype=status.dtype, device=status.device)
+    # ONE small collective: it carries the overflow flags and every scanner's num_kmers, and it orders
+    # every rank's stores (entries and fill counts) before every owner's count
+    dist.all_gather_into_tensor(every.view(-1), status, group=group)
     counter.import_published()
+    return every
+
+
+def read_routed_status(every: torch.Tensor) -> Tuple[bool, int, List[int]]:
+    """-> (some region overflowed on some rank: redo the step with exchange_fused,
+           num_kmers of the whole job, num_kmers per rank)."""
+    e = every.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    per_rank = [int(lo) | (int(hi) << 32) for lo, hi in zip(e[:, 1], e[:, 2])]
+    return bool(e[:, 0].any()), sum(per_rank), per_rank

@@ -359,3 +359,16 @@ def test_agree_raises_on_every_rank_when_any_rank_fails(tmp_path):
     assert "own shard does not fit" in outs[1]
     assert "other rank 1 failed: MemoryError: shard does not fit" in outs[0]
     assert "other rank 1 failed" in outs[2]
+
+
+def test_read_routed_status_decodes_flags_and_64_bit_counts():
+    """The status words every rank all-gathers in a routed step: overflow flag, num_kmers low / high."""
+    import torch
+    from pykmer_b200 import dist as pdist
+    big = 5_000_000_123                                            # needs the high word
+    rows = [[0, 781_061_717 & 0xFFFFFFFF, 0, 0], [0, big & 0xFFFFFFFF, big >> 32, 0], [0, 0, 0, 0]]
+    every = torch.tensor(rows, dtype=torch.int64).to(torch.int32)  # low words above 2^31 wrap to negative int32
+    overflow, total, per_rank = pdist.read_routed_status(every)
+    assert not overflow and per_rank == [781_061_717, big, 0] and total == 781_061_717 + big
+    rows[2][0] = 1
+    assert pdist.read_routed_status(torch.tensor(rows, dtype=torch.int64).to(torch.int32))[0]

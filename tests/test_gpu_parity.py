@@ -1031,6 +1031,8 @@ def test_routed_exchange_on_one_gpu(env, K, wlog, nranks):
                     ct.finalize()                              # harmless: the step is discarded
                 continue
             assert not flagged.any()
+            # the status words also carry every scanner's num_kmers (no separate read-back in a step)
+            assert pdist.read_routed_status(status)[2] == [sc.scan_result() for sc in scanners]
             tables = []
             for ct in counters:
                 ct.finalize()
