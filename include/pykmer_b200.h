@@ -115,11 +115,31 @@ int pk_indexer_flush(pk_indexer *ix);
  * complete after finalize. */
 int pk_indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5]);
 /* Same, and the whole table (range_hi - range_lo bytes) lands in table_host (pinned
- * memory for full speed).  In PARTITION mode each table window is copied out as soon
- * as it is committed, so the transfer overlaps the counting of the later windows. */
+ * memory for full speed).  In PARTITION mode each table window leaves as soon as it is
+ * committed -- packed, see below -- so the transfer overlaps the counting of the later windows. */
 int pk_indexer_finalize_to_host(pk_indexer *ix, int64_t hist_host[255], uint64_t stats_host[5],
                                 uint8_t *table_host);
+/* what the last pk_indexer_finalize_to_host moved: {bytes device-to-host, windows sent packed, windows sent
+ * as they are, host threads that rebuilt the packed ones} */
+int pk_indexer_transfer_stats(pk_indexer *ix, uint64_t stats_host[4]);
 int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec);
+
+/* The packed form in which pk_indexer_finalize_to_host moves a finished table over PCIe (the .kin bytes of
+ * tools.py:196,240-243 are mostly zeros: 25 % of the entries are in use at K=15, 3 % at K=17), per slice of
+ * n entries, n a multiple of 1024:
+ *   bitmap[n / 64]       bit i of word j <=> entry 64 j + i is non-zero
+ *   chunk_off[n / 1024]  where the non-zero bytes of entries [1024 c, +1024) start in nz, in 16-byte units
+ *   nz                   those bytes in entry order, every chunk padded to a multiple of 16 (chunks in any order)
+ * finalize_to_host packs every window behind its last kernel, copies only the packed form into pinned slots
+ * and rebuilds the bytes in table_host on the host's cores while later windows are counted; dense windows
+ * (packed size above 5/8 of the bytes), and windows whose slot is still being rebuilt, are copied as they
+ * are.  PYKMER_B200_PACKED_D2H=0 turns the packed form off, PYKMER_B200_UNPACK_THREADS sets the team size.
+ * The two halves on their own: */
+int pk_table_pack_device(const uint8_t *table_dev, size_t n, uint64_t *bitmap_dev, uint32_t *chunk_off_dev,
+                         uint8_t *nz_dev /* room for n + n / 64 bytes */, uint32_t *nz_units_host, pk_stream stream);
+/* host only (no CUDA call): dst[0, n) from the packed form; offsets are checked against nz_bytes */
+int pk_table_unpack(const uint64_t *bitmap, const uint32_t *chunk_off, const uint8_t *nz, size_t nz_bytes,
+                    size_t n, uint8_t *dst, int threads);
 
 /* Device view of the table (valid after finalize), and a copy to host memory. */
 int pk_indexer_table_device(pk_indexer *ix, const uint8_t **table_dev, size_t *bytes);

@@ -295,3 +295,34 @@ def matrix_from_gram(G: np.ndarray) -> np.ndarray:
     m[:, :, 1] = d[None, :]
     m[:, :, 2] = G.astype(np.uint64)
     return m
+
+
+def pack_table(table: np.ndarray):
+    """The packed form of a table slice (include/pykmer_b200.h: pk_table_pack_device) restated with NumPy,
+    chunks in ascending order: -> (bitmap uint64[n/64], chunk_off uint32[n/1024], nz uint8[]).  The device
+    may lay the chunks out in any order, so compare through unpack_table, not array by array."""
+    t = np.ascontiguousarray(table, dtype=np.uint8)
+    assert t.size % 1024 == 0
+    present = t != 0
+    bitmap = np.packbits(present, bitorder="little").view(np.uint64)
+    per_chunk = present.reshape(-1, 1024).sum(axis=1).astype(np.int64)
+    units = (per_chunk + 15) // 16
+    chunk_off = np.concatenate(([0], np.cumsum(units)[:-1])).astype(np.uint32)
+    nz = np.zeros(int(units.sum()) * 16, dtype=np.uint8)
+    vals = t[present]
+    starts = np.concatenate(([0], np.cumsum(per_chunk)[:-1]))
+    # byte k of chunk c goes to chunk_off[c] * 16 + k
+    idx = np.repeat(chunk_off.astype(np.int64) * 16 - starts, per_chunk) + np.arange(vals.size)
+    nz[idx] = vals
+    return bitmap, chunk_off, nz
+
+
+def unpack_table(bitmap: np.ndarray, chunk_off: np.ndarray, nz: np.ndarray, n: int) -> np.ndarray:
+    """Literal inverse of pack_table for chunks laid out in any order."""
+    present = np.unpackbits(np.ascontiguousarray(bitmap).view(np.uint8), bitorder="little")[:n].astype(bool)
+    per_chunk = present.reshape(-1, 1024).sum(axis=1).astype(np.int64)
+    starts = np.concatenate(([0], np.cumsum(per_chunk)[:-1]))
+    idx = np.repeat(chunk_off.astype(np.int64) * 16 - starts, per_chunk) + np.arange(int(per_chunk.sum()))
+    out = np.zeros(n, dtype=np.uint8)
+    out[present] = nz[idx]
+    return out

@@ -21,7 +21,7 @@ SYMBOLS = (
     "pk_indexer_create", "pk_indexer_destroy", "pk_indexer_reset", "pk_indexer_set_records",
     "pk_indexer_append_records", "pk_indexer_flush",
     "pk_indexer_feed_device", "pk_indexer_feed_host", "pk_indexer_sync", "pk_indexer_finalize",
-    "pk_indexer_finalize_to_host",
+    "pk_indexer_finalize_to_host", "pk_indexer_transfer_stats",
     "pk_indexer_record_flags", "pk_indexer_table_device", "pk_indexer_table_to_host",
     "pk_indexer_launch_count", "pk_indexer_mode", "pk_indexer_window_log2", "pk_indexer_set_profiling", "pk_indexer_profile",
     "pk_indexer_prime", "pk_indexer_scan_result", "pk_indexer_export_segments",
@@ -29,7 +29,7 @@ SYMBOLS = (
     "pk_indexer_scan_pass1", "pk_indexer_pass1_counts", "pk_indexer_scan_pass2_remote",
     "pk_indexer_pub_base", "pk_indexer_set_route", "pk_indexer_scan_routed", "pk_indexer_set_import_layout",
     "pk_indexer_import_published",
-    "pk_table_stats_device",
+    "pk_table_stats_device", "pk_table_pack_device", "pk_table_unpack",
     "pk_threshold_pack_device", "pk_gram_device", "pk_threshold_pack_tiled_device", "pk_gram_tiled_device", "pk_gram_tiled_exact", "pk_pair_counts_device", "pk_merge_host",
     "pk_synth_table_device", "pk_bgzf_inflate", "pk_fasta_clean", "pk_bgzf_deflate", "pk_fasta_find_headers",
 )
@@ -72,6 +72,7 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_sync": [vp],
         "pk_indexer_finalize": [vp, vp, vp],
         "pk_indexer_finalize_to_host": [vp, vp, vp, vp],
+        "pk_indexer_transfer_stats": [vp, vp],
         "pk_indexer_record_flags": [vp, vp, sz],
         "pk_indexer_table_device": [vp, c.POINTER(vp), c.POINTER(sz)],
         "pk_indexer_table_to_host": [vp, vp, sz, sz],
@@ -96,6 +97,8 @@ def _load() -> ctypes.CDLL:
         "pk_indexer_set_import_layout": [vp, c.c_uint32, vp, c.c_uint32, c.c_uint32],
         "pk_indexer_import_published": [vp, vp],
         "pk_table_stats_device": [vp, sz, vp, vp, vp],
+        "pk_table_pack_device": [vp, sz, vp, vp, vp, c.POINTER(c.c_uint32), vp],
+        "pk_table_unpack": [vp, vp, vp, sz, sz, vp, i32],
         "pk_threshold_pack_device": [vp, sz, i32, i32, vp, vp],
         "pk_gram_device": [vp, i32, sz, sz, vp, i32, vp],
         "pk_threshold_pack_tiled_device": [vp, sz, sz, i32, i32, vp, i32, i32, vp],

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpykmer_b200.so")
-SOURCES = ["api.cu", "indexer.cu", "merger.cu", "gram_i8.cu", "gram_f4.cu", "ingest.cpp"]
+SOURCES = ["api.cu", "indexer.cu", "merger.cu", "gram_i8.cu", "gram_f4.cu", "ingest.cpp", "unpack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math", "-shared",

@@ -158,6 +158,13 @@ struct F4Cfg {
     static_assert(kTileStages % kGroups == 0 && kStages >= kGroups - 1 && kSmem <= 227 * 1024, "ring depth / shared memory budget");
 };
 
+// 32 arrivals of one warp on one mbarrier word serialise like shared-memory atomics on one address; one
+// arrival per warp (every lane fences, __syncwarp, lane 0 arrives) removes that.  Measured per kernel form
+// (profiles/r02l_gram_sweep_arrivals.txt, K=13): 129..256 rows 3.85 -> 3.50 ms with both barriers per warp
+// (one of the two alone: 3.67 / 3.84); <= 128 rows 1.42 per thread against 1.54 per warp -- there the
+// __syncwarp costs more than the arrivals, the stages are half as long.
+__host__ __device__ constexpr bool arrive_per_warp(int np) { return np > 128; }
+
 struct GramArgs {
     CUtensorMap tmap;          // tiled masks as a 3-D tensor {32 words, tile_rows, tiles}, box {32, 64, 1}, SWIZZLE_128B
     size_t tiles;              // tiles per row (words / 32)
@@ -208,6 +215,8 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // one mbarrier arrival per producer WARP (after __syncwarp) or one per thread, see arrive_per_warp()
+    constexpr bool warp_full = arrive_per_warp(NP), warp_raw = arrive_per_warp(NP);
 
     // this CTA's tiles [t0, t1); DUAL: first half [t0, tm) on lanes 0..63, second half [tm, t1) on 64..127
     const size_t t0 = min(g.tiles, (size_t)blockIdx.x * g.tiles_per_cta);
@@ -218,12 +227,12 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; s++) {
-            mbar_init(smem_u32(&full_bar[s]), C::kGroupThreads);
+            mbar_init(smem_u32(&full_bar[s]), warp_full ? C::kGroupWarps : C::kGroupThreads);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         for (int s = 0; s < C::kRawSlots; s++) {
             mbar_init(smem_u32(&raw_full[s]), 1);
-            mbar_init(smem_u32(&raw_empty[s]), C::kRawReaders);
+            mbar_init(smem_u32(&raw_empty[s]), warp_raw ? C::kRawReaders / 32 : C::kRawReaders);
         }
         mbar_init(smem_u32(done_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -294,7 +303,14 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
             if (to_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(smem_u32(&full_bar[s]));
+            // every lane has drained and fenced its own stores; ONE arrival per warp -- 32 arrivals on one
+            // mbarrier word serialise like any shared-memory atomic on one address
+            if (warp_full) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+            } else {
+                mbar_arrive(smem_u32(&full_bar[s]));
+            }
         };
 
         constexpr int kMyChunks = C::kMyStages * C::kStageChunks;           // chunks of a line this thread expands: 4
@@ -316,7 +332,12 @@ __global__ void __launch_bounds__(F4Cfg<NP>::kThreads, 1) k_gram_f4(const __grid
             // for outstanding loads by itself (SASS: LD ... SYNCS.ARRIVE back to back), and a TMA write that
             // overtakes them showed up as one stale row in a few launches out of ten (round 2, pass c).
             __threadfence_block();
-            mbar_arrive(smem_u32(&raw_empty[rs]));
+            if (warp_raw) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&raw_empty[rs]));
+            } else {
+                mbar_arrive(smem_u32(&raw_empty[rs]));
+            }
 #pragma unroll
             for (int m = 0; m < C::kMyStages; m++)
                 produce_stage(t * C::kTileStages + (size_t)(m * C::kGroups + group), &ch[m * C::kStageChunks]);

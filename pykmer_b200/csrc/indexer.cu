@@ -29,7 +29,9 @@
 //   k_table_stats              stand-alone 256-bin histogram pass (DIRECT mode).
 //   k_update_carry             keeps the last 32 stream bytes for the next feed.
 #include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
 #include <type_traits>
 #include <vector>
 #include <stdlib.h>
@@ -43,6 +45,7 @@ namespace {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr size_t kStageBytes = 32u << 20;   // pinned-copy chunk of feed_host
+constexpr size_t kPackChunk = 1024;          // entries per chunk of a packed table slice (unpack.cpp: kChunk)
 constexpr int kCarry = 32;                  // bytes of stream tail kept between feeds
 constexpr int kMaxBuckets = 16384;          // windows per handle in PARTITION / SCAN mode
 constexpr int kMaxSegments = 128;           // feeds buffered between two flushes
@@ -745,6 +748,68 @@ __global__ void __launch_bounds__(256) k_reduce_bins(const unsigned long long *_
     bins[threadIdx.x] = s;
 }
 
+// ------------------------------------------------------------------------------ packed transfer
+// A finished table slice on its way to the host (pk_indexer_finalize_to_host): one bit per entry, the
+// non-zero bytes in entry order, and per chunk of 1024 entries where its bytes start -- the format
+// csrc/unpack.cpp rebuilds on the host's cores.  One warp per chunk: two coalesced 512-byte loads, the
+// lane's non-zero bytes compacted into shared memory at the lane's rank (two warp scans), one atomicAdd
+// reserves the chunk's room (16-byte units, so the copy out is whole uint4s; chunks land in any order),
+// 128 bytes of bitmap.  Reads 1 B per entry (the slice was just written: mostly L2 hits), writes
+// 1/8 + fill B per entry.
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w) {     // bit i <=> byte i of w is not zero
+    return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ uint32_t nonzero16(const uint4 v) {
+    return nonzero_nibble(v.x) | (nonzero_nibble(v.y) << 4) | (nonzero_nibble(v.z) << 8) | (nonzero_nibble(v.w) << 12);
+}
+__device__ __forceinline__ void compact16(const uint4 v, uint8_t *dst) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t x = (w[k] >> (8 * b)) & 0xFFu;
+            if (x) *dst++ = (uint8_t)x;
+        }
+}
+
+__global__ void __launch_bounds__(256) k_table_pack(const uint8_t *__restrict__ table, size_t nchunks,
+                                                    uint16_t *__restrict__ bitmap16, uint32_t *__restrict__ chunk_off,
+                                                    uint8_t *__restrict__ nz, uint32_t *__restrict__ cursor) {
+    __shared__ __align__(16) uint8_t stage[8][kPackChunk + 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *sb = stage[warp];
+    for (size_t c = (size_t)blockIdx.x * 8 + warp; c < nchunks; c += (size_t)gridDim.x * 8) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(table + c * kPackChunk);
+        const uint4 a = __ldcs(src + lane), b = __ldcs(src + 32 + lane);
+        const uint32_t ma = nonzero16(a), mb = nonzero16(b);
+        const uint32_t ca = __popc(ma), cb = __popc(mb);
+        uint32_t pa = ca, pb = cb;                          // inclusive scans over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, pa, d), ub = __shfl_up_sync(0xFFFFFFFFu, pb, d);
+            if (lane >= d) { pa += ua; pb += ub; }
+        }
+        const uint32_t tot_a = __shfl_sync(0xFFFFFFFFu, pa, 31), total = tot_a + __shfl_sync(0xFFFFFFFFu, pb, 31);
+        if (ca) compact16(a, sb + (pa - ca));
+        if (cb) compact16(b, sb + tot_a + (pb - cb));
+        const uint32_t units = (total + 15u) >> 4;
+        if (lane < 16 && total + lane < units * 16u) sb[total + lane] = 0;      // padding of the last unit
+        uint32_t off = 0;
+        if (lane == 0) {
+            off = atomicAdd(cursor, units);
+            chunk_off[c] = off;
+        }
+        off = __shfl_sync(0xFFFFFFFFu, off, 0);
+        __syncwarp();
+        uint4 *dst = reinterpret_cast<uint4 *>(nz) + off;
+        for (uint32_t i = lane; i < units; i += 32) dst[i] = reinterpret_cast<const uint4 *>(sb)[i];
+        bitmap16[c * (kPackChunk / 16) + lane] = (uint16_t)ma;
+        bitmap16[c * (kPackChunk / 16) + 32 + lane] = (uint16_t)mb;
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------ byte windows
 // Sparse tables (K >= 17: a few k-mers per hundred entries) pay for the 32-bit counters twice:
 // a window covers only 2^24 entries, and every commit reads 4 bytes to write one.  Here the
@@ -1390,6 +1455,8 @@ struct pk_indexer {
     OvfTable ovf = {nullptr, nullptr, nullptr, nullptr, 0};
     bool sub_smem_set = false;
     cudaEvent_t committed[2] = {nullptr, nullptr};
+    struct TableShipper *shipper = nullptr;    // packed device-to-host transfer of finished table slices
+    uint64_t xfer[4] = {0, 0, 0, 0};           // last finalize_to_host: bytes device-to-host, packed / raw slices, unpack threads
     int nseg = 0;
     size_t l2_persist_bytes = 0;               // persisting-L2 carve-out granted for `scratch`
     bool table_valid = false;                  // every window has been written since reset
@@ -1467,6 +1534,254 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
     return 1;
 }
 
+// ---- packed device-to-host transfer of a finished table (pk_indexer_finalize_to_host) ---------------
+// The table is the largest thing an indexing job moves over PCIe and it is mostly zeros, so every
+// finished slice (a window) is packed on the device (k_table_pack), only bitmap + chunk offsets +
+// non-zero bytes cross the bus into a pinned slot, and a team of host threads rebuilds the bytes in the
+// caller's buffer (unpack.cpp) while the next windows are still being counted and copied.  The caller's
+// thread runs kLag windows behind the launches: it waits for a window's packed size (4 bytes the pack
+// kernel's cursor sends home), queues the copies, and hands the slot to the team.  A slice goes RAW --
+// the plain cudaMemcpyAsync of the table bytes, as before -- when it is dense (packed size above
+// 5/8 of the bytes), when it is no whole number of chunks, or when its slot is still being unpacked:
+// the host's cores and the bus then share the work in whatever ratio keeps both busy.
+void pk_unpack_chunks(const uint64_t *bitmap, const uint32_t *chunk_off, const uint8_t *nz, size_t nz_readable,
+                      uint8_t *dst, size_t c0, size_t c1);          // unpack.cpp
+
+struct TableShipper {
+    static constexpr int kSlots = 4, kLag = 2;
+    struct Job {
+        int slot = 0;
+        size_t n = 0, nz_bytes = 0;
+        uint8_t *dst = nullptr;
+        std::atomic<int> state{0};              // 0 = nobody waits for the copy yet, 1 = one thread does, 2 = arrived
+        std::atomic<size_t> next{0}, done{0};   // chunks handed out / rebuilt
+    };
+    int device = 0;
+    size_t max_n = 0;                           // entries of the largest slice
+    size_t off_bytes = 0, nz_at = 0, nz_cap = 0, dev_bytes = 0, host_bytes = 0;
+    uint8_t *d_buf[kSlots] = {nullptr}, *h_buf[kSlots] = {nullptr};
+    uint32_t *d_cur = nullptr, *h_cur = nullptr;   // device cursors (one per slot); pinned: one word per slice
+    size_t h_cur_cap = 0;
+    cudaEvent_t packed[kSlots] = {nullptr}, copied[kSlots] = {nullptr};
+    bool slot_copied[kSlots] = {false};         // copied[slot] has been recorded in this run
+    std::atomic<int> slot_busy[kSlots];
+    // one run = one flush
+    std::vector<Job> jobs;
+    std::atomic<size_t> njobs{0}, jobs_done{0};
+    std::atomic<bool> closing{false};
+    std::atomic<int> failed{0};
+    std::vector<std::thread> team;
+    struct Pending { size_t idx; int slot; const uint8_t *src; uint8_t *dst; size_t n; bool packable; };
+    std::vector<Pending> pending;
+    size_t issued = 0, serviced = 0, packed_slices = 0, raw_slices = 0, d2h_bytes = 0;
+    int team_size = 0;
+    bool running = false;
+
+    static int threads() {
+        if (const char *v = getenv("PYKMER_B200_UNPACK_THREADS")) return std::max(1, atoi(v));
+        int hc = (int)std::thread::hardware_concurrency(), local = 1;
+        if (const char *v = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(v));
+        return std::max(1, std::min(hc / local - 1, 32));     // the caller's thread keeps a core
+    }
+
+    int ensure(int device_, size_t max_n_, size_t nslices) {
+        if (max_n_ > max_n) {
+            release_buffers();
+            device = device_;
+            max_n = max_n_;
+            const size_t bm = max_n / 8;
+            off_bytes = max_n / kPackChunk * sizeof(uint32_t);
+            nz_at = (bm + off_bytes + 255) & ~(size_t)255;
+            dev_bytes = nz_at + max_n + max_n / kPackChunk * 16 + 256;   // every chunk may pad up to 15 bytes
+            nz_cap = max_n / 2 + 4096;                                    // denser slices go raw
+            host_bytes = nz_at + nz_cap + 256;
+            for (int i = 0; i < kSlots; i++) {
+                PK_CUDA(cudaMalloc(&d_buf[i], dev_bytes));
+                PK_CUDA(cudaHostAlloc(&h_buf[i], host_bytes, cudaHostAllocDefault));
+                PK_CUDA(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+                PK_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            }
+            PK_CUDA(cudaMalloc(&d_cur, kSlots * sizeof(uint32_t)));
+        }
+        if (nslices > h_cur_cap) {
+            if (h_cur) cudaFreeHost(h_cur);
+            h_cur = nullptr;
+            PK_CUDA(cudaHostAlloc(&h_cur, nslices * sizeof(uint32_t), cudaHostAllocDefault));
+            h_cur_cap = nslices;
+        }
+        return PK_OK;
+    }
+
+    void release_buffers() {
+        for (int i = 0; i < kSlots; i++) {
+            if (d_buf[i]) cudaFree(d_buf[i]);
+            if (h_buf[i]) cudaFreeHost(h_buf[i]);
+            if (packed[i]) cudaEventDestroy(packed[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            d_buf[i] = h_buf[i] = nullptr;
+            packed[i] = copied[i] = nullptr;
+        }
+        if (d_cur) cudaFree(d_cur);
+        d_cur = nullptr;
+        max_n = 0;
+    }
+
+    ~TableShipper() {
+        stop_team();
+        release_buffers();
+        if (h_cur) cudaFreeHost(h_cur);
+    }
+
+    void team_main() {
+        cudaSetDevice(device);
+        for (size_t j = 0;; j++) {
+            while (j >= njobs.load(std::memory_order_acquire)) {
+                if (closing.load(std::memory_order_acquire) && j >= njobs.load(std::memory_order_acquire)) return;
+                std::this_thread::yield();
+            }
+            Job &job = jobs[j];
+            int expect = 0;
+            if (job.state.compare_exchange_strong(expect, 1)) {          // one thread waits for the copy
+                if (cudaEventSynchronize(copied[job.slot]) != cudaSuccess) failed.store(1);
+                job.state.store(2, std::memory_order_release);
+            } else {
+                while (job.state.load(std::memory_order_acquire) != 2) std::this_thread::yield();
+            }
+            const size_t nchunks = job.n / kPackChunk, grain = 128;      // 128 KiB of table per grab
+            const uint8_t *h = h_buf[job.slot];
+            for (;;) {
+                const size_t c0 = job.next.fetch_add(grain);
+                if (c0 >= nchunks) break;
+                const size_t c1 = std::min(nchunks, c0 + grain);
+                if (!failed.load(std::memory_order_relaxed))
+                    pk_unpack_chunks(reinterpret_cast<const uint64_t *>(h), reinterpret_cast<const uint32_t *>(h + max_n / 8),
+                                     h + nz_at, job.nz_bytes + 64, job.dst, c0, c1);
+                if (job.done.fetch_add(c1 - c0) + (c1 - c0) == nchunks) {  // last piece: the slot is free again
+                    slot_busy[job.slot].store(0, std::memory_order_release);
+                    jobs_done.fetch_add(1, std::memory_order_release);
+                }
+            }
+        }
+    }
+
+    void begin(size_t nslices) {
+        jobs = std::vector<Job>(nslices);
+        njobs.store(0); jobs_done.store(0); closing.store(false); failed.store(0);
+        for (int i = 0; i < kSlots; i++) { slot_busy[i].store(0); slot_copied[i] = false; }
+        pending.clear();
+        issued = serviced = packed_slices = raw_slices = d2h_bytes = 0;
+        const int nt = team_size = threads();
+        for (int t = 0; t < nt; t++) team.emplace_back([this] { team_main(); });
+        running = true;
+    }
+
+    void stop_team() {
+        closing.store(true, std::memory_order_release);
+        for (auto &t : team) t.join();
+        team.clear();
+    }
+
+    // after the slice's last kernel has been queued on st: pack it behind that kernel
+    int pack(const uint8_t *slice_dev, uint8_t *dst_host, size_t n, cudaStream_t st, int sm_count) {
+        const size_t idx = issued++;
+        const int slot = (int)(idx % kSlots);
+        const bool packable = n % kPackChunk == 0 && n <= max_n && n >= kPackChunk;
+        if (packable) {
+            if (slot_copied[slot]) PK_CUDA(cudaStreamWaitEvent(st, copied[slot], 0));   // its last copy has left the slot
+            PK_CUDA(cudaMemsetAsync(d_cur + slot, 0, sizeof(uint32_t), st));
+            const size_t nchunks = n / kPackChunk;
+            const int grid = (int)std::min<size_t>((size_t)sm_count * 8, (nchunks + 7) / 8);
+            k_table_pack<<<grid, 256, 0, st>>>(slice_dev, nchunks, reinterpret_cast<uint16_t *>(d_buf[slot]),
+                                                 reinterpret_cast<uint32_t *>(d_buf[slot] + max_n / 8), d_buf[slot] + nz_at,
+                                                 d_cur + slot);
+            PK_CUDA(cudaGetLastError());
+            PK_CUDA(cudaMemcpyAsync(h_cur + idx, d_cur + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        } else {
+            h_cur[idx] = 0xFFFFFFFFu;
+        }
+        PK_CUDA(cudaEventRecord(packed[slot], st));
+        pending.push_back({idx, slot, slice_dev, dst_host, n, packable});
+        return PK_OK;
+    }
+
+    // queue the copies of every slice issued at least `lag` slices ago
+    int service(cudaStream_t copy_stream, size_t lag) {
+        while (serviced + lag < issued) {
+            const Pending p = pending[serviced++];
+            const bool packable = p.packable;
+            PK_CUDA(cudaEventSynchronize(packed[p.slot]));
+            const size_t nz_bytes = packable ? (size_t)h_cur[p.idx] * 16 : 0;
+            const size_t packed_bytes = p.n / 8 + p.n / kPackChunk * sizeof(uint32_t) + nz_bytes;
+            const bool go_packed = packable && nz_bytes <= nz_cap && packed_bytes * 8 <= p.n * 5 &&
+                                   slot_busy[p.slot].load(std::memory_order_acquire) == 0;
+            PK_CUDA(cudaStreamWaitEvent(copy_stream, packed[p.slot], 0));
+            if (!go_packed) {
+                PK_CUDA(cudaMemcpyAsync(p.dst, p.src, p.n, cudaMemcpyDeviceToHost, copy_stream));
+                raw_slices++;
+                d2h_bytes += p.n + (packable ? sizeof(uint32_t) : 0);
+                continue;
+            }
+            slot_busy[p.slot].store(1, std::memory_order_release);
+            uint8_t *h = h_buf[p.slot];
+            const uint8_t *d = d_buf[p.slot];
+            PK_CUDA(cudaMemcpyAsync(h, d, p.n / 8, cudaMemcpyDeviceToHost, copy_stream));
+            PK_CUDA(cudaMemcpyAsync(h + max_n / 8, d + max_n / 8, p.n / kPackChunk * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, copy_stream));
+            if (nz_bytes) PK_CUDA(cudaMemcpyAsync(h + nz_at, d + nz_at, nz_bytes, cudaMemcpyDeviceToHost, copy_stream));
+            PK_CUDA(cudaEventRecord(copied[p.slot], copy_stream));
+            slot_copied[p.slot] = true;
+            Job &job = jobs[njobs.load(std::memory_order_relaxed)];
+            job.slot = p.slot; job.n = p.n; job.nz_bytes = nz_bytes; job.dst = p.dst;
+            njobs.fetch_add(1, std::memory_order_release);
+            packed_slices++;
+            d2h_bytes += packed_bytes + sizeof(uint32_t);
+        }
+        return PK_OK;
+    }
+
+    // drain: the remaining copies, then every slot rebuilt (raw copies are joined by the caller's stream sync)
+    int finish(cudaStream_t copy_stream) {
+        running = false;
+        const int rc = service(copy_stream, 0);
+        if (rc == PK_OK)
+            while (jobs_done.load(std::memory_order_acquire) < njobs.load(std::memory_order_acquire)) std::this_thread::yield();
+        stop_team();
+        pending.clear();
+        if (rc != PK_OK) return rc;
+        if (failed.load()) return pk_set_error(PK_ERR_CUDA, "packed table transfer: waiting for a copy failed");
+        return PK_OK;
+    }
+};
+
+// start a packed transfer for this flush, or return with ix->shipper idle (plain copies)
+static int shipper_begin(pk_indexer *ix, uint8_t *table_host, size_t slice_entries, size_t nslices) {
+    if (!table_host || ix->table_bytes < ((size_t)1 << 22)) return PK_OK;
+    if (const char *v = getenv("PYKMER_B200_PACKED_D2H"))
+        if (atoi(v) == 0) return PK_OK;                     // test hook: the plain copy of every window
+    if (!ix->shipper) ix->shipper = new (std::nothrow) TableShipper();
+    if (!ix->shipper) return pk_set_error(PK_ERR_NOMEM, "packed table transfer: out of host memory");
+    const int rc = ix->shipper->ensure(ix->device, std::min(slice_entries, ix->table_bytes), nslices);
+    if (rc != PK_OK) return rc;
+    ix->shipper->begin(nslices);
+    return PK_OK;
+}
+
+// one finished slice: packed behind its last kernel when a transfer is running, else the plain copy
+static int ship_slice(pk_indexer *ix, cudaStream_t st, uint32_t b, const uint8_t *slice_dev, uint8_t *dst_host, size_t n) {
+    if (ix->shipper && ix->shipper->running) {
+        const int rc = ix->shipper->pack(slice_dev, dst_host, n, st, ix->sm_count);
+        if (rc != PK_OK) return rc;
+        ix->launches++;
+        return ix->shipper->service(ix->copy_stream, TableShipper::kLag);
+    }
+    PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
+    PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
+    PK_CUDA(cudaMemcpyAsync(dst_host, slice_dev, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+    ix->xfer[0] += n;
+    ix->xfer[2] += 1;
+    return PK_OK;
+}
+
 // PARTITION: drain the buffered entries window by window into the table: count the
 // window's entries into the L2-resident counters, then commit them (clamp, write the
 // table slice once, re-zero, histogram).  Counting and committing two windows side by
@@ -1481,6 +1796,10 @@ static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table
     const size_t win = (size_t)1 << ix->win_log2;
     PK_CUDA(cudaMemsetAsync(ix->counters + 1, 0, 256 * sizeof(unsigned long long), st));
     const uint32_t *src = ix->pool_ext ? ix->pool_ext : (const uint32_t *)ix->pool;
+    {
+        const int rc = shipper_begin(ix, table_host, win, ix->nbuckets);
+        if (rc != PK_OK) return rc;
+    }
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
         const size_t nvec = (n + 15) / 16;                  // the allocation is padded to 256 bytes
@@ -1501,9 +1820,8 @@ static int indexer_flush_inplace(pk_indexer *ix, cudaStream_t st, uint8_t *table
             ix->launches++;
         }
         if (table_host) {                                   // ship this window while the next is counted
-            PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
-            PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
-            PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+            const int rc = ship_slice(ix, st, b, tw, table_host + (size_t)b * win, n);
+            if (rc != PK_OK) return rc;
         }
     }
     PK_CUDA(cudaGetLastError());
@@ -1534,6 +1852,10 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
         PK_CUDA(cudaMemsetAsync(ix->bins_part, 0, (size_t)8 * ix->sm_count * 256 * sizeof(unsigned long long), st));
     unsigned long long *bins = with_stats ? ix->bins_part : nullptr;
     const int grid = ix->sm_count * (ix->count8 ? ix->cnt8_blocks_per_sm : ix->cnt_blocks_per_sm);
+    {
+        const int rc = shipper_begin(ix, table_host, win, ix->nbuckets);
+        if (rc != PK_OK) return rc;
+    }
     for (uint32_t b = 0; b < ix->nbuckets; b++) {
         const size_t n = std::min(win, ix->table_bytes - (size_t)b * win);
         if (ix->nseg) {
@@ -1566,9 +1888,8 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
         }
         ix->launches++;
         if (table_host) {                                   // ship this window while the next is counted
-            PK_CUDA(cudaEventRecord(ix->committed[b & 1u], st));
-            PK_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->committed[b & 1u], 0));
-            PK_CUDA(cudaMemcpyAsync(table_host + (size_t)b * win, tw, n, cudaMemcpyDeviceToHost, ix->copy_stream));
+            const int rc = ship_slice(ix, st, b, tw, table_host + (size_t)b * win, n);
+            if (rc != PK_OK) return rc;
         }
     }
     return indexer_flush_finish(ix, st, with_stats, table_host);
@@ -1577,6 +1898,14 @@ static int indexer_flush_l2(pk_indexer *ix, cudaStream_t st, bool with_stats, ui
 // common end of a flush: join the table copies, reduce the histogram, recycle the buffers
 static int indexer_flush_finish(pk_indexer *ix, cudaStream_t st, bool with_stats, uint8_t *table_host) {
     const int rows = ix->sm_count * 8;                      // every row of bins_part (unused ones are zero)
+    if (ix->shipper && ix->shipper->running) {              // the last copies, and every slot rebuilt on the host
+        const int rc = ix->shipper->finish(ix->copy_stream);
+        if (rc != PK_OK) return rc;
+        ix->xfer[0] = ix->shipper->d2h_bytes;
+        ix->xfer[1] = ix->shipper->packed_slices;
+        ix->xfer[2] = ix->shipper->raw_slices;
+        ix->xfer[3] = (uint64_t)ix->shipper->team_size;
+    }
     if (table_host) {
         PK_CUDA(cudaEventRecord(ix->committed[0], ix->copy_stream));
         PK_CUDA(cudaStreamWaitEvent(st, ix->committed[0], 0));
@@ -2062,6 +2391,7 @@ PK_API int pk_indexer_destroy(pk_indexer *ix) {
     cudaFree(ix->pool); cudaFree(ix->seg); cudaFree(ix->cursor); cudaFree(ix->scratch);
     cudaFree(ix->bins_part); cudaFree(ix->route); cudaFree(ix->pool2); cudaFree(ix->sub);
     cudaFree(ix->import_off);
+    delete ix->shipper;
     cudaFree(ix->ovf.keys); cudaFree(ix->ovf.vals); cudaFree(ix->ovf.list); cudaFree(ix->ovf.meta);
     if (ix->l2_persist_bytes) {
         // give the carve-out back with its last user: left in place it shrinks the L2 of everything that
@@ -2286,14 +2616,18 @@ static int indexer_finalize(pk_indexer *ix, int64_t hist_host[255], uint64_t sta
         if (rc != PK_OK) return rc;
     }
     cudaStream_t st = ix->work_stream;
+    if (table_host) memset(ix->xfer, 0, sizeof ix->xfer);
     if (ix->mode == PK_MODE_PARTITION && (ix->nseg || !ix->table_valid || !ix->stats_valid)) {
         const int rc = indexer_flush(ix, st, true, table_host);   // statistics fused into the commit
         if (rc != PK_OK) return rc;
         copied = table_host != nullptr;
     }
     // DIRECT: counters + 1 already hold the histogram (kept as transitions by every update)
-    if (table_host && !copied)
+    if (table_host && !copied) {
         PK_CUDA(cudaMemcpyAsync(table_host, ix->table, ix->table_bytes, cudaMemcpyDeviceToHost, st));
+        ix->xfer[0] += ix->table_bytes;
+        ix->xfer[2] += 1;
+    }
     PK_CUDA(cudaMemcpyAsync(ix->h_counters, ix->counters, 257 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaStreamSynchronize(st));
@@ -2312,6 +2646,41 @@ PK_API int pk_indexer_finalize_to_host(pk_indexer *ix, int64_t hist_host[255], u
                                        uint8_t *table_host) {
     PK_REQUIRE(table_host != nullptr, "pk_indexer_finalize_to_host: NULL table buffer");
     return indexer_finalize(ix, hist_host, stats_host, table_host);
+}
+
+// the packing half of the packed transfer on its own (tests, other consumers): nz_dev needs room for
+// n + n / 64 bytes; *nz_units_host = 16-byte units written.  Synchronises `stream`.
+PK_API int pk_table_pack_device(const uint8_t *table_dev, size_t n, uint64_t *bitmap_dev, uint32_t *chunk_off_dev,
+                                uint8_t *nz_dev, uint32_t *nz_units_host, pk_stream stream) {
+    PK_REQUIRE(n % kPackChunk == 0, "pk_table_pack_device: %zu entries are not a multiple of the %zu-entry chunk", n, kPackChunk);
+    PK_REQUIRE(nz_units_host != nullptr, "pk_table_pack_device: NULL output");
+    *nz_units_host = 0;
+    if (n == 0) return PK_OK;
+    PK_REQUIRE(table_dev && bitmap_dev && chunk_off_dev && nz_dev, "pk_table_pack_device: NULL buffer");
+    PK_REQUIRE(((uintptr_t)table_dev & 15) == 0 && ((uintptr_t)nz_dev & 15) == 0, "pk_table_pack_device: table and nz must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0;
+    PK_CUDA(cudaGetDevice(&device));
+    uint32_t *cursor = nullptr;
+    PK_CUDA(cudaMalloc(&cursor, sizeof(uint32_t)));
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st);
+    const size_t nchunks = n / kPackChunk;
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<size_t>((size_t)pk_sm_count(device) * 8, (nchunks + 7) / 8);
+        k_table_pack<<<grid, 256, 0, st>>>(table_dev, nchunks, reinterpret_cast<uint16_t *>(bitmap_dev), chunk_off_dev, nz_dev, cursor);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nz_units_host, cursor, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(cursor);
+    PK_CUDA(e);
+    return PK_OK;
+}
+
+PK_API int pk_indexer_transfer_stats(pk_indexer *ix, uint64_t stats_host[4]) {
+    PK_REQUIRE(ix != nullptr && stats_host != nullptr, "pk_indexer_transfer_stats: NULL argument");
+    memcpy(stats_host, ix->xfer, sizeof ix->xfer);
+    return PK_OK;
 }
 
 PK_API int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec) {

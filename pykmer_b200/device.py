@@ -166,6 +166,13 @@ class Indexer:
                                "vals_count": int(st[2]), "vals_min": int(st[3]),
                                "vals_max": int(st[4])}
 
+    def transfer_stats(self) -> dict:
+        """What the last finalize(table_out=...) moved over PCIe (pk_indexer_transfer_stats)."""
+        st = np.zeros(4, dtype=np.uint64)
+        nat.check(lib.pk_indexer_transfer_stats(self._h, st.ctypes.data))
+        return {"d2h_bytes": int(st[0]), "packed_windows": int(st[1]), "raw_windows": int(st[2]),
+                "unpack_threads": int(st[3])}
+
     def record_flags(self) -> np.ndarray:
         flags = np.zeros(max(self._nrec, 1), dtype=np.uint8)
         nat.check(lib.pk_indexer_record_flags(self._h, flags.ctypes.data, self._nrec))
@@ -337,6 +344,36 @@ def table_stats(table, device: Optional[int] = None):
         nat.check(lib.pk_table_stats_device(t.data_ptr(), t.numel(), hist.ctypes.data,
                                             st.ctypes.data, _stream_ptr()))
     return hist.tolist(), tuple(int(v) for v in st)
+
+
+def table_pack(table, device: Optional[int] = None):
+    """The packed form a finished table crosses PCIe in (include/pykmer_b200.h: pk_table_pack_device):
+    -> (bitmap uint64[n/64], chunk_off uint32[n/1024], nz uint8[...]) as NumPy arrays."""
+    t = to_device_u8(table, device)
+    n = t.numel()
+    bitmap = torch.empty(n // 64, dtype=torch.int64, device=t.device)
+    chunk_off = torch.empty(n // 1024, dtype=torch.int32, device=t.device)
+    nz = torch.empty(n + n // 64 + 16, dtype=torch.uint8, device=t.device)
+    units = ctypes.c_uint32(0)
+    with torch.cuda.device(t.device):
+        nat.check(lib.pk_table_pack_device(t.data_ptr(), n, bitmap.data_ptr(), chunk_off.data_ptr(), nz.data_ptr(),
+                                           ctypes.byref(units), _stream_ptr()))
+    return (bitmap.cpu().numpy().view(np.uint64), chunk_off.cpu().numpy().view(np.uint32),
+            nz[: units.value * 16].cpu().numpy())
+
+
+def table_unpack(bitmap: np.ndarray, chunk_off: np.ndarray, nz: np.ndarray, n: int, threads: int = 0,
+                 out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Host side of the packed transfer (pk_table_unpack; no CUDA call): the n table bytes."""
+    bitmap = np.ascontiguousarray(bitmap, dtype=np.uint64)
+    chunk_off = np.ascontiguousarray(chunk_off, dtype=np.uint32)
+    nz = np.ascontiguousarray(nz, dtype=np.uint8)
+    if out is None:
+        out = np.empty(n, dtype=np.uint8)
+    assert out.size == n and out.dtype == np.uint8 and out.flags.c_contiguous
+    nat.check(lib.pk_table_unpack(bitmap.ctypes.data, chunk_off.ctypes.data, nz.ctypes.data if nz.size else None,
+                                  nz.size, n, out.ctypes.data, threads))
+    return out
 
 
 def pair_counts(s, o, min_count: int = 1, max_count: int = 255, device: Optional[int] = None):

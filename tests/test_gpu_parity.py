@@ -816,30 +816,65 @@ def test_full_size_k17_shard_schemes_agree(env):
     assert len(set(digests)) == 1 and all(s == stats[0] for s in stats)
 
 
-@pytest.mark.parametrize("mode,wlog", [(1, None), (2, 10), (2, 24)])
-def test_finalize_to_host_streams_the_table(env, mode, wlog):
+@pytest.mark.parametrize("mode,wlog,bases,packed,threads", [
+    (1, None, 300_000, "1", None), (2, 10, 300_000, "1", "3"), (2, 24, 300_000, "1", None), (2, 14, 300_000, "1", "1"),
+    (2, 16, 300_000, "0", None),                     # the plain copy of every window
+    (2, 18, 12_000_000, "1", None),                  # dense table: every window is sent as it is
+    (2, 16, 2_500_000, "1", "2"),                    # about half full: packed and raw windows side by side
+])
+def test_finalize_to_host_streams_the_table(env, mode, wlog, bases, packed, threads):
+    """pk_indexer_finalize_to_host: windows leave packed (bitmap + non-zero bytes, rebuilt by a team of host
+    threads) or as they are -- dense windows, busy slots, PYKMER_B200_PACKED_D2H=0 -- and land the same bytes."""
     rng = np.random.default_rng(321)
-    s = _random_stream(rng, 300_000)
+    s = _random_stream(rng, bases)
     K = 11
     want, num, _ = env["oracle"].index_stream(s, K)
     dev = env["dev"]
     if wlog is not None:
         os.environ["PYKMER_B200_WINDOW_LOG2"] = str(wlog)
+    os.environ["PYKMER_B200_PACKED_D2H"] = packed
+    if threads:
+        os.environ["PYKMER_B200_UNPACK_THREADS"] = threads
     try:
         ix = dev.Indexer(K, mode=mode)
+        with ix:
+            out = dev.pinned_empty(4 ** K + 64)[37:37 + 4 ** K] if threads == "2" else dev.pinned_empty(4 ** K)
+            for rep in range(2):
+                out.fill_(9)
+                ix.reset()
+                ix.feed_host(s)
+                hist, st = ix.finalize(table_out=out)
+                assert st["num_kmers"] == num and np.array_equal(out.numpy(), want)
+                assert hist == env["oracle"].table_stats(want)[0]
+                x = ix.transfer_stats()
+                if mode == 2:
+                    assert x["packed_windows"] + x["raw_windows"] == max(1, (4 ** K) >> wlog)
+                    if packed == "0" or bases == 12_000_000:
+                        assert x["packed_windows"] == 0 and x["d2h_bytes"] >= 4 ** K
+                    elif bases == 300_000:
+                        assert x["packed_windows"] > 0 and x["d2h_bytes"] < 4 ** K // 2
+                    if threads and x["packed_windows"]:
+                        assert x["unpack_threads"] == int(threads)
+            hist2, st2 = ix.finalize(table_out=out)              # nothing pending: plain copy
+            assert (hist2, st2) == (hist, st) and np.array_equal(out.numpy(), want)
     finally:
-        os.environ.pop("PYKMER_B200_WINDOW_LOG2", None)
-    with ix:
-        out = dev.pinned_empty(4 ** K)
-        for rep in range(2):
-            out.zero_()
-            ix.reset()
-            ix.feed_host(s)
-            hist, st = ix.finalize(table_out=out)
-            assert st["num_kmers"] == num and np.array_equal(out.numpy(), want)
-            assert hist == env["oracle"].table_stats(want)[0]
-        hist2, st2 = ix.finalize(table_out=out)              # nothing pending: plain copy
-        assert (hist2, st2) == (hist, st) and np.array_equal(out.numpy(), want)
+        for k in ("PYKMER_B200_WINDOW_LOG2", "PYKMER_B200_PACKED_D2H", "PYKMER_B200_UNPACK_THREADS"):
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("n,fill", [(1024, 0.0), (1024, 1.0), (1 << 16, 0.5), (1 << 22, 0.25), (3 << 20, 0.03), (1 << 24, 0.9)])
+def test_table_pack_kernel_and_host_unpack(env, n, fill):
+    """k_table_pack against the NumPy restatement (chunks may land in any order: compared through the
+    literal inverse), and the device-packed slice through the host's pk_table_unpack."""
+    dev, oracle = env["dev"], env["oracle"]
+    rng = np.random.default_rng(n % 1000 + int(fill * 100))
+    t = rng.integers(1, 256, n, dtype=np.uint8)
+    t[rng.random(n) >= fill] = 0
+    bm, off, nz = dev.table_pack(t)
+    o_bm, o_off, o_nz = oracle.pack_table(t)
+    assert np.array_equal(bm, o_bm) and nz.size == o_nz.size
+    assert np.array_equal(oracle.unpack_table(bm, off, nz, n), t)
+    assert np.array_equal(dev.table_unpack(bm, off, nz, n), t)
 
 
 @pytest.mark.parametrize("K,wlog,nranks", [(9, 10, 3), (11, 12, 2), (17, 12, 4)])

@@ -406,6 +406,57 @@ def test_merge_tables_streams_slabs_in_order(tmp_path, monkeypatch):
             assert np.array_equal(got, want), (packed, slab)
 
 
+def _sparse_table(rng, n, fill):
+    t = rng.integers(1, 256, n, dtype=np.uint8)
+    t[rng.random(n) >= fill] = 0
+    return t
+
+
+@pytest.mark.parametrize("isa", ["auto", "bmi2", "scalar"])
+def test_table_unpack_rebuilds_packed_slices(isa, tmp_path):
+    """Host half of the packed table transfer (csrc/unpack.cpp) on every code path: AVX-512 VBMI2 expand,
+    BMI2 pdep, plain loop -- each in its own process, the path is chosen once (PYKMER_B200_UNPACK)."""
+    code = """
+import numpy as np, sys
+sys.path.insert(0, %r)
+from oracle import oracle
+from pykmer_b200 import device as dev
+rng = np.random.default_rng(5)
+for n, fill in ((1024, 0.0), (1024, 1.0), (4096, 0.5), (1 << 20, 0.25), (1 << 20, 0.03), (3 << 18, 0.9)):
+    t = rng.integers(1, 256, n, dtype=np.uint8); t[rng.random(n) >= fill] = 0
+    bm, off, nz = oracle.pack_table(t)
+    assert np.array_equal(oracle.unpack_table(bm, off, nz, n), t)
+    for threads in (1, 5):
+        assert np.array_equal(dev.table_unpack(bm, off, nz, n, threads=threads), t), (n, fill, threads)
+    # chunks in any order: reverse them
+    per = (np.unpackbits(bm.view(np.uint8), bitorder="little").reshape(-1, 1024).sum(axis=1) + 15) // 16
+    roff = (np.concatenate(([0], np.cumsum(per[::-1])[:-1]))[::-1]).astype(np.uint32)
+    rnz = np.concatenate([nz[int(o) * 16:(int(o) + int(p)) * 16] for o, p in zip(off[::-1], per[::-1])] + [np.zeros(0, np.uint8)])
+    out = np.full(n + 64, 7, dtype=np.uint8)               # unaligned destination, guard bytes
+    dev.table_unpack(bm, roff, rnz, n, out=out[3:3 + n])
+    assert np.array_equal(out[3:3 + n], t) and (out[:3] == 7).all() and (out[3 + n:] == 7).all()
+# a chunk that would run past the packed bytes is refused
+t = np.ones(2048, dtype=np.uint8)
+bm, off, nz = oracle.pack_table(t)
+try:
+    dev.table_unpack(bm, off, nz[:-16], 2048)
+    raise SystemExit("accepted a truncated packed slice")
+except ValueError:
+    pass
+try:
+    dev.table_unpack(bm[:8], off[:1], nz, 1000)
+    raise SystemExit("accepted a slice that is no whole number of chunks")
+except ValueError:
+    pass
+print("ok")
+""" % ROOT
+    env = dict(os.environ)
+    if isa != "auto":
+        env["PYKMER_B200_UNPACK"] = isa
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == "ok", res.stdout + res.stderr
+
+
 def test_library_carries_the_tensor_core_instructions():
     """The built sm_100a library really holds the 5th-generation tensor-core code paths: UTCOMMA
     (tcgen05.mma kind::mxf4, gram_f4.cu), UTCIMMA (kind::i8, gram_i8.cu), TMEM loads / stores."""

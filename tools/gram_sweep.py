@@ -50,7 +50,7 @@ def child():
         if variant == "tmem":
             print(f"N={n:3d} i8                 {ref_ms:7.3f} ms   {ref_ms * 1.965e6 / (2 * steps):6.1f} clk per K=32 step", flush=True)
         tiled = rows.view(n, WORDS // 32, 32).permute(1, 0, 2).contiguous().view(-1)
-        for diag in (0, 1, 2, 3, 4, 8):
+        for diag in [int(v) for v in os.environ.get("SWEEP_DIAGS", "0,1,2,3,4,8").split(",")]:
             os.environ["PYKMER_B200_GRAM_DIAG"] = str(diag)
             ms = timed(lambda: dev.gram_tiled(tiled, n, WORDS, out=G, accumulate=False))
             ok = "" if diag else (" exact" if torch.equal(G, ref) else " MISMATCH")
