@@ -1544,6 +1544,15 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
 // the plain cudaMemcpyAsync of the table bytes, as before -- when it is dense (packed size above
 // 5/8 of the bytes), when it is no whole number of chunks, or when its slot is still being unpacked:
 // the host's cores and the bus then share the work in whatever ratio keeps both busy.
+// Measured on the 16-core GPU box, K=15 (profiles/r02n_*): 33.8 ms end to end with plain copies, 26.4 ms with
+// this pipeline.  The 4-byte cursor copy on the work stream queues on the copy engine behind the bulk copies
+// of the earlier windows, so the kernels run at most a window or two ahead of the transfer.  Taking that
+// coupling away (cursor stored straight into pinned memory, 8 device / 6 host slots, one raw copy in
+// flight at a time) let the flush, the copies and 15 streaming-store threads all hit host memory at once
+// and measured 29.4 .. 30.9 ms whatever the lag and slot counts; coding the counts as nibbles + escapes
+// (0.29 GB instead of 0.41 GB on the bus) made the team compute-bound and measured 30.3 .. 33.4 ms; counting
+// the first 5/8 of the stream under the host-to-device copy (an early flush) changed nothing, the phase
+// after the last input byte is bound by the host's memory writes, not by the GPU.  All three were removed.
 void pk_unpack_chunks(const uint64_t *bitmap, const uint32_t *chunk_off, const uint8_t *nz, size_t nz_readable,
                       uint8_t *dst, size_t c0, size_t c1);          // unpack.cpp
 
@@ -1578,7 +1587,8 @@ struct TableShipper {
     bool running = false;
 
     static int threads() {
-        if (const char *v = getenv("PYKMER_B200_UNPACK_THREADS")) return std::max(1, atoi(v));
+        if (const char *v = getenv("PYKMER_B200_UNPACK_THREADS"))
+            if (atoi(v) > 0) return std::min(atoi(v), 64);
         int hc = (int)std::thread::hardware_concurrency(), local = 1;
         if (const char *v = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(v));
         return std::max(1, std::min(hc / local - 1, 32));     // the caller's thread keeps a core
@@ -1743,6 +1753,10 @@ struct TableShipper {
     int finish(cudaStream_t copy_stream) {
         running = false;
         const int rc = service(copy_stream, 0);
+        if (const char *v = getenv("PYKMER_B200_VERBOSE"))
+            if (atoi(v) >= 1)
+                fprintf(stderr, "[pykmer_b200] packed transfer: %zu slices (%zu packed, %zu raw), %.1f MB, %d host threads\n",
+                        issued, packed_slices, raw_slices, d2h_bytes / 1e6, team_size);
         if (rc == PK_OK)
             while (jobs_done.load(std::memory_order_acquire) < njobs.load(std::memory_order_acquire)) std::this_thread::yield();
         stop_team();
