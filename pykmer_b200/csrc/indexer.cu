@@ -498,7 +498,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
     __shared__ uint8_t lut[256];
     __shared__ uint32_t s_part[kScanThreads];
     __shared__ uint32_t s_total;
+    __shared__ uint32_t *s_peer[16];                       // the owners' buffers (remote destinations only)
     lut[threadIdx.x] = (uint8_t)pk_lut_entry(threadIdx.x);
+    if (threadIdx.x < 16) s_peer[threadIdx.x] = p.peer[threadIdx.x];
 
     using WT = WarpTile<WIDE>;
     const long long ngroups = (long long)((p.n + 15) / 16);
@@ -589,13 +591,22 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
             }
         }
         __syncthreads();
-        // D: contiguous runs go out with coalesced stores
+        // D: contiguous runs go out with coalesced stores.  The destination is chosen OUTSIDE the loop: picking
+        // p.peer[owner] out of the kernel's parameter block per entry cost 11 % of the kernel's instructions
+        // also where there are no peers at all (ncu source view, profiles/r02p_ncu_scan_scatter_source.txt)
         const uint32_t total = s_total;
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            const uint32_t b = s_bid[i];
-            uint32_t *dst = p.win_owner ? p.peer[p.win_owner[b]] : p.pool;
-            const uint32_t base = s_gbase[b];
-            if (base != 0xFFFFFFFFu) dst[base + (i - s_toff[b])] = s_ent[i];
+        if (!p.win_owner) {
+            uint32_t *const pool = p.pool;
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                const uint32_t b = s_bid[i], base = s_gbase[b];
+                if (base != 0xFFFFFFFFu) pool[base + (i - s_toff[b])] = s_ent[i];
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                const uint32_t b = s_bid[i], base = s_gbase[b];
+                uint32_t *const dst = s_peer[__ldg(p.win_owner + b)];
+                if (base != 0xFFFFFFFFu) dst[base + (i - s_toff[b])] = s_ent[i];
+            }
         }
         // the next iteration only touches s_cnt before its first barrier
     }

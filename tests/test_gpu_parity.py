@@ -819,14 +819,14 @@ def test_full_size_k17_shard_schemes_agree(env):
 @pytest.mark.parametrize("mode,wlog,bases,packed,threads", [
     (1, None, 300_000, "1", None), (2, 10, 300_000, "1", "3"), (2, 24, 300_000, "1", None), (2, 14, 300_000, "1", "1"),
     (2, 16, 300_000, "0", None),                     # the plain copy of every window
-    (2, 18, 12_000_000, "1", None),                  # dense table: every window is sent as it is
+    (2, 18, 40_000_000, "1", None),                  # every canonical 11-mer present: the dense low windows are sent as they are
     (2, 16, 2_500_000, "1", "2"),                    # about half full: packed and raw windows side by side
 ])
 def test_finalize_to_host_streams_the_table(env, mode, wlog, bases, packed, threads):
     """pk_indexer_finalize_to_host: windows leave packed (bitmap + non-zero bytes, rebuilt by a team of host
     threads) or as they are -- dense windows, busy slots, PYKMER_B200_PACKED_D2H=0 -- and land the same bytes."""
     rng = np.random.default_rng(321)
-    s = _random_stream(rng, bases)
+    s = _random_stream(rng, bases) if bases < 40_000_000 else _random_stream(rng, bases, alphabet=b"ACGT")
     K = 11
     want, num, _ = env["oracle"].index_stream(s, K)
     dev = env["dev"]
@@ -849,8 +849,10 @@ def test_finalize_to_host_streams_the_table(env, mode, wlog, bases, packed, thre
                 x = ix.transfer_stats()
                 if mode == 2:
                     assert x["packed_windows"] + x["raw_windows"] == max(1, (4 ** K) >> wlog)
-                    if packed == "0" or bases == 12_000_000:
+                    if packed == "0":
                         assert x["packed_windows"] == 0 and x["d2h_bytes"] >= 4 ** K
+                    elif bases == 40_000_000:                # the low windows are full, the high ones hold no canonical k-mer
+                        assert x["raw_windows"] >= 4
                     elif bases == 300_000:
                         assert x["packed_windows"] > 0 and (threads or x["d2h_bytes"] < 4 ** K // 2)
                     if threads and x["packed_windows"]:
