@@ -523,6 +523,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
         if (tile < ntiles) {
             WT t;
             t.load(p, tile, ngroups, lut);
+            {   // the bases of this warp's NEXT tile: into L1 while this tile is sorted (the load at the top of a
+                // tile was 12 % of the kernel's stall samples, long scoreboard)
+                const long long gn = t.g + (long long)gridDim.x * kScanWarps * WT::GPW;
+                if (gn >= 0 && gn < ngroups) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.seq + (size_t)gn * 16));
+            }
             uint32_t cm = 0;
             if (t.emits)
                 cm = pk_scan_group<WIDE, FULL>(
@@ -597,12 +602,12 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
         const uint32_t total = s_total;
         if (!p.win_owner) {
             uint32_t *const pool = p.pool;
-            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            for (uint32_t i = threadIdx.x; i < total; i += kScanThreads) {   // (four entries in flight per thread: no faster)
                 const uint32_t b = s_bid[i], base = s_gbase[b];
                 if (base != 0xFFFFFFFFu) pool[base + (i - s_toff[b])] = s_ent[i];
             }
         } else {
-            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            for (uint32_t i = threadIdx.x; i < total; i += kScanThreads) {
                 const uint32_t b = s_bid[i], base = s_gbase[b];
                 uint32_t *const dst = s_peer[__ldg(p.win_owner + b)];
                 if (base != 0xFFFFFFFFu) dst[base + (i - s_toff[b])] = s_ent[i];
