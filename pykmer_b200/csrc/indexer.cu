@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
         }
         __syncthreads();
         // B: exclusive scan over the windows; reserve the tile's share of every segment
+        uint32_t def_c = 0, def_room = 0, def_pos = 0;     // deferred reservation of this thread's window (per == 1)
         {
             const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
             uint32_t s = 0;
@@ -569,18 +570,34 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
             }
             __syncthreads();
             uint32_t run = s_part[threadIdx.x];
-            for (uint32_t b = b0; b < b1; b++) {
-                const uint32_t c = s_cnt[b];
-                s_toff[b] = run;
-                run += c;
-                if (c) {
-                    const uint32_t room = p.seg_cap ? __ldg(p.seg_cap + b) : 0xFFFFFFFFu;   // before the atomic's round trip
-                    const uint32_t pos = atomicAdd(&p.seg_fill[b], c);
-                    if (pos + c > room) {                           // the estimate fell short: redo exactly
-                        if (*reinterpret_cast<volatile uint32_t *>(p.ctl + 1) == 0u) atomicExch(p.ctl + 1, 1u);
-                        s_gbase[b] = 0xFFFFFFFFu;
-                    } else {
-                        s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + pos;
+            auto reserve = [&](uint32_t b, uint32_t c, uint32_t room, uint32_t pos) {
+                if (pos + c > room) {                               // the estimate fell short: redo exactly
+                    if (*reinterpret_cast<volatile uint32_t *>(p.ctl + 1) == 0u) atomicExch(p.ctl + 1, 1u);
+                    s_gbase[b] = 0xFFFFFFFFu;
+                } else {
+                    s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + pos;
+                }
+            };
+            if (per == 1) {
+                // one window per thread (up to 256 windows): the reservation's round trip to L2 runs under the
+                // staging below -- its result is only needed by the write-out (the barrier stalls around this
+                // block were 12 % of the kernel's stall samples)
+                if (b0 < b1) {
+                    def_c = s_cnt[b0];
+                    s_toff[b0] = run;
+                    if (def_c) {
+                        def_room = p.seg_cap ? __ldg(p.seg_cap + b0) : 0xFFFFFFFFu;
+                        def_pos = atomicAdd(&p.seg_fill[b0], def_c);
+                    }
+                }
+            } else {
+                for (uint32_t b = b0; b < b1; b++) {
+                    const uint32_t c = s_cnt[b];
+                    s_toff[b] = run;
+                    run += c;
+                    if (c) {
+                        const uint32_t room = p.seg_cap ? __ldg(p.seg_cap + b) : 0xFFFFFFFFu;   // before the atomic's round trip
+                        reserve(b, c, room, atomicAdd(&p.seg_fill[b], c));
                     }
                 }
             }
@@ -593,6 +610,15 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
                 const uint32_t b = key[s] >> 16, pos = s_toff[b] + (key[s] & 0xFFFFu);
                 s_ent[pos] = ent[s];
                 s_bid[pos] = (uint16_t)b;
+            }
+        }
+        if (per == 1 && def_c) {                            // the deferred reservation has come back by now
+            const uint32_t b = threadIdx.x;
+            if (def_pos + def_c > def_room) {
+                if (*reinterpret_cast<volatile uint32_t *>(p.ctl + 1) == 0u) atomicExch(p.ctl + 1, 1u);
+                s_gbase[b] = 0xFFFFFFFFu;
+            } else {
+                s_gbase[b] = (p.win_owner ? p.dest_off[b] : p.seg_off[b]) + def_pos;
             }
         }
         __syncthreads();
