@@ -1812,8 +1812,12 @@ struct TableShipper {
 // start a packed transfer for this flush, or return with ix->shipper idle (plain copies)
 static int shipper_begin(pk_indexer *ix, uint8_t *table_host, size_t slice_entries, size_t nslices) {
     if (!table_host || ix->table_bytes < ((size_t)1 << 22)) return PK_OK;
-    if (const char *v = getenv("PYKMER_B200_PACKED_D2H"))
-        if (atoi(v) == 0) return PK_OK;                     // test hook: the plain copy of every window
+    // the packed form pays when enough cores rebuild the table: 26.4 ms against 33.8 with 15 threads, 28.3 with 7
+    // (one GPU, 16 cores), 19.1 against 23.4 ms with 11 per rank (two GPUs, 24 cores) -- and loses with 3 per rank
+    // (eight GPUs on 32 cores: 17.9 against 15.7 ms, the ranks then fight over the host's memory).  So by default
+    // it is used from 6 threads per rank up; PYKMER_B200_PACKED_D2H=1 / 0 forces it on / off.
+    const char *v = getenv("PYKMER_B200_PACKED_D2H");
+    if (v ? atoi(v) == 0 : TableShipper::threads() < 6) return PK_OK;
     if (!ix->shipper) ix->shipper = new (std::nothrow) TableShipper();
     if (!ix->shipper) return pk_set_error(PK_ERR_NOMEM, "packed table transfer: out of host memory");
     const int rc = ix->shipper->ensure(ix->device, std::min(slice_entries, ix->table_bytes), nslices);
