@@ -1717,6 +1717,7 @@ struct TableShipper {
     }
 
     void begin(size_t nslices) {
+        if (!team.empty()) stop_team();                     // a run that ended in an error left its team behind
         jobs = std::vector<Job>(nslices);
         njobs.store(0); jobs_done.store(0); closing.store(false); failed.store(0);
         for (int i = 0; i < kSlots; i++) { slot_busy[i].store(0); slot_copied[i] = false; }
