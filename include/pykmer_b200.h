@@ -133,8 +133,9 @@ int pk_indexer_record_flags(pk_indexer *ix, uint8_t *flags_host, size_t nrec);
  * finalize_to_host packs every window behind its last kernel, copies only the packed form into pinned slots
  * and rebuilds the bytes in table_host on the host's cores while later windows are counted; dense windows
  * (packed size above 5/8 of the bytes), and windows whose slot is still being rebuilt, are copied as they
- * are.  The packed form is used when at least 6 host threads per rank can rebuild (all cores but one, divided by
- * LOCAL_WORLD_SIZE; PYKMER_B200_UNPACK_THREADS overrides); PYKMER_B200_PACKED_D2H=1 / 0 forces it on / off.
+ * are.  With more than two ranks per host (LOCAL_WORLD_SIZE) only windows that pack to a quarter of their bytes go
+ * packed.  PYKMER_B200_PACKED_D2H=0 turns the packed form off, =1 keeps the 5/8 rule whatever the number of ranks;
+ * PYKMER_B200_UNPACK_THREADS sets the team size (default: all cores but one, divided by LOCAL_WORLD_SIZE).
  * The two halves on their own: */
 int pk_table_pack_device(const uint8_t *table_dev, size_t n, uint64_t *bitmap_dev, uint32_t *chunk_off_dev,
                          uint8_t *nz_dev /* room for n + n / 64 bytes */, uint32_t *nz_units_host, pk_stream stream);

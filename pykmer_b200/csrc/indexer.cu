@@ -1584,7 +1584,7 @@ static unsigned window_launch_attr(pk_indexer *ix, cudaLaunchAttribute *attr) {
 // thread runs kLag windows behind the launches: it waits for a window's packed size (4 bytes the pack
 // kernel's cursor sends home), queues the copies, and hands the slot to the team.  A slice goes RAW --
 // the plain cudaMemcpyAsync of the table bytes, as before -- when it is dense (packed size above
-// 5/8 of the bytes), when it is no whole number of chunks, or when its slot is still being unpacked:
+// 5/8 of the bytes; 1/4 when more than two ranks share the host), when it is no whole number of chunks, or when its slot is still being unpacked:
 // the host's cores and the bus then share the work in whatever ratio keeps both busy.
 // Measured on the 16-core GPU box, K=15 (profiles/r02n_*): 33.8 ms end to end with plain copies, 26.4 ms with
 // this pipeline.  The 4-byte cursor copy on the work stream queues on the copy engine behind the bulk copies
@@ -1626,6 +1626,7 @@ struct TableShipper {
     std::vector<Pending> pending;
     size_t issued = 0, serviced = 0, packed_slices = 0, raw_slices = 0, d2h_bytes = 0;
     int team_size = 0;
+    int dense_eighths = 5;                      // a window goes packed up to this many eighths of its bytes
     bool running = false;
 
     static int threads() {
@@ -1765,7 +1766,7 @@ struct TableShipper {
             PK_CUDA(cudaEventSynchronize(packed[p.slot]));
             const size_t nz_bytes = packable ? (size_t)h_cur[p.idx] * 16 : 0;
             const size_t packed_bytes = p.n / 8 + p.n / kPackChunk * sizeof(uint32_t) + nz_bytes;
-            const bool go_packed = packable && nz_bytes <= nz_cap && packed_bytes * 8 <= p.n * 5 &&
+            const bool go_packed = packable && nz_bytes <= nz_cap && packed_bytes * 8 <= p.n * (size_t)dense_eighths &&
                                    slot_busy[p.slot].load(std::memory_order_acquire) == 0;
             PK_CUDA(cudaStreamWaitEvent(copy_stream, packed[p.slot], 0));
             if (!go_packed) {
@@ -1813,14 +1814,20 @@ struct TableShipper {
 // start a packed transfer for this flush, or return with ix->shipper idle (plain copies)
 static int shipper_begin(pk_indexer *ix, uint8_t *table_host, size_t slice_entries, size_t nslices) {
     if (!table_host || ix->table_bytes < ((size_t)1 << 22)) return PK_OK;
-    // the packed form pays when enough cores rebuild the table: 26.4 ms against 33.8 with 15 threads, 28.3 with 7
-    // (one GPU, 16 cores), 19.1 against 23.4 ms with 11 per rank (two GPUs, 24 cores) -- and loses with 3 per rank
-    // (eight GPUs on 32 cores: 17.9 against 15.7 ms, the ranks then fight over the host's memory).  So by default
-    // it is used from 6 threads per rank up; PYKMER_B200_PACKED_D2H=1 / 0 forces it on / off.
+    // What the packed form is worth depends on how many cores rebuild and on how sparse the table is.  One GPU
+    // (16 cores): K=15 26.4 .. 30.1 ms against 33.8 .. 34.3, K=17 140 against 316; two GPUs (24 cores): 19.1
+    // against 23.4, 132 against 202.  With four or eight ranks on 32 cores (7 / 3 threads per rank) the ranks
+    // fight over the host's memory: K=17 (3 % of the entries in use, packed size 1/6) still wins, 145 against 193 ms
+    // and 171 against 172, K=15 (25 % in use, packed size 0.4) loses, 19.7 against 17.8 and 17.9 against 15.7 ms.
+    // So with more than two ranks per host only windows that pack to a quarter of their bytes go packed.
+    // PYKMER_B200_PACKED_D2H=0 turns the packed form off, =1 takes the 5/8 rule whatever the number of ranks.
     const char *v = getenv("PYKMER_B200_PACKED_D2H");
-    if (v ? atoi(v) == 0 : TableShipper::threads() < 6) return PK_OK;
+    if (v && atoi(v) == 0) return PK_OK;
+    int local_ranks = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) local_ranks = std::max(1, atoi(lw));
     if (!ix->shipper) ix->shipper = new (std::nothrow) TableShipper();
     if (!ix->shipper) return pk_set_error(PK_ERR_NOMEM, "packed table transfer: out of host memory");
+    ix->shipper->dense_eighths = (v || local_ranks <= 2) ? 5 : 2;
     const int rc = ix->shipper->ensure(ix->device, std::min(slice_entries, ix->table_bytes), nslices);
     if (rc != PK_OK) return rc;
     ix->shipper->begin(nslices);
