@@ -864,6 +864,33 @@ def test_finalize_to_host_streams_the_table(env, mode, wlog, bases, packed, thre
             os.environ.pop(k, None)
 
 
+def test_packed_transfer_is_stricter_when_ranks_share_the_host(env):
+    """With more than two ranks per host (LOCAL_WORLD_SIZE) only windows that pack to a quarter of their bytes
+    leave packed; PYKMER_B200_PACKED_D2H=1 keeps the 5/8 rule.  Same bytes either way."""
+    rng = np.random.default_rng(99)
+    s = _random_stream(rng, 2_500_000)
+    K = 11
+    want, num, _ = env["oracle"].index_stream(s, K)
+    dev = env["dev"]
+    counts = {}
+    for name, extra in (("loose", {"PYKMER_B200_PACKED_D2H": "1"}), ("strict", {})):
+        os.environ.update({"PYKMER_B200_WINDOW_LOG2": "16", "LOCAL_WORLD_SIZE": "4", **extra})
+        try:
+            with dev.Indexer(K, mode=2) as ix:
+                out = dev.pinned_empty(4 ** K)
+                out.fill_(3)
+                ix.feed_host(s)
+                hist, st = ix.finalize(table_out=out)
+                assert st["num_kmers"] == num and np.array_equal(out.numpy(), want)
+                counts[name] = ix.transfer_stats()
+        finally:
+            for k in ("PYKMER_B200_WINDOW_LOG2", "LOCAL_WORLD_SIZE", "PYKMER_B200_PACKED_D2H"):
+                os.environ.pop(k, None)
+    # how many windows go packed also depends on how far the (small) team falls behind, so only the totals are fixed
+    for c in counts.values():
+        assert c["packed_windows"] + c["raw_windows"] == (4 ** K) >> 16 and c["d2h_bytes"] <= 4 ** K + 4 * 64 + 2056
+
+
 @pytest.mark.parametrize("n,fill", [(1024, 0.0), (1024, 1.0), (1 << 16, 0.5), (1 << 22, 0.25), (3 << 20, 0.03), (1 << 24, 0.9)])
 def test_table_pack_kernel_and_host_unpack(env, n, fill):
     """k_table_pack against the NumPy restatement (chunks may land in any order: compared through the
