@@ -140,6 +140,28 @@ PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t span, uint32_t cc, uin
         const uint64_t rp_lo = ((((uint64_t)r1 << 32) | r2) >> sh0) | ((uint64_t)r0 << (64 - sh0));
         const uint64_t rp_hi = (uint64_t)r0 >> sh0;
         const uint64_t kmask = pk_kmer_mask(K);
+        if (FULL && Wm == 0xFFFFu) {                              // see the 32-bit form below
+            uint64_t prev;
+            {
+                const uint64_t f = pk_fwd_at(pc2, pc1, cc, 0, K), r = rp_lo & kmask;
+                prev = f < r ? f : r;
+            }
+#pragma unroll
+            for (int j = 1; j < 16; j++) {
+                const uint64_t f = pk_fwd_at(pc2, pc1, cc, j, K);
+                const uint64_t r = ((rp_lo >> (2 * j)) | (rp_hi << (64 - 2 * j))) & kmask;
+                const uint64_t off = f < r ? f : r;
+                if (off == prev) {
+                    pend++;
+                } else {
+                    emit(j, prev, pend + 1u);
+                    prev = off;
+                    pend = 0;
+                }
+            }
+            emit(16, prev, pend + 1u);
+            return 0xFFFFu;
+        }
         uint64_t prev = ~0ull;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -165,6 +187,30 @@ PK_HD uint32_t pk_scan_group(int K, uint64_t lo, uint64_t span, uint32_t cc, uin
         const uint64_t rsh = (((uint64_t)r0 << 32) | r1) >> (34 - 2 * K);
         const uint32_t lo32 = (uint32_t)lo;
         const uint32_t span_m1 = (uint32_t)(span - 1);           // span <= 2^32
+        if (FULL && Wm == 0xFFFFu) {
+            // all 16 windows valid and no range to test -- nearly every group of a genome: no validity
+            // test per window, and a run is always open after the first one
+            uint32_t prev = (uint32_t)(cat >> 30) & mask;
+            {
+                const uint32_t r = (uint32_t)rsh & mask;
+                prev = prev < r ? prev : r;
+            }
+#pragma unroll
+            for (int j = 1; j < 16; j++) {
+                const uint32_t f = (uint32_t)(cat >> (2 * (15 - j))) & mask;
+                const uint32_t r = (uint32_t)(rsh >> (2 * j)) & mask;
+                const uint32_t off = f < r ? f : r;               // indexer.py:341
+                if (off == prev) {
+                    pend++;
+                } else {
+                    emit(j, prev, pend + 1u);
+                    prev = off;
+                    pend = 0;
+                }
+            }
+            emit(16, prev, pend + 1u);
+            return 0xFFFFu;
+        }
         uint32_t prev = 0xFFFFFFFFu;                             // no run yet (never a valid offset + count)
         bool have = false;
 #pragma unroll
