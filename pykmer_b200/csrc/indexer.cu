@@ -1638,6 +1638,12 @@ struct TableShipper {
     }
 
     int ensure(int device_, size_t max_n_, size_t nslices) {
+        const int rc = ensure_buffers(device_, max_n_, nslices);
+        if (rc != PK_OK) release_buffers();                 // nothing half-allocated survives a failure
+        return rc;
+    }
+
+    int ensure_buffers(int device_, size_t max_n_, size_t nslices) {
         if (max_n_ > max_n) {
             release_buffers();
             device = device_;
