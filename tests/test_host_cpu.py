@@ -468,6 +468,6 @@ def test_library_carries_the_tensor_core_instructions():
     res = subprocess.run([tool, "-sass", "-arch", "sm_100a", nat.LIB_PATH], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-500:]
     sass = res.stdout
-    for mnemonic in ("UTCOMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR"):
+    for mnemonic in ("UTCOMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG"):     # UTMALDG: the Gram kernel's TMA loads
         assert mnemonic in sass, mnemonic
-    assert "k_gram_f4" in sass and "k_gram_i8" in sass
+    assert "k_gram_f4" in sass and "k_gram_i8" in sass and "k_table_pack" in sass
