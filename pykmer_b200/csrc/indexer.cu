@@ -69,6 +69,8 @@ struct ScanParams {
     size_t nrec;
     uint8_t *rec_flags;
     uint64_t stream_off;      // stream offset of seq[0]
+    long long ngroups, ntiles;   // 16-base groups / warp tiles of this feed (the host divides once: the kernels
+                                 // otherwise redo the 64-bit division by 31 in every tile iteration, ncu source view)
     // PARTITION
     uint32_t win_log2, nbuckets;
     uint32_t *seg_cnt;        // [nbuckets] entries of this feed per window (pass 1 out)
@@ -248,8 +250,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_direct(const ScanPa
     constexpr int U = 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long *q = s_q[warp];
-    const long long ngroups = (long long)((p.n + 15) / 16);
-    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
+    const long long ngroups = p.ngroups, ntiles = p.ntiles;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     unsigned long long counted = 0;
     RecCache rcache;
@@ -340,8 +341,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_bucket_count(const ScanPa
     for (uint32_t b = threadIdx.x; b < p.nbuckets; b += blockDim.x) s_cnt[b] = 0;
     __syncthreads();
     using WT = WarpTile<WIDE>;
-    const long long ngroups = (long long)((p.n + 15) / 16);
-    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
+    const long long ngroups = p.ngroups, ntiles = p.ntiles;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const uint32_t wl = p.win_log2;
     const uint32_t smask = (1u << p.sample_shift) - 1u;
@@ -503,8 +503,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_scatter(const ScanPara
     if (threadIdx.x < 16) s_peer[threadIdx.x] = p.peer[threadIdx.x];
 
     using WT = WarpTile<WIDE>;
-    const long long ngroups = (long long)((p.n + 15) / 16);
-    const long long ntiles = (ngroups + WT::GPW - 1) / WT::GPW;
+    const long long ngroups = p.ngroups, ntiles = p.ntiles;
     const long long nblock_tiles = (ntiles + kScanWarps - 1) / kScanWarps;
     const uint32_t wl = p.win_log2, wmask = (1u << wl) - 1u;
     const int warp = threadIdx.x >> 5;
@@ -2112,6 +2111,8 @@ static int indexer_launch_scan(pk_indexer *ix, const uint8_t *seq_dev, size_t n,
     const long long ngroups = (long long)((n + 15) / 16);
     const long long ntiles = (ngroups + gpw - 1) / gpw;
     const long long want = (ntiles + kScanWarps - 1) / kScanWarps;
+    p.ngroups = ngroups;
+    p.ntiles = ntiles;
     // grid-stride kernels: exactly as many blocks as are resident at once (no partial second wave)
     if (ix->mode == PK_MODE_DIRECT) {
         int per_sm = 0;
