@@ -10,6 +10,8 @@
 // blocks of text and falls back to its own line-by-line path whenever pk_fasta_clean reports
 // anything unusual.  Host code only: no CUDA call, usable without a GPU.
 #include <atomic>
+#include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 #include <vector>
@@ -121,6 +123,63 @@ PK_API int pk_bgzf_inflate(const uint8_t *comp, size_t comp_len, uint8_t *out, s
     return PK_OK;
 }
 
+namespace {
+
+// AVX-512 (BW + VBMI2) forms of the two passes of pk_fasta_clean over src[a, b): 64 bytes per step.
+// count: bytes kept (everything but \n and \r) and the class flags (2 = other strip()-able white space,
+// 4 = non-ASCII); a block holding any byte below 0x21 other than the two terminators is classified byte
+// by byte (rare in sequence text).  compact: VPCOMPRESSB in its register form + one store; the store
+// is masked where 64 bytes would run into the next thread's part of dst.
+__attribute__((target("avx512f,avx512bw,avx512vbmi2,popcnt")))
+void clean_count_avx512(const uint8_t *src, size_t a, size_t b, const uint8_t *cls, size_t *kept_out, uint32_t *flags_out) {
+    const __m512i nl = _mm512_set1_epi8('\n'), cr = _mm512_set1_epi8('\r'), low = _mm512_set1_epi8(0x21);
+    size_t k = 0, i = a;
+    uint32_t f = 0;
+    for (; i + 64 <= b; i += 64) {
+        const __m512i v = _mm512_loadu_si512(src + i);
+        const __mmask64 term = _mm512_cmpeq_epi8_mask(v, nl) | _mm512_cmpeq_epi8_mask(v, cr);
+        k += 64 - (size_t)__builtin_popcountll(term);
+        if (_mm512_movepi8_mask(v)) f |= 4u;
+        if (_mm512_cmplt_epu8_mask(v, low) & ~term)
+            for (size_t j = i; j < i + 64; j++) f |= cls[src[j]];
+    }
+    for (; i < b; i++) {
+        const uint8_t c = cls[src[i]];
+        k += c != 1;
+        f |= c;
+    }
+    *kept_out = k;
+    *flags_out = f & 6u;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vbmi2,popcnt")))
+void clean_compact_avx512(const uint8_t *src, size_t a, size_t b, uint8_t *o, uint8_t *o_end) {
+    const __m512i nl = _mm512_set1_epi8('\n'), cr = _mm512_set1_epi8('\r');
+    size_t i = a;
+    for (; i + 64 <= b; i += 64) {
+        const __m512i v = _mm512_loadu_si512(src + i);
+        const __mmask64 keep = ~(_mm512_cmpeq_epi8_mask(v, nl) | _mm512_cmpeq_epi8_mask(v, cr));
+        const __m512i packed = _mm512_maskz_compress_epi8(keep, v);
+        const size_t cnt = (size_t)__builtin_popcountll(keep);
+        if (o + 64 <= o_end) _mm512_storeu_si512(o, packed);
+        else _mm512_mask_storeu_epi8(o, cnt >= 64 ? ~0ull : ((1ull << cnt) - 1), packed);
+        o += cnt;
+    }
+    for (; i < b; i++)
+        if (src[i] != '\n' && src[i] != '\r') *o++ = src[i];
+}
+
+bool clean_has_avx512() {
+    static const bool ok = [] {
+        __builtin_cpu_init();
+        if (const char *v = getenv("PYKMER_B200_CLEAN")) if (!strcmp(v, "scalar")) return false;   // test hook
+        return __builtin_cpu_supports("avx512vbmi2") && __builtin_cpu_supports("avx512bw");
+    }();
+    return ok;
+}
+
+}  // namespace
+
 // Sequence lines without inner white space: dst = src minus '\n' and '\r' (every line is then
 // already stripped, so the record's bases are just the remaining bytes, indexer.py:56-58,84).
 // flags bit 0 = src holds a strip()-able byte other than the two line terminators
@@ -153,9 +212,14 @@ PK_API int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_
         memcpy(cls, tmp, sizeof tmp);
         cls_ready.store(1);
     }
+    const bool simd = clean_has_avx512();
     auto count = [&](int t) {
         size_t a, b;
         range(t, a, b);
+        if (simd) {
+            clean_count_avx512(src, a, b, cls, &kept[(size_t)t + 1], &fl[(size_t)t]);
+            return;
+        }
         size_t k = 0;
         uint32_t f = 0;
         for (size_t i = a; i < b; i++) {
@@ -182,6 +246,10 @@ PK_API int pk_fasta_clean(const uint8_t *src, size_t n, uint8_t *dst, size_t *n_
         size_t a, b;
         range(t, a, b);
         uint8_t *o = dst + kept[(size_t)t];
+        if (simd) {
+            clean_compact_avx512(src, a, b, o, dst + kept[(size_t)t + 1]);
+            return;
+        }
         size_t i = a;
         while (i < b) {                                    // copy line by line
             const uint8_t *nl = (const uint8_t *)memchr(src + i, '\n', b - i);

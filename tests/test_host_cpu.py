@@ -406,6 +406,50 @@ def test_merge_tables_streams_slabs_in_order(tmp_path, monkeypatch):
             assert np.array_equal(got, want), (packed, slab)
 
 
+@pytest.mark.parametrize("path", ["auto", "scalar"])
+def test_fasta_clean_simd_and_scalar_agree_with_python(path):
+    """pk_fasta_clean (AVX-512 VBMI2 compress, or the scalar line copier: PYKMER_B200_CLEAN=scalar) against
+    bytes.translate on text with every kind of line end, sizes around the 64-byte blocks and the thread
+    cuts, and the two flags (other white space, non-ASCII)."""
+    code = """
+import ctypes, numpy as np, sys
+sys.path.insert(0, %r)
+from pykmer_b200 import _native as nat
+rng = np.random.default_rng(3)
+def clean(buf, threads):
+    src = np.frombuffer(buf, dtype=np.uint8)
+    dst = np.full(src.size + 80, 0xEE, dtype=np.uint8)
+    kept, flags = ctypes.c_size_t(0), ctypes.c_uint32(0)
+    nat.check(nat.lib.pk_fasta_clean(src.ctypes.data, src.size, dst.ctypes.data, ctypes.byref(kept), ctypes.byref(flags), threads))
+    return dst, kept.value, flags.value
+for n in (0, 1, 63, 64, 65, 127, 128, 1000, 4097, (1 << 20) + 77, (3 << 20) + 5):
+    for style in range(4):
+        body = rng.choice(np.frombuffer(b"ACGTNacgtn", dtype=np.uint8), n).copy()
+        if n:
+            step = (61, 71, 64, 1)[style]
+            body[step - 1::step] = 10                                  # \\n
+            if style == 1: body[step - 2::step] = 13                    # \\r\\n
+            if style == 2 and n > 200: body[100] = 13                   # a lone \\r inside a line
+        buf = body.tobytes()
+        want = buf.translate(None, b"\\r\\n")
+        for threads in (1, 3, 0):
+            dst, kept, flags = clean(buf, threads)
+            assert flags == 0 and kept == len(want) and dst[:kept].tobytes() == want, (n, style, threads)
+            assert (dst[kept:] == 0xEE).all(), (n, style, threads)      # nothing written past the output
+for extra, want_flags in ((b" ", 1), (b"\\t", 1), (b"\\x1c", 1), (b"\\x0b", 1), (b"\\xc3", 2), (b"\\x00", 0), (b"\\x1b", 0)):
+    for pos in (0, 63, 64, 700, 4999):
+        buf = bytearray(b"ACGT" * 1250); buf[pos:pos + 1] = extra
+        dst, kept, flags = clean(bytes(buf), 2)
+        assert flags == want_flags, (extra, pos, flags)
+print("ok")
+""" % ROOT
+    env = dict(os.environ)
+    if path != "auto":
+        env["PYKMER_B200_CLEAN"] = path
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == "ok", res.stdout + res.stderr
+
+
 def _sparse_table(rng, n, fill):
     t = rng.integers(1, 256, n, dtype=np.uint8)
     t[rng.random(n) >= fill] = 0
