@@ -450,6 +450,21 @@ print("ok")
     assert res.returncode == 0 and res.stdout.strip() == "ok", res.stdout + res.stderr
 
 
+def test_packed_table_golden_pins_the_format():
+    """tests/golden/packed_table.npz (oracle/make_golden_packed.py): the library's host unpacker rebuilds the
+    table from the committed packed bytes, and the oracle still packs the table to exactly those bytes."""
+    from pykmer_b200 import device as dev
+    g = np.load(os.path.join(GOLD, "packed_table.npz"))
+    t = g["table"]
+    assert np.array_equal(dev.table_unpack(g["bitmap"], g["chunk_off"], g["nz"], t.size), t)
+    assert np.array_equal(oracle.unpack_table(g["bitmap"], g["chunk_off"], g["nz"], t.size), t)
+    bm, off, nz = oracle.pack_table(t)
+    assert np.array_equal(bm, g["bitmap"]) and np.array_equal(off, g["chunk_off"]) and np.array_equal(nz, g["nz"])
+    off = g["chunk_off"].astype(np.int64)
+    assert off[0] == 0 and off[2] - off[1] == 64 and off[3] == off[2]       # a full chunk: 64 units, an empty one: none
+    assert int(g["bitmap"][16:32].min()) == 2 ** 64 - 1 and int(g["bitmap"][32:48].max()) == 0
+
+
 def _sparse_table(rng, n, fill):
     t = rng.integers(1, 256, n, dtype=np.uint8)
     t[rng.random(n) >= fill] = 0
